@@ -1,0 +1,206 @@
+"""TEST INFRASTRUCTURE -- generates `tests/golden/*.pt` by running the UNMODIFIED reference modules
+(imported from /root/reference through `oracle/ref_shim.py`) on seeded synthetic checkpoints.
+
+    python -m oracle.make_golden            # rewrites tests/golden/
+
+The reference has no golden vectors of its own; these fixtures are what pins the oracle
+(`oracle/vv_oracle.py`) and, through it, the CUDA path.  Only runs in the build container (the GPU box
+has no /root/reference); the fixtures it writes are committed.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import ref_shim  # noqa: E402
+from vibevoice_b200.configuration import preset_config  # noqa: E402
+from vibevoice_b200.synth import SynthTokenizer, synth_state_dict  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+SEED = 1234
+
+
+def _sub(sd, prefix):
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+def _ref_cfg(ns, cfg):
+    """reference VibeVoiceConfig object built from our attribute bag (same JSON schema)."""
+    d = cfg.to_dict()
+    dec = dict(d["decoder_config"]); dec["model_type"] = "qwen2"; dec.pop("_attn_implementation", None)
+    return ns.cfg.VibeVoiceConfig(acoustic_tokenizer_config=d["acoustic_tokenizer_config"],
+                                  semantic_tokenizer_config=d["semantic_tokenizer_config"],
+                                  decoder_config=dec, diffusion_head_config=d["diffusion_head_config"])
+
+
+def gen_scheduler(ns):
+    """Raw scheduler trajectories on a scripted model output (dpm_solver.py:321-423, 935-1022)."""
+    out = {}
+    for n in (5, 10, 20, 30):
+        s = ns.dpm.DPMSolverMultistepScheduler(num_train_timesteps=1000, beta_schedule="cosine",
+                                               prediction_type="v_prediction")
+        s.set_timesteps(n)
+        g = torch.Generator().manual_seed(100 + n)
+        z = torch.randn(3, 64, generator=g)
+        vs = torch.randn(n, 3, 64, generator=g)
+        traj = []
+        zz = z.clone()
+        for i, t in enumerate(s.timesteps):
+            zz = s.step(vs[i], t, zz).prev_sample
+            traj.append(zz.clone())
+        out[n] = dict(timesteps=s.timesteps.clone(), sigmas=s.sigmas.clone(), z0=z, vs=vs, traj=torch.stack(traj))
+    return out
+
+
+def gen_head(ns, preset="tiny"):
+    cfg = preset_config(preset)
+    rc = _ref_cfg(ns, cfg)
+    sd = synth_state_dict(cfg, SEED, torch.float32, parts=("head",))
+    head = ns.head.VibeVoiceDiffusionHead(rc.diffusion_head_config).eval()
+    missing = head.load_state_dict(_sub(sd, "model.prediction_head."), strict=True)
+    g = torch.Generator().manual_seed(7)
+    H = cfg.decoder_config.hidden_size
+    noisy, cond = torch.randn(6, 64, generator=g), torch.randn(6, H, generator=g)
+    t = torch.tensor([999.0, 500.0, 33.0, 999.0, 500.0, 33.0])
+    with torch.no_grad():
+        y = head(noisy, t, condition=cond)
+    # full CFG sampler through the reference's own method with a stand-in `self`
+    infer = sys.modules["vibevoice.modular.modeling_vibevoice_inference"].VibeVoiceForConditionalGenerationInference
+    samples = {}
+    for n_steps, cfg_scale in ((5, 1.5), (10, 1.3), (30, 1.3)):
+        sched = ns.dpm.DPMSolverMultistepScheduler(num_train_timesteps=1000, beta_schedule="cosine",
+                                                   prediction_type="v_prediction")
+        head.device  # noqa  (PreTrainedModel property used by :700)
+        fake = types.SimpleNamespace(model=types.SimpleNamespace(noise_scheduler=sched, prediction_head=head),
+                                     ddpm_inference_steps=n_steps, config=types.SimpleNamespace(acoustic_vae_dim=64))
+        pos, neg = torch.randn(2, H, generator=g), torch.randn(2, H, generator=g)
+        torch.manual_seed(11 + n_steps)
+        noise = torch.randn(4, 64)
+        torch.manual_seed(11 + n_steps)
+        lat = infer.sample_speech_tokens(fake, pos, neg, cfg_scale=cfg_scale)
+        samples[n_steps] = dict(pos=pos, neg=neg, cfg_scale=cfg_scale, noise=noise, latent=lat.clone())
+    return dict(preset=preset, noisy=noisy, cond=cond, t=t, y=y, samples=samples)
+
+
+def _tokenizer_models(ns, cfg):
+    rc = _ref_cfg(ns, cfg)
+    sd = synth_state_dict(cfg, SEED, torch.float32, parts=("acoustic_decoder", "acoustic_encoder", "semantic"))
+    ac = ns.tok.VibeVoiceAcousticTokenizerModel(rc.acoustic_tokenizer_config).eval()
+    ac.load_state_dict(_sub(sd, "model.acoustic_tokenizer."), strict=True)
+    se = ns.tok.VibeVoiceSemanticTokenizerModel(rc.semantic_tokenizer_config).eval()
+    se.load_state_dict(_sub(sd, "model.semantic_tokenizer."), strict=True)
+    return ac, se
+
+
+def gen_codec(ns, preset="tiny"):
+    """Streaming decode/encode over several frames, ragged row subsets, and a `set_to_zero` (speech_end)."""
+    cfg = preset_config(preset)
+    ac, se = _tokenizer_models(ns, cfg)
+    g = torch.Generator().manual_seed(21)
+    n_rows = 3
+    script = [[0, 1, 2], [0, 2], [0, 1, 2], [1], [0, 1, 2], [0, 1, 2]]   # rows decoding at each frame
+    zero_before = {4: [0]}                                              # speech_end for row 0 before frame 4
+    a_cache, s_cache = ns.tok.VibeVoiceTokenizerStreamingCache(), ns.tok.VibeVoiceTokenizerStreamingCache()
+    frames = []
+    with torch.no_grad():
+        for f, rows in enumerate(script):
+            if f in zero_before:
+                zr = torch.tensor(zero_before[f])
+                a_cache.set_to_zero(zr); s_cache.set_to_zero(zr)
+            lat = torch.randn(len(rows), 1, 64, generator=g)
+            idx = torch.tensor(rows)
+            audio = ac.decode(lat, cache=a_cache, sample_indices=idx, use_cache=True)
+            sem = se.encode(audio, cache=s_cache, sample_indices=idx, use_cache=True).mean
+            frames.append(dict(rows=rows, latent=lat, audio=audio.clone(), semantic=sem.clone()))
+        # non-streaming equivalents for one row (also what voice-prompt prefill uses for the encoder)
+        wav = torch.randn(2, 1, 3200 * 3 + 777, generator=g) * 0.1
+        enc_mean = ac.encode(wav).mean
+        sem_full = se.encode(wav).mean
+    return dict(preset=preset, n_rows=n_rows, zero_before=zero_before, frames=frames, wav=wav,
+                acoustic_encode_mean=enc_mean, semantic_encode_full=sem_full)
+
+
+def gen_connector(ns, preset="tiny"):
+    cfg = preset_config(preset)
+    sd = synth_state_dict(cfg, SEED, torch.float32, parts=("connectors",))
+    H = cfg.decoder_config.hidden_size
+    g = torch.Generator().manual_seed(31)
+    out = {}
+    for name, din in (("acoustic", 64), ("semantic", 128)):
+        m = ns.modeling.SpeechConnector(din, H).eval()
+        m.load_state_dict(_sub(sd, f"model.{name}_connector."), strict=True)
+        x = torch.randn(3, 1, din, generator=g)
+        with torch.no_grad():
+            out[name] = dict(x=x, y=m(x))
+    return dict(preset=preset, **out)
+
+
+def build_ref_model(ns, cfg, dtype=torch.float32):
+    """Full reference inference model with synthetic weights (used by the loop fixture)."""
+    infer_mod = sys.modules["vibevoice.modular.modeling_vibevoice_inference"]
+    rc = _ref_cfg(ns, cfg)
+    rc.decoder_config._attn_implementation = "sdpa"
+    model = infer_mod.VibeVoiceForConditionalGenerationInference(rc)
+    sd = synth_state_dict(cfg, SEED, torch.float32)
+    sd = {k: v for k, v in sd.items()}
+    if cfg.decoder_config.tie_word_embeddings:
+        sd["lm_head.weight"] = sd["model.language_model.embed_tokens.weight"]
+    res = model.load_state_dict(sd, strict=False)
+    bad = [k for k in res.missing_keys if "fix_std" not in k and "rotary" not in k]
+    assert not bad and not res.unexpected_keys, (bad, res.unexpected_keys)
+    return model.eval()
+
+
+def gen_lm(ns, preset="tiny"):
+    """Installed transformers Qwen2Model (the third-party arithmetic the reference calls at
+    modeling_vibevoice.py:121): prefill + single-token decode steps."""
+    from transformers import Qwen2Config, Qwen2Model
+    cfg = preset_config(preset)
+    dc = cfg.decoder_config
+    qc = Qwen2Config(hidden_size=dc.hidden_size, intermediate_size=dc.intermediate_size,
+                     num_hidden_layers=dc.num_hidden_layers, num_attention_heads=dc.num_attention_heads,
+                     num_key_value_heads=dc.num_key_value_heads, head_dim=dc.head_dim,
+                     max_position_embeddings=dc.max_position_embeddings, rms_norm_eps=dc.rms_norm_eps,
+                     rope_theta=dc.rope_theta, vocab_size=dc.vocab_size, tie_word_embeddings=True,
+                     attn_implementation="eager")
+    m = Qwen2Model(qc).eval()
+    sd = synth_state_dict(cfg, SEED, torch.float32, parts=("lm",))
+    res = m.load_state_dict(_sub(sd, "model.language_model."), strict=False)
+    assert not [k for k in res.missing_keys if "rotary" not in k] and not res.unexpected_keys, res
+    g = torch.Generator().manual_seed(41)
+    ids = torch.randint(0, dc.vocab_size - 20, (1, 9), generator=g)
+    steps = torch.randn(3, 1, 1, dc.hidden_size, generator=g) * 0.05
+    with torch.no_grad():
+        o = m(input_ids=ids, use_cache=True)
+        hs = [o.last_hidden_state[0].clone()]
+        pkv = o.past_key_values
+        for e in steps:
+            o = m(inputs_embeds=e, past_key_values=pkv, use_cache=True)
+            pkv = o.past_key_values
+            hs.append(o.last_hidden_state[0].clone())
+    return dict(preset=preset, ids=ids, step_embeds=steps, hidden=hs)
+
+
+GENERATORS = dict(scheduler=gen_scheduler, head=gen_head, codec=gen_codec, connector=gen_connector, lm=gen_lm)
+
+
+def main():
+    ns = ref_shim.load_reference()
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for name, fn in GENERATORS.items():
+        torch.manual_seed(0)
+        data = fn(ns)
+        path = os.path.join(GOLDEN_DIR, f"{name}.pt")
+        torch.save(data, path)
+        print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,90 @@
+"""The oracle (oracle/vv_oracle.py) against golden vectors produced by the reference's own modules
+(oracle/make_golden.py).  CPU only; this is what pins the checker every CUDA parity test relies on."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vv_oracle as O
+from vibevoice_b200.configuration import preset_config
+from vibevoice_b200.synth import synth_state_dict
+
+SEED = 1234
+
+
+def close(a, b, rtol=1e-5, atol=1e-6):
+    torch.testing.assert_close(a.float(), b.float(), rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize("n", [5, 10, 20, 30])
+def test_dpm_tables_match_reference_scheduler(golden, n):
+    g = golden("scheduler")[n]
+    tab = O.dpm_tables(n)
+    assert np.array_equal(tab.timesteps, g["timesteps"].numpy())          # integer bookkeeping: bit-exact
+    assert np.array_equal(tab.sigmas, g["sigmas"].numpy())                 # fp32 table: bit-exact
+    assert tab.order[0] == 1 and tab.order[-1] == 1 and (tab.order[1:-1] == 2).all()
+    z, x0p = g["z0"].clone(), None
+    for i in range(n):
+        z, x0p = O.dpm_step(tab, i, g["vs"][i], z, x0p)
+        close(z, g["traj"][i], rtol=0, atol=0)                             # scalar-table form is bit-exact in fp32
+
+
+def test_known_timesteps():
+    # N=10 -> 999,899,...,100 ; N=30 -> 999,966,932,...,33
+    assert O.dpm_tables(10).timesteps.tolist() == [999, 899, 799, 699, 599, 500, 400, 300, 200, 100]
+    t30 = O.dpm_tables(30).timesteps
+    assert t30[0] == 999 and t30[1] == 966 and t30[2] == 932 and t30[-1] == 33
+    assert abs(O.dpm_tables(10).sigmas[0] - 20291.3) < 1.0 and O.dpm_tables(10).sigmas[-1] == 0.0
+
+
+def test_head_forward_and_sampler(golden):
+    g = golden("head")
+    cfg = preset_config(g["preset"])
+    w = synth_state_dict(cfg, SEED, torch.float32, parts=("head",))
+    y = O.head_forward(w, g["noisy"], g["t"], g["cond"])
+    close(y, g["y"], rtol=1e-5, atol=1e-6)
+    for n_steps, s in g["samples"].items():
+        lat = O.sample_speech_tokens(w, s["pos"], s["neg"], s["cfg_scale"], n_steps, s["noise"])
+        close(lat, s["latent"], rtol=1e-4, atol=2e-5)
+
+
+def test_streaming_codec(golden):
+    g = golden("codec")
+    cfg = preset_config(g["preset"])
+    w = synth_state_dict(cfg, SEED, torch.float32, parts=("acoustic_decoder", "acoustic_encoder", "semantic"))
+    a, s = O.StreamState(g["n_rows"]), O.StreamState(g["n_rows"])
+    for f, fr in enumerate(g["frames"]):
+        if f in g["zero_before"]:
+            a.set_to_zero(g["zero_before"][f]); s.set_to_zero(g["zero_before"][f])
+        audio = O.decoder_frame(w, cfg.acoustic_tokenizer_config, fr["latent"], a, fr["rows"])
+        assert audio.shape == (len(fr["rows"]), 1, 3200)
+        close(audio, fr["audio"], rtol=1e-4, atol=1e-5)
+        sem = O.encoder_frame(w, cfg.semantic_tokenizer_config, fr["audio"], s, fr["rows"])
+        assert sem.shape == (len(fr["rows"]), 1, 128)
+        close(sem, fr["semantic"], rtol=1e-4, atol=1e-5)
+    enc = O.encoder_full(w, cfg.acoustic_tokenizer_config, g["wav"], "model.acoustic_tokenizer.encoder")
+    close(enc, g["acoustic_encode_mean"], rtol=1e-4, atol=1e-5)
+    sem = O.encoder_full(w, cfg.semantic_tokenizer_config, g["wav"], "model.semantic_tokenizer.encoder")
+    close(sem, g["semantic_encode_full"], rtol=1e-4, atol=1e-5)
+
+
+def test_connectors(golden):
+    g = golden("connector")
+    cfg = preset_config(g["preset"])
+    w = synth_state_dict(cfg, SEED, torch.float32, parts=("connectors",))
+    for name in ("acoustic", "semantic"):
+        close(O.connector(w, f"model.{name}_connector", g[name]["x"]), g[name]["y"], rtol=1e-5, atol=1e-6)
+
+
+def test_qwen2_prefill_and_decode(golden):
+    g = golden("lm")
+    cfg = preset_config(g["preset"])
+    dc = cfg.decoder_config
+    w = synth_state_dict(cfg, SEED, torch.float32, parts=("lm",))
+    cache = O.KVCache(dc.num_hidden_layers)
+    e = w["model.language_model.embed_tokens.weight"][g["ids"][0]]
+    hs = O.qwen2_forward(w, dc, e, cache, 0)
+    close(hs, g["hidden"][0], rtol=1e-4, atol=1e-5)
+    for i, emb in enumerate(g["step_embeds"]):
+        hs = O.qwen2_forward(w, dc, emb[0], cache, len(cache))
+        close(hs, g["hidden"][i + 1], rtol=1e-4, atol=1e-5)
+    assert len(cache) == g["ids"].shape[1] + len(g["step_embeds"])
