@@ -1,0 +1,1211 @@
+// vv_runtime.cu -- native runtime behind include/vibevoice_b200.h: weight registry + repacker,
+// paged KV allocator, streaming-codec state slab, per-frame kernel programs (CUDA-graph cached).
+//
+// The reference owns none of this (it is eager PyTorch + HF DynamicCache + python dict caches:
+// modeling_vibevoice_inference.py:367-695, modular_vibevoice_tokenizer.py:193-256); SURVEY 8b
+// sketches the C ABI this file implements.
+#include "../../include/vibevoice_b200.h"
+#include "vv_kernels.cuh"
+
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+using namespace vv;
+
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[2048];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CK(expr)                                                                                     \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) return fail(VV_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+  } while (0)
+#define CKL() CK(cudaGetLastError())
+#define RET(expr)            \
+  do {                       \
+    int _r = (expr);         \
+    if (_r < 0) return _r;   \
+  } while (0)
+
+struct RawTensor {
+  void* p = nullptr;
+  std::vector<int64_t> shape;
+  bool is_f32 = false;
+  size_t numel = 0;
+};
+
+struct Block {            // Block1D (tokenizer.py:620-684)
+  int C = 0;
+  float *norm_w = nullptr, *dw_w = nullptr, *dw_b = nullptr, *gamma = nullptr, *ffn_norm_w = nullptr, *b1 = nullptr, *b2 = nullptr,
+        *ffn_gamma = nullptr;
+  bf16 *w1 = nullptr, *w2 = nullptr;
+  float *hist = nullptr, *next = nullptr;   // [B][6][C]
+};
+struct ConvL {             // stem / downsample / upsample / head conv in window-GEMV form
+  int Cin = 0, Cout = 0, k = 0, stride = 1, ctx = 0, N = 0, K = 0;
+  bf16* w = nullptr; float* wf = nullptr; float* bias = nullptr;
+  float *hist = nullptr, *next = nullptr;   // [B][ctx][Cin]
+};
+struct Codec {
+  std::vector<ConvL> convs;                  // index i = layer before stage i ; last = head
+  std::vector<std::vector<Block>> stages;
+  std::vector<int> T;                        // frames per stage (per 1 latent frame)
+  std::vector<int> C;
+  StateSeg* segs_dev = nullptr; int n_segs = 0;
+  int64_t weight_bytes = 0;
+};
+struct LmLayer { bf16 *wqkv, *wo, *wgu, *wdown; float *bqkv, *ln1, *ln2; };
+struct HeadLayer { bf16 *wgu, *wdown; float* norm; };
+
+struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
+
+struct vv_ctx {
+  vv_model_desc d;
+  int device = 0;
+  bool finalized = false;
+  bool use_graphs = true;
+  int sm_count = 148;
+  std::map<std::string, RawTensor> raw;
+  std::set<std::string> expected;
+  std::vector<void*> allocs;
+  float speech_scale = NAN, speech_bias = NAN;
+  // LM
+  std::vector<LmLayer> lm;
+  float* lm_norm = nullptr; bf16* embed = nullptr; bf16* head_valid = nullptr; int* valid_ids_dev = nullptr; float* inv_freq = nullptr;
+  int Nqkv = 0;
+  // head
+  bf16 *h_noisy = nullptr, *h_cond = nullptr, *h_t0 = nullptr, *h_t2 = nullptr, *h_mod = nullptr, *h_final = nullptr;
+  std::vector<HeadLayer> head;
+  int n_steps = 0; float* temb = nullptr; DpmCoef* coef_dev = nullptr; float* tfreqs = nullptr;
+  // connectors
+  bf16 *ca_fc1 = nullptr, *ca_fc2 = nullptr, *cs_fc1 = nullptr, *cs_fc2 = nullptr;
+  float *ca_b1 = nullptr, *ca_b2 = nullptr, *ca_n = nullptr, *cs_b1 = nullptr, *cs_b2 = nullptr, *cs_n = nullptr;
+  Codec dec, enc;
+  int64_t wbytes[6] = {0, 0, 0, 0, 0, 0};
+  // KV
+  int64_t n_pages = 0; int max_pages = 0; bf16 *kpool = nullptr, *vpool = nullptr;
+  int* page_table_dev = nullptr; int* page_table_host = nullptr; int* kv_len_dev = nullptr; int* row_mode_dev = nullptr;
+  std::vector<int64_t> kv_len_host; std::vector<std::vector<int>> seq_pages; std::vector<int> free_pages;
+  // scratch
+  float *s_h = nullptr, *s_qkv = nullptr, *s_qrot = nullptr, *s_attn = nullptr, *s_act = nullptr, *s_pacc = nullptr, *s_pml = nullptr;
+  int nsplit = 128;
+  float *s_condp = nullptr, *s_call = nullptr, *s_mod = nullptr, *s_hx = nullptr, *s_hg = nullptr, *s_v = nullptr, *s_z = nullptr,
+        *s_x0 = nullptr, *s_tfeat = nullptr, *s_t1 = nullptr;
+  float *s_xa = nullptr, *s_xb = nullptr, *s_u = nullptr, *s_win = nullptr, *s_xn = nullptr;
+  float *s_e = nullptr, *s_c1 = nullptr, *s_feat = nullptr, *s_audio = nullptr, *s_latent = nullptr;
+  int* s_tok = nullptr;
+  std::map<std::string, GraphEntry> graphs;
+  int64_t launches = 0;
+  std::map<long long, int> occ_cache;
+};
+
+struct L {  // launcher
+  vv_ctx* c; cudaStream_t s;
+};
+
+// ------------------------------------------------------------------------------------------------
+template <class T>
+static int dmalloc(vv_ctx* c, T** p, size_t n, bool zero = true) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) return fail(VV_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
+  if (zero) cudaMemset(q, 0, std::max<size_t>(n, 1) * sizeof(T));
+  c->allocs.push_back(q);
+  *p = (T*)q;
+  return 0;
+}
+
+static int gemv_smem_bytes(int MB, int K) { int Kp = (K + 255) & ~255; return (MB * Kp + 2 * 8 * 4 * MB) * 4; }
+
+template <int MB>
+static int launch_gemv_t(const L& l, GemvP& p, int grid, int smem) {
+  static bool attr_set[8] = {false, false, false, false, false, false, false, false};
+  (void)attr_set;
+  CK(cudaFuncSetAttribute(gemv_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  gemv_kernel<MB><<<grid, 256, smem, l.s>>>(p);
+  CKL();
+  l.c->launches++;
+  return 0;
+}
+
+template <int MB>
+static int gemv_occupancy(vv_ctx* c, int smem) {
+  long long key = ((long long)MB << 32) | (unsigned)smem;
+  auto it = c->occ_cache.find(key);
+  if (it != c->occ_cache.end()) return it->second;
+  int occ = 1;
+  cudaFuncSetAttribute(gemv_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gemv_kernel<MB>, 256, smem) != cudaSuccess || occ < 1) occ = 1;
+  c->occ_cache[key] = occ;
+  return occ;
+}
+
+// y = epi(W * pro(x) + bias); dispatches GEMV (M <= 16) or the tiled GEMM.
+static int linear(const L& l, GemvP p) {
+  if (p.K % 8 != 0) return fail(VV_ERR_INVALID, "linear: K=%d not a multiple of 8", p.K);
+  if (p.M > 16) {
+    if (p.pro != PRO_NONE || p.epi == EPI_SWIGLU) return fail(VV_ERR_INVALID, "gemm_tiled: prologue/swiglu unsupported");
+    dim3 grid((p.N + 63) / 64, (p.M + 63) / 64);
+    gemm_tiled_kernel<<<grid, 256, 0, l.s>>>(p);
+    CKL();
+    l.c->launches++;
+    return 0;
+  }
+  int MB = p.M <= 1 ? 1 : (p.M <= 2 ? 2 : (p.M <= 4 ? 4 : 8));
+  while (MB > 1 && gemv_smem_bytes(MB, p.K) > 200 * 1024) MB >>= 1;
+  if (gemv_smem_bytes(MB, p.K) > 200 * 1024) return fail(VV_ERR_INVALID, "gemv: K=%d too large", p.K);
+  int WR = 8;
+  while (WR > 1 && (p.N + 4 * WR - 1) / (4 * WR) < 2 * l.c->sm_count) WR >>= 1;
+  p.WK = 8 / WR;
+  const int ntasks = (p.N + 4 * WR - 1) / (4 * WR);
+  const int smem = gemv_smem_bytes(MB, p.K);
+  int occ = MB == 1 ? gemv_occupancy<1>(l.c, smem) : MB == 2 ? gemv_occupancy<2>(l.c, smem) : MB == 4 ? gemv_occupancy<4>(l.c, smem)
+                                                                                                          : gemv_occupancy<8>(l.c, smem);
+  int grid = std::min(ntasks, l.c->sm_count * occ);
+  switch (MB) {
+    case 1: return launch_gemv_t<1>(l, p, grid, smem);
+    case 2: return launch_gemv_t<2>(l, p, grid, smem);
+    case 4: return launch_gemv_t<4>(l, p, grid, smem);
+    default: return launch_gemv_t<8>(l, p, grid, smem);
+  }
+}
+
+static GemvP mk(const bf16* W, const float* bias, const float* x, long long ldx, float* y, int ldy, int M, int N, int K) {
+  GemvP p;
+  memset(&p, 0, sizeof p);
+  p.W = W; p.bias = bias; p.x = x; p.xmap = dense_rows(ldx); p.y = y; p.ldy = ldy; p.M = M; p.N = N; p.K = K;
+  p.pro = PRO_NONE; p.epi = EPI_NONE; p.WK = 1;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// expected tensor names (same as vibevoice_b200/synth.py::param_specs, i.e. the HF checkpoint keys)
+// ------------------------------------------------------------------------------------------------
+static std::string S(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  return buf;
+}
+static void block_names(std::set<std::string>& e, const std::string& p) {
+  for (const char* s : {"norm.weight", "mixer.conv.conv.conv.weight", "mixer.conv.conv.conv.bias", "gamma", "ffn_norm.weight",
+                        "ffn.linear1.weight", "ffn.linear1.bias", "ffn.linear2.weight", "ffn.linear2.bias", "ffn_gamma"})
+    e.insert(p + "." + s);
+}
+static void build_expected(vv_ctx* c) {
+  auto& e = c->expected;
+  const auto& d = c->d;
+  const std::string lm = "model.language_model";
+  e.insert(lm + ".embed_tokens.weight");
+  e.insert(lm + ".norm.weight");
+  for (int l = 0; l < d.num_layers; ++l) {
+    std::string q = S("%s.layers.%d", lm.c_str(), l);
+    for (const char* s : {"self_attn.q_proj.weight", "self_attn.q_proj.bias", "self_attn.k_proj.weight", "self_attn.k_proj.bias",
+                          "self_attn.v_proj.weight", "self_attn.v_proj.bias", "self_attn.o_proj.weight", "mlp.gate_proj.weight",
+                          "mlp.up_proj.weight", "mlp.down_proj.weight", "input_layernorm.weight", "post_attention_layernorm.weight"})
+      e.insert(q + "." + s);
+  }
+  if (!d.tie_word_embeddings) e.insert("lm_head.weight");
+  const std::string h = "model.prediction_head";
+  for (const char* s : {"noisy_images_proj.weight", "cond_proj.weight", "t_embedder.mlp.0.weight", "t_embedder.mlp.2.weight",
+                        "final_layer.linear.weight", "final_layer.adaLN_modulation.1.weight"})
+    e.insert(h + "." + s);
+  for (int l = 0; l < d.head_layers; ++l)
+    for (const char* s : {"ffn.gate_proj.weight", "ffn.up_proj.weight", "ffn.down_proj.weight", "norm.weight", "adaLN_modulation.1.weight"})
+      e.insert(S("%s.layers.%d.%s", h.c_str(), l, s));
+  for (const char* cn : {"model.acoustic_connector", "model.semantic_connector"})
+    for (const char* s : {"fc1.weight", "fc1.bias", "norm.weight", "fc2.weight", "fc2.bias"}) e.insert(std::string(cn) + "." + s);
+  const std::string dp = "model.acoustic_tokenizer.decoder", ep = "model.semantic_tokenizer.encoder";
+  for (int i = 0; i < d.n_stages; ++i) {
+    if (i == 0) { e.insert(dp + ".upsample_layers.0.0.conv.conv.weight"); e.insert(dp + ".upsample_layers.0.0.conv.conv.bias"); }
+    else { e.insert(S("%s.upsample_layers.%d.0.convtr.convtr.weight", dp.c_str(), i)); e.insert(S("%s.upsample_layers.%d.0.convtr.convtr.bias", dp.c_str(), i)); }
+    for (int j = 0; j < d.dec_depths[i]; ++j) block_names(e, S("%s.stages.%d.%d", dp.c_str(), i, j));
+    e.insert(S("%s.downsample_layers.%d.0.conv.conv.weight", ep.c_str(), i));
+    e.insert(S("%s.downsample_layers.%d.0.conv.conv.bias", ep.c_str(), i));
+    for (int j = 0; j < d.enc_depths[i]; ++j) block_names(e, S("%s.stages.%d.%d", ep.c_str(), i, j));
+  }
+  for (const char* s : {"head.conv.conv.weight", "head.conv.conv.bias"}) { e.insert(dp + "." + s); e.insert(ep + "." + s); }
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int vv_abi_version(void) { return VV_ABI_VERSION; }
+extern "C" const char* vv_last_error(void) { return g_err.c_str(); }
+
+extern "C" int vv_create(const vv_model_desc* desc, int device, vv_ctx** out) {
+  if (!desc || !out) return fail(VV_ERR_INVALID, "vv_create: null argument");
+  if (desc->head_dim != HD) return fail(VV_ERR_INVALID, "head_dim %d unsupported (kernels are specialised for 128)", desc->head_dim);
+  if (desc->max_batch < 1 || desc->max_batch > 8) return fail(VV_ERR_INVALID, "max_batch must be in [1,8]");
+  if (desc->n_stages < 2 || desc->n_stages > 8) return fail(VV_ERR_INVALID, "n_stages out of range");
+  if (desc->num_q_heads % desc->num_kv_heads || desc->num_q_heads / desc->num_kv_heads > ATT_MAXG)
+    return fail(VV_ERR_INVALID, "GQA group size unsupported");
+  if (desc->latent_size != 64 || desc->acoustic_vae_dim != 64) return fail(VV_ERR_INVALID, "latent size must be 64");
+  if (desc->n_valid_ids < 1 || desc->n_valid_ids > 8) return fail(VV_ERR_INVALID, "n_valid_ids out of range");
+  CK(cudaSetDevice(device));
+  vv_ctx* c = new vv_ctx();
+  c->d = *desc;
+  c->device = device;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  const char* ng = getenv("VV_NO_GRAPH");
+  c->use_graphs = !(ng && ng[0] == '1');
+  build_expected(c);
+  *out = c;
+  return 0;
+}
+
+extern "C" void vv_destroy(vv_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& g : c->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+  for (auto& r : c->raw) if (r.second.p) cudaFree(r.second.p);
+  for (void* p : c->allocs) cudaFree(p);
+  if (c->page_table_host) cudaFreeHost(c->page_table_host);
+  delete c;
+}
+
+static bool stored_as_f32(const std::string& name, const int64_t* shape, int ndim) {
+  if (ndim <= 1) return true;
+  if (name.find("mixer.conv.conv.conv.weight") != std::string::npos) return true;                 // depthwise [C,1,7]
+  if (ndim == 3 && (shape[0] == 1 || shape[1] == 1)) return true;                                  // 1->32 stem, 32->1 head
+  return false;
+}
+
+extern "C" int vv_load_tensor(vv_ctx* c, const char* name_, const void* data, int dtype, const int64_t* shape, int ndim) {
+  if (!c || !name_ || !data) return fail(VV_ERR_INVALID, "vv_load_tensor: null argument");
+  if (c->finalized) return fail(VV_ERR_STATE, "vv_load_tensor after vv_finalize_weights");
+  std::string name(name_);
+  CK(cudaSetDevice(c->device));
+  if (name == "model.speech_scaling_factor" || name == "model.speech_bias_factor") {
+    float v; char tmp[4];
+    CK(cudaMemcpy(tmp, data, dtype == VV_DT_F32 ? 4 : 2, cudaMemcpyDefault));
+    if (dtype == VV_DT_F32) memcpy(&v, tmp, 4);
+    else if (dtype == VV_DT_BF16) { unsigned u = ((unsigned)(*(unsigned short*)tmp)) << 16; memcpy(&v, &u, 4); }
+    else v = __half2float(*(__half*)tmp);
+    (name == "model.speech_scaling_factor" ? c->speech_scale : c->speech_bias) = v;
+    return 0;
+  }
+  if (!c->expected.count(name)) {
+    if (name.rfind("model.acoustic_tokenizer.encoder.", 0) == 0 || name.find("fix_std") != std::string::npos ||
+        name.find("rotary_emb") != std::string::npos || (name == "lm_head.weight" && c->d.tie_word_embeddings))
+      return 1;   // not on this path
+    return fail(VV_ERR_INVALID, "vv_load_tensor: unknown tensor '%s'", name.c_str());
+  }
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= (size_t)shape[i];
+  RawTensor t;
+  t.shape.assign(shape, shape + ndim);
+  t.numel = n;
+  t.is_f32 = stored_as_f32(name, shape, ndim);
+  const size_t esz = dtype == VV_DT_F32 ? 4 : 2;
+  void* dst = nullptr;
+  CK(cudaMalloc(&dst, n * (t.is_f32 ? 4 : 2)));
+  t.p = dst;
+  const bool same = (t.is_f32 && dtype == VV_DT_F32) || (!t.is_f32 && dtype == VV_DT_BF16);
+  if (same) {
+    CK(cudaMemcpy(dst, data, n * esz, cudaMemcpyDefault));
+  } else {
+    void* tmp = nullptr;
+    CK(cudaMalloc(&tmp, n * esz));
+    CK(cudaMemcpy(tmp, data, n * esz, cudaMemcpyDefault));
+    const int grid = (int)std::min<size_t>((n + 255) / 256, 65535);
+    if (t.is_f32 && dtype == VV_DT_BF16) cvt_bf16_to_f32_kernel<<<grid, 256>>>((const bf16*)tmp, (float*)dst, n);
+    else if (t.is_f32 && dtype == VV_DT_F16) cvt_f16_to_f32_kernel<<<grid, 256>>>((const __half*)tmp, (float*)dst, n);
+    else if (!t.is_f32 && dtype == VV_DT_F32) cvt_f32_to_bf16_kernel<<<grid, 256>>>((const float*)tmp, (bf16*)dst, n);
+    else cvt_f16_to_bf16_kernel<<<grid, 256>>>((const __half*)tmp, (bf16*)dst, n);
+    CKL();
+    CK(cudaDeviceSynchronize());
+    cudaFree(tmp);
+  }
+  auto it = c->raw.find(name);
+  if (it != c->raw.end() && it->second.p) cudaFree(it->second.p);
+  c->raw[name] = t;
+  return 0;
+}
+
+extern "C" int vv_set_speech_factors(vv_ctx* c, float s, float b) {
+  if (!c) return fail(VV_ERR_INVALID, "null ctx");
+  c->speech_scale = s; c->speech_bias = b;
+  return 0;
+}
+
+// ---- repack helpers ------------------------------------------------------------------------------
+static int need(vv_ctx* c, const std::string& name, RawTensor** t, std::vector<int64_t> shape) {
+  auto it = c->raw.find(name);
+  if (it == c->raw.end()) return fail(VV_ERR_STATE, "missing tensor %s", name.c_str());
+  if (it->second.shape != shape) {
+    std::string a, b;
+    for (auto v : it->second.shape) a += std::to_string(v) + ",";
+    for (auto v : shape) b += std::to_string(v) + ",";
+    return fail(VV_ERR_INVALID, "tensor %s has shape [%s] expected [%s]", name.c_str(), a.c_str(), b.c_str());
+  }
+  *t = &it->second;
+  return 0;
+}
+static int take_bf16(vv_ctx* c, const std::string& name, std::vector<int64_t> shape, bf16** out, int64_t* bytes) {
+  RawTensor* t;
+  RET(need(c, name, &t, shape));
+  if (t->is_f32) return fail(VV_ERR_INVALID, "%s stored as f32, expected bf16", name.c_str());
+  *out = (bf16*)t->p;
+  c->allocs.push_back(t->p);
+  t->p = nullptr;
+  if (bytes) *bytes += (int64_t)t->numel * 2;
+  return 0;
+}
+static int take_f32(vv_ctx* c, const std::string& name, std::vector<int64_t> shape, float** out, int64_t* bytes) {
+  RawTensor* t;
+  RET(need(c, name, &t, shape));
+  if (!t->is_f32) return fail(VV_ERR_INVALID, "%s stored as bf16, expected f32", name.c_str());
+  *out = (float*)t->p;
+  c->allocs.push_back(t->p);
+  t->p = nullptr;
+  if (bytes) *bytes += (int64_t)t->numel * 2;   // algorithmic bytes are quoted at bf16
+  return 0;
+}
+static void drop(vv_ctx* c, const std::string& name) {
+  auto it = c->raw.find(name);
+  if (it != c->raw.end() && it->second.p) { cudaFree(it->second.p); it->second.p = nullptr; }
+}
+
+static int build_block(vv_ctx* c, const std::string& p, int C, Block* b, int64_t* bytes, std::vector<StateSeg>* segs) {
+  b->C = C;
+  RET(take_f32(c, p + ".norm.weight", {C}, &b->norm_w, bytes));
+  RawTensor* t;
+  RET(need(c, p + ".mixer.conv.conv.conv.weight", &t, {C, 1, 7}));
+  RET(dmalloc(c, &b->dw_w, (size_t)7 * C));
+  repack_dw_kernel<<<(C * 7 + 255) / 256, 256>>>((const float*)t->p, b->dw_w, C);
+  CKL();
+  *bytes += (int64_t)C * 7 * 2;
+  RET(take_f32(c, p + ".mixer.conv.conv.conv.bias", {C}, &b->dw_b, bytes));
+  RET(take_f32(c, p + ".gamma", {C}, &b->gamma, bytes));
+  RET(take_f32(c, p + ".ffn_norm.weight", {C}, &b->ffn_norm_w, bytes));
+  RET(take_bf16(c, p + ".ffn.linear1.weight", {4 * C, C}, &b->w1, bytes));
+  RET(take_f32(c, p + ".ffn.linear1.bias", {4 * C}, &b->b1, bytes));
+  RET(take_bf16(c, p + ".ffn.linear2.weight", {C, 4 * C}, &b->w2, bytes));
+  RET(take_f32(c, p + ".ffn.linear2.bias", {C}, &b->b2, bytes));
+  RET(take_f32(c, p + ".ffn_gamma", {C}, &b->ffn_gamma, bytes));
+  const int B = c->d.max_batch;
+  RET(dmalloc(c, &b->hist, (size_t)B * 6 * C));
+  RET(dmalloc(c, &b->next, (size_t)B * 6 * C));
+  segs->push_back({b->hist, b->next, 6 * C});
+  return 0;
+}
+
+// Conv1d [Co][Ci][k] -> window GEMV weight [Co][k*Ci]
+static int build_conv(vv_ctx* c, const std::string& p, int Ci, int Co, int k, int stride, ConvL* L_, int64_t* bytes,
+                      std::vector<StateSeg>* segs) {
+  L_->Cin = Ci; L_->Cout = Co; L_->k = k; L_->stride = stride; L_->ctx = (k - 1) - (stride - 1); L_->N = Co; L_->K = k * Ci;
+  RawTensor* t;
+  RET(need(c, p + ".weight", &t, {Co, Ci, k}));
+  const size_t n = (size_t)Co * Ci * k;
+  if (t->is_f32) {
+    RET(dmalloc(c, &L_->wf, n));
+    repack_conv_f32_kernel<<<(int)((n + 255) / 256), 256>>>((const float*)t->p, L_->wf, Co, Ci, k);
+  } else {
+    RET(dmalloc(c, &L_->w, n));
+    repack_conv_kernel<<<(int)std::min<size_t>((n + 255) / 256, 65535), 256>>>((const bf16*)t->p, L_->w, Co, Ci, k);
+  }
+  CKL();
+  *bytes += (int64_t)n * 2;
+  RET(take_f32(c, p + ".bias", {Co}, &L_->bias, bytes));
+  const int B = c->d.max_batch;
+  RET(dmalloc(c, &L_->hist, (size_t)B * L_->ctx * Ci));
+  RET(dmalloc(c, &L_->next, (size_t)B * L_->ctx * Ci));
+  segs->push_back({L_->hist, L_->next, L_->ctx * Ci});
+  return 0;
+}
+// ConvTranspose1d [Ci][Co][2s] -> [(j,co)][(half,ci)], bias tiled over j
+static int build_convtr(vv_ctx* c, const std::string& p, int Ci, int Co, int s, ConvL* L_, int64_t* bytes, std::vector<StateSeg>* segs) {
+  L_->Cin = Ci; L_->Cout = Co; L_->k = 2 * s; L_->stride = s; L_->ctx = 1; L_->N = s * Co; L_->K = 2 * Ci;
+  RawTensor* t;
+  RET(need(c, p + ".weight", &t, {Ci, Co, 2 * s}));
+  if (t->is_f32) return fail(VV_ERR_INVALID, "%s: unexpected f32 convtr weight", p.c_str());
+  const size_t n = (size_t)Ci * Co * 2 * s;
+  RET(dmalloc(c, &L_->w, n));
+  repack_convtr_kernel<<<(int)std::min<size_t>((n + 255) / 256, 65535), 256>>>((const bf16*)t->p, L_->w, Ci, Co, s);
+  CKL();
+  *bytes += (int64_t)n * 2;
+  RawTensor* bt;
+  RET(need(c, p + ".bias", &bt, {Co}));
+  RET(dmalloc(c, &L_->bias, (size_t)s * Co));
+  tile_bias_kernel<<<(s * Co + 255) / 256, 256>>>((const float*)bt->p, L_->bias, Co, s);
+  CKL();
+  *bytes += (int64_t)Co * 2;
+  const int B = c->d.max_batch;
+  RET(dmalloc(c, &L_->hist, (size_t)B * Ci));
+  RET(dmalloc(c, &L_->next, (size_t)B * Ci));
+  segs->push_back({L_->hist, L_->next, Ci});
+  return 0;
+}
+
+static int upload_segs(vv_ctx* c, Codec* k, const std::vector<StateSeg>& segs) {
+  k->n_segs = (int)segs.size();
+  RET(dmalloc(c, &k->segs_dev, segs.size()));
+  CK(cudaMemcpy(k->segs_dev, segs.data(), segs.size() * sizeof(StateSeg), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int vv_finalize_weights(vv_ctx* c) {
+  if (!c) return fail(VV_ERR_INVALID, "null ctx");
+  if (c->finalized) return fail(VV_ERR_STATE, "already finalized");
+  CK(cudaSetDevice(c->device));
+  {
+    std::string missing; int nm = 0;
+    for (auto& n : c->expected) if (!c->raw.count(n)) { if (nm < 8) missing += n + " "; ++nm; }
+    if (nm) return fail(VV_ERR_STATE, "%d tensors missing, e.g. %s", nm, missing.c_str());
+    if (std::isnan(c->speech_scale) || std::isnan(c->speech_bias))
+      return fail(VV_ERR_STATE, "speech_scaling_factor / speech_bias_factor are NaN (random-init checkpoints: call vv_set_speech_factors)");
+  }
+  const auto& d = c->d;
+  const int H = d.hidden_size, I = d.intermediate_size, nq = d.num_q_heads * HD, nkv = d.num_kv_heads * HD, B = d.max_batch;
+  const int M2 = 2 * B;
+  // ---------------- LM ----------------
+  const std::string lm = "model.language_model";
+  c->Nqkv = nq + 2 * nkv;
+  c->lm.resize(d.num_layers);
+  int64_t* wb = &c->wbytes[0];
+  for (int l = 0; l < d.num_layers; ++l) {
+    LmLayer& y = c->lm[l];
+    std::string q = S("%s.layers.%d", lm.c_str(), l);
+    RawTensor *tq, *tk, *tv, *bq, *bk, *bv, *tg, *tu;
+    RET(need(c, q + ".self_attn.q_proj.weight", &tq, {nq, H}));
+    RET(need(c, q + ".self_attn.k_proj.weight", &tk, {nkv, H}));
+    RET(need(c, q + ".self_attn.v_proj.weight", &tv, {nkv, H}));
+    RET(need(c, q + ".self_attn.q_proj.bias", &bq, {nq}));
+    RET(need(c, q + ".self_attn.k_proj.bias", &bk, {nkv}));
+    RET(need(c, q + ".self_attn.v_proj.bias", &bv, {nkv}));
+    RET(dmalloc(c, &y.wqkv, (size_t)c->Nqkv * H, false));
+    RET(dmalloc(c, &y.bqkv, (size_t)c->Nqkv, false));
+    CK(cudaMemcpy(y.wqkv, tq->p, (size_t)nq * H * 2, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(y.wqkv + (size_t)nq * H, tk->p, (size_t)nkv * H * 2, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(y.wqkv + (size_t)(nq + nkv) * H, tv->p, (size_t)nkv * H * 2, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(y.bqkv, bq->p, (size_t)nq * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(y.bqkv + nq, bk->p, (size_t)nkv * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(y.bqkv + nq + nkv, bv->p, (size_t)nkv * 4, cudaMemcpyDeviceToDevice));
+    *wb += (int64_t)c->Nqkv * H * 2 + (int64_t)c->Nqkv * 2;
+    for (const char* s : {"q", "k", "v"}) { drop(c, q + ".self_attn." + s + "_proj.weight"); drop(c, q + ".self_attn." + s + "_proj.bias"); }
+    RET(take_bf16(c, q + ".self_attn.o_proj.weight", {H, nq}, &y.wo, wb));
+    RET(need(c, q + ".mlp.gate_proj.weight", &tg, {I, H}));
+    RET(need(c, q + ".mlp.up_proj.weight", &tu, {I, H}));
+    RET(dmalloc(c, &y.wgu, (size_t)2 * I * H, false));
+    interleave_rows_kernel<<<4096, 256>>>((const bf16*)tg->p, (const bf16*)tu->p, y.wgu, (size_t)I, (size_t)H);
+    CKL();
+    CK(cudaDeviceSynchronize());
+    *wb += (int64_t)2 * I * H * 2;
+    drop(c, q + ".mlp.gate_proj.weight"); drop(c, q + ".mlp.up_proj.weight");
+    RET(take_bf16(c, q + ".mlp.down_proj.weight", {H, I}, &y.wdown, wb));
+    RET(take_f32(c, q + ".input_layernorm.weight", {H}, &y.ln1, wb));
+    RET(take_f32(c, q + ".post_attention_layernorm.weight", {H}, &y.ln2, wb));
+  }
+  RET(take_f32(c, lm + ".norm.weight", {H}, &c->lm_norm, wb));
+  RET(take_bf16(c, lm + ".embed_tokens.weight", {d.vocab_size, H}, &c->embed, nullptr));
+  {
+    RET(dmalloc(c, &c->valid_ids_dev, 8));
+    CK(cudaMemcpy(c->valid_ids_dev, d.valid_ids, sizeof(int) * d.n_valid_ids, cudaMemcpyHostToDevice));
+    RET(dmalloc(c, &c->head_valid, (size_t)8 * H));
+    const bf16* table = c->embed;
+    if (!d.tie_word_embeddings) {
+      bf16* lmh;
+      RET(take_bf16(c, "lm_head.weight", {d.vocab_size, H}, &lmh, nullptr));
+      table = lmh;
+    }
+    gather_rows_kernel<<<d.n_valid_ids, 256>>>(table, c->valid_ids_dev, c->head_valid, H);
+    CKL();
+    *wb += (int64_t)d.n_valid_ids * H * 2;
+    RET(dmalloc(c, &c->inv_freq, HD / 2));
+    std::vector<float> f(HD / 2);
+    for (int i = 0; i < HD / 2; ++i) f[i] = 1.0f / powf(d.rope_theta, (float)(2 * i) / (float)HD);
+    CK(cudaMemcpy(c->inv_freq, f.data(), sizeof(float) * (HD / 2), cudaMemcpyHostToDevice));
+  }
+  // ---------------- diffusion head ----------------
+  {
+    const std::string h = "model.prediction_head";
+    const int F = d.head_ffn_dim, LH = d.head_layers;
+    int64_t* hb = &c->wbytes[1];
+    RET(take_bf16(c, h + ".noisy_images_proj.weight", {H, 64}, &c->h_noisy, hb));
+    RET(take_bf16(c, h + ".cond_proj.weight", {H, H}, &c->h_cond, &c->wbytes[2]));
+    RET(take_bf16(c, h + ".t_embedder.mlp.0.weight", {H, 256}, &c->h_t0, nullptr));
+    RET(take_bf16(c, h + ".t_embedder.mlp.2.weight", {H, H}, &c->h_t2, nullptr));
+    RET(take_bf16(c, h + ".final_layer.linear.weight", {64, H}, &c->h_final, hb));
+    const size_t modrows = (size_t)(3 * LH + 2) * H;
+    RET(dmalloc(c, &c->h_mod, modrows * H, false));
+    c->head.resize(LH);
+    for (int l = 0; l < LH; ++l) {
+      std::string q = S("%s.layers.%d", h.c_str(), l);
+      RawTensor *tg, *tu, *tm;
+      RET(need(c, q + ".ffn.gate_proj.weight", &tg, {F, H}));
+      RET(need(c, q + ".ffn.up_proj.weight", &tu, {F, H}));
+      RET(dmalloc(c, &c->head[l].wgu, (size_t)2 * F * H, false));
+      interleave_rows_kernel<<<4096, 256>>>((const bf16*)tg->p, (const bf16*)tu->p, c->head[l].wgu, (size_t)F, (size_t)H);
+      CKL();
+      CK(cudaDeviceSynchronize());
+      *hb += (int64_t)2 * F * H * 2;
+      drop(c, q + ".ffn.gate_proj.weight"); drop(c, q + ".ffn.up_proj.weight");
+      RET(take_bf16(c, q + ".ffn.down_proj.weight", {H, F}, &c->head[l].wdown, hb));
+      RET(take_f32(c, q + ".norm.weight", {H}, &c->head[l].norm, hb));
+      RET(need(c, q + ".adaLN_modulation.1.weight", &tm, {3 * H, H}));
+      CK(cudaMemcpy(c->h_mod + (size_t)l * 3 * H * H, tm->p, (size_t)3 * H * H * 2, cudaMemcpyDeviceToDevice));
+      *hb += (int64_t)3 * H * H * 2;
+      drop(c, q + ".adaLN_modulation.1.weight");
+    }
+    RawTensor* tm;
+    RET(need(c, h + ".final_layer.adaLN_modulation.1.weight", &tm, {2 * H, H}));
+    CK(cudaMemcpy(c->h_mod + (size_t)LH * 3 * H * H, tm->p, (size_t)2 * H * H * 2, cudaMemcpyDeviceToDevice));
+    *hb += (int64_t)2 * H * H * 2;
+    drop(c, h + ".final_layer.adaLN_modulation.1.weight");
+    const int NS = std::max(d.max_diffusion_steps, 1);
+    RET(dmalloc(c, &c->temb, (size_t)NS * H));
+    RET(dmalloc(c, &c->coef_dev, (size_t)NS));
+    RET(dmalloc(c, &c->tfreqs, 128));
+    std::vector<float> fr(128);
+    for (int j = 0; j < 128; ++j) fr[j] = expf((-9.210340371976184f * (float)j) / 128.0f);
+    CK(cudaMemcpy(c->tfreqs, fr.data(), 128 * 4, cudaMemcpyHostToDevice));
+    RET(dmalloc(c, &c->s_tfeat, (size_t)NS * 256));
+    RET(dmalloc(c, &c->s_t1, (size_t)NS * H));
+    RET(dmalloc(c, &c->s_condp, (size_t)M2 * H));
+    RET(dmalloc(c, &c->s_call, (size_t)NS * M2 * H));
+    RET(dmalloc(c, &c->s_mod, (size_t)M2 * modrows));
+    RET(dmalloc(c, &c->s_hx, (size_t)M2 * H));
+    RET(dmalloc(c, &c->s_hg, (size_t)M2 * F));
+    RET(dmalloc(c, &c->s_v, (size_t)M2 * 64));
+    RET(dmalloc(c, &c->s_z, (size_t)B * 64));
+    RET(dmalloc(c, &c->s_x0, (size_t)B * 64));
+  }
+  // ---------------- connectors ----------------
+  {
+    int64_t* cb = &c->wbytes[5];
+    const std::string a = "model.acoustic_connector", s = "model.semantic_connector";
+    RET(take_bf16(c, a + ".fc1.weight", {H, d.acoustic_vae_dim}, &c->ca_fc1, cb));
+    RET(take_f32(c, a + ".fc1.bias", {H}, &c->ca_b1, cb));
+    RET(take_f32(c, a + ".norm.weight", {H}, &c->ca_n, cb));
+    RET(take_bf16(c, a + ".fc2.weight", {H, H}, &c->ca_fc2, cb));
+    RET(take_f32(c, a + ".fc2.bias", {H}, &c->ca_b2, cb));
+    RET(take_bf16(c, s + ".fc1.weight", {H, d.semantic_vae_dim}, &c->cs_fc1, cb));
+    RET(take_f32(c, s + ".fc1.bias", {H}, &c->cs_b1, cb));
+    RET(take_f32(c, s + ".norm.weight", {H}, &c->cs_n, cb));
+    RET(take_bf16(c, s + ".fc2.weight", {H, H}, &c->cs_fc2, cb));
+    RET(take_f32(c, s + ".fc2.bias", {H}, &c->cs_b2, cb));
+    RET(dmalloc(c, &c->s_e, (size_t)B * H));
+    RET(dmalloc(c, &c->s_c1, (size_t)B * H));
+    RET(dmalloc(c, &c->s_feat, (size_t)B * d.semantic_vae_dim));
+    RET(dmalloc(c, &c->s_audio, (size_t)B * 3200 * 4));
+    RET(dmalloc(c, &c->s_latent, (size_t)B * 64));
+  }
+  // ---------------- codec decoder (tokenizer.py:823-912) ----------------
+  int hop = 1;
+  for (int i = 0; i < d.n_stages - 1; ++i) hop *= d.dec_ratios[i];
+  size_t max_tc = 0, max_win = 0;
+  {
+    Codec& k = c->dec;
+    int64_t* kb = &c->wbytes[3];
+    std::vector<StateSeg> segs;
+    const std::string p = "model.acoustic_tokenizer.decoder";
+    const int ns = d.n_stages, nf = d.dec_n_filters;
+    k.convs.resize(ns + 1); k.stages.resize(ns); k.T.resize(ns); k.C.resize(ns);
+    int T = 1;
+    for (int i = 0; i < ns; ++i) {
+      const int C = nf << (ns - 1 - i);
+      if (i == 0) RET(build_conv(c, p + ".upsample_layers.0.0.conv.conv", d.acoustic_vae_dim, C, 7, 1, &k.convs[0], kb, &segs));
+      else { RET(build_convtr(c, S("%s.upsample_layers.%d.0.convtr.convtr", p.c_str(), i), C * 2, C, d.dec_ratios[i - 1], &k.convs[i], kb, &segs)); T *= d.dec_ratios[i - 1]; }
+      k.T[i] = T; k.C[i] = C;
+      max_tc = std::max(max_tc, (size_t)T * C);
+      max_win = std::max(max_win, (size_t)(T + 8) * C * 2);
+      k.stages[i].resize(d.dec_depths[i]);
+      for (int j = 0; j < d.dec_depths[i]; ++j) RET(build_block(c, S("%s.stages.%d.%d", p.c_str(), i, j), C, &k.stages[i][j], kb, &segs));
+    }
+    RET(build_conv(c, p + ".head.conv.conv", nf, 1, 7, 1, &k.convs[ns], kb, &segs));
+    if (T != hop) return fail(VV_ERR_INVALID, "decoder hop mismatch");
+    RET(upload_segs(c, &k, segs));
+    k.weight_bytes = *kb;
+  }
+  // ---------------- semantic encoder (tokenizer.py:694-774) ----------------
+  {
+    Codec& k = c->enc;
+    int64_t* kb = &c->wbytes[4];
+    std::vector<StateSeg> segs;
+    const std::string p = "model.semantic_tokenizer.encoder";
+    const int ns = d.n_stages, nf = d.enc_n_filters;
+    k.convs.resize(ns + 1); k.stages.resize(ns); k.T.resize(ns); k.C.resize(ns);
+    int T = hop;
+    for (int i = 0; i < ns; ++i) {
+      const int C = nf << i;
+      if (i == 0) RET(build_conv(c, p + ".downsample_layers.0.0.conv.conv", 1, C, 7, 1, &k.convs[0], kb, &segs));
+      else {
+        const int r = d.enc_ratios[ns - 1 - i];     // TokenizerEncoder reverses the ratio list (tokenizer.py:701)
+        RET(build_conv(c, S("%s.downsample_layers.%d.0.conv.conv", p.c_str(), i), C / 2, C, 2 * r, r, &k.convs[i], kb, &segs));
+        if (T % r) return fail(VV_ERR_INVALID, "encoder ratio mismatch");
+        T /= r;
+      }
+      k.T[i] = T; k.C[i] = C;
+      max_tc = std::max(max_tc, (size_t)T * C);
+      max_win = std::max(max_win, (size_t)(T + 16) * C * 2);
+      k.stages[i].resize(d.enc_depths[i]);
+      for (int j = 0; j < d.enc_depths[i]; ++j) RET(build_block(c, S("%s.stages.%d.%d", p.c_str(), i, j), C, &k.stages[i][j], kb, &segs));
+    }
+    if (T != 1) return fail(VV_ERR_INVALID, "encoder hop mismatch");
+    RET(build_conv(c, p + ".head.conv.conv", nf << (ns - 1), d.semantic_vae_dim, 7, 1, &k.convs[ns], kb, &segs));
+    RET(upload_segs(c, &k, segs));
+    k.weight_bytes = *kb;
+  }
+  max_win = std::max(max_win, (size_t)(hop + 8) * 64);
+  RET(dmalloc(c, &c->s_xa, (size_t)B * max_tc));
+  RET(dmalloc(c, &c->s_xb, (size_t)B * max_tc));
+  RET(dmalloc(c, &c->s_xn, (size_t)B * max_tc));
+  RET(dmalloc(c, &c->s_u, (size_t)B * max_tc * 4));
+  RET(dmalloc(c, &c->s_win, (size_t)B * max_win));
+  // ---------------- LM scratch ----------------
+  RET(dmalloc(c, &c->s_h, (size_t)M2 * H));
+  RET(dmalloc(c, &c->s_qkv, (size_t)M2 * c->Nqkv));
+  RET(dmalloc(c, &c->s_qrot, (size_t)M2 * nq));
+  RET(dmalloc(c, &c->s_attn, (size_t)M2 * nq));
+  RET(dmalloc(c, &c->s_act, (size_t)M2 * I));
+  RET(dmalloc(c, &c->s_pacc, (size_t)M2 * d.num_q_heads * c->nsplit * HD));
+  RET(dmalloc(c, &c->s_pml, (size_t)M2 * d.num_q_heads * c->nsplit * 2));
+  RET(dmalloc(c, &c->s_tok, 64));
+  RET(dmalloc(c, &c->kv_len_dev, 16));
+  RET(dmalloc(c, &c->row_mode_dev, 16));
+  {
+    int ones[16];
+    for (int i = 0; i < 16; ++i) ones[i] = 1;
+    CK(cudaMemcpy(c->row_mode_dev, ones, sizeof ones, cudaMemcpyHostToDevice));
+  }
+  c->kv_len_host.assign(M2, 0);
+  c->seq_pages.assign(M2, {});
+  for (auto& r : c->raw) if (r.second.p) { cudaFree(r.second.p); r.second.p = nullptr; }
+  CK(cudaDeviceSynchronize());
+  c->finalized = true;
+  return 0;
+}
+
+extern "C" int64_t vv_weight_bytes(vv_ctx* c, int which) { return (c && which >= 0 && which < 6) ? c->wbytes[which] : -1; }
+extern "C" int64_t vv_launch_count(vv_ctx* c) { return c ? c->launches : -1; }
+
+// ------------------------------------------------------------------------------------------------
+// graph cache: every per-frame program is captured once per distinct argument tuple and replayed
+// ------------------------------------------------------------------------------------------------
+template <class F>
+static int run_cached(vv_ctx* c, const std::string& key, cudaStream_t s, F&& enqueue) {
+  if (!c->use_graphs || s == nullptr) { L l{c, s}; return enqueue(l); }
+  auto it = c->graphs.find(key);
+  if (it == c->graphs.end()) {
+    const int64_t before = c->launches;
+    CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    L l{c, s};
+    int r = enqueue(l);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(s, &g);
+    if (r < 0) { if (g) cudaGraphDestroy(g); return r; }
+    if (e != cudaSuccess) return fail(VV_ERR_CUDA, "graph capture failed (%s): %s", key.c_str(), cudaGetErrorString(e));
+    GraphEntry ge;
+    ge.launches = c->launches - before;
+    c->launches = before;
+    e = cudaGraphInstantiate(&ge.exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(VV_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    it = c->graphs.emplace(key, ge).first;
+  }
+  CK(cudaGraphLaunch(it->second.exec, s));
+  c->launches += it->second.launches;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// KV pages
+// ------------------------------------------------------------------------------------------------
+extern "C" int vv_kv_init(vv_ctx* c, int64_t n_pages) {
+  if (!c || !c->finalized) return fail(VV_ERR_STATE, "vv_kv_init before vv_finalize_weights");
+  if (c->kpool) return fail(VV_ERR_STATE, "KV pool already initialised");
+  CK(cudaSetDevice(c->device));
+  const auto& d = c->d;
+  const size_t per_layer = (size_t)n_pages * d.num_kv_heads * KV_PAGE * HD;
+  RET(dmalloc(c, &c->kpool, per_layer * d.num_layers));
+  RET(dmalloc(c, &c->vpool, per_layer * d.num_layers));
+  c->n_pages = n_pages;
+  c->max_pages = (int)n_pages;
+  const size_t nt = (size_t)2 * d.max_batch * c->max_pages;
+  RET(dmalloc(c, &c->page_table_dev, nt));
+  CK(cudaMallocHost(&c->page_table_host, nt * sizeof(int)));
+  memset(c->page_table_host, 0, nt * sizeof(int));
+  c->free_pages.clear();
+  for (int i = (int)n_pages - 1; i >= 0; --i) c->free_pages.push_back(i);
+  return 0;
+}
+extern "C" int64_t vv_kv_pages_free(vv_ctx* c) { return c ? (int64_t)c->free_pages.size() : -1; }
+extern "C" int64_t vv_kv_len(vv_ctx* c, int seq) { return (c && seq >= 0 && seq < (int)c->kv_len_host.size()) ? c->kv_len_host[seq] : -1; }
+
+extern "C" int vv_kv_reserve(vv_ctx* c, int seq, int64_t n_tokens, void* stream) {
+  if (!c || !c->kpool) return fail(VV_ERR_STATE, "KV pool not initialised");
+  if (seq < 0 || seq >= 2 * c->d.max_batch) return fail(VV_ERR_INVALID, "bad seq %d", seq);
+  auto& pg = c->seq_pages[seq];
+  const int64_t needp = (n_tokens + KV_PAGE - 1) / KV_PAGE;
+  const size_t first = pg.size();
+  while ((int64_t)pg.size() < needp) {
+    if (c->free_pages.empty()) return fail(VV_ERR_NOMEM, "KV page pool exhausted (seq %d needs %lld pages)", seq, (long long)needp);
+    int p = c->free_pages.back();
+    c->free_pages.pop_back();
+    c->page_table_host[(size_t)seq * c->max_pages + pg.size()] = p;
+    pg.push_back(p);
+  }
+  if (pg.size() > first) {
+    const size_t o = (size_t)seq * c->max_pages + first;
+    CK(cudaMemcpyAsync(c->page_table_dev + o, c->page_table_host + o, (pg.size() - first) * sizeof(int), cudaMemcpyHostToDevice,
+                       (cudaStream_t)stream));
+  }
+  return 0;
+}
+
+struct Lens { int v[16]; };
+__global__ void kv_set_all_kernel(int* kv_len, Lens l, int n) { if (threadIdx.x < n) kv_len[threadIdx.x] = l.v[threadIdx.x]; }
+
+static int push_lens(vv_ctx* c, cudaStream_t s) {
+  Lens l;
+  const int n = 2 * c->d.max_batch;
+  for (int i = 0; i < 16; ++i) l.v[i] = i < n ? (int)c->kv_len_host[i] : 0;
+  kv_set_all_kernel<<<1, 32, 0, s>>>(c->kv_len_dev, l, n);
+  CKL();
+  c->launches++;
+  return 0;
+}
+extern "C" int vv_kv_set_len(vv_ctx* c, int seq, int64_t len, void* stream) {
+  if (!c || !c->kpool) return fail(VV_ERR_STATE, "KV pool not initialised");
+  if (seq < 0 || seq >= 2 * c->d.max_batch) return fail(VV_ERR_INVALID, "bad seq %d", seq);
+  c->kv_len_host[seq] = len;
+  return push_lens(c, (cudaStream_t)stream);
+}
+extern "C" int vv_kv_commit(vv_ctx* c, const int32_t* adv, void* stream) {
+  if (!c || !c->kpool) return fail(VV_ERR_STATE, "KV pool not initialised");
+  for (int i = 0; i < 2 * c->d.max_batch; ++i) c->kv_len_host[i] += adv[i] ? 1 : 0;
+  return push_lens(c, (cudaStream_t)stream);
+}
+extern "C" int vv_set_row_mode(vv_ctx* c, const int32_t* rm, void* stream) {
+  if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
+  Lens l;
+  for (int i = 0; i < 16; ++i) l.v[i] = i < 2 * c->d.max_batch ? rm[i] : 0;
+  kv_set_all_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(c->row_mode_dev, l, 2 * c->d.max_batch);
+  CKL();
+  c->launches++;
+  return 0;
+}
+extern "C" int vv_set_rope_inv_freq(vv_ctx* c, const float* f, int n) {
+  if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
+  if (n != HD / 2) return fail(VV_ERR_INVALID, "inv_freq must have %d entries", HD / 2);
+  CK(cudaMemcpy(c->inv_freq, f, sizeof(float) * n, cudaMemcpyHostToDevice));
+  return 0;
+}
+extern "C" int vv_kv_write(vv_ctx* c, int seq, int layer, int64_t pos0, int64_t n_tokens, const void* k, const void* v, void* stream) {
+  if (!c || !c->kpool) return fail(VV_ERR_STATE, "KV pool not initialised");
+  RET(vv_kv_reserve(c, seq, pos0 + n_tokens, stream));
+  const auto& d = c->d;
+  const size_t per_layer = (size_t)c->n_pages * d.num_kv_heads * KV_PAGE * HD;
+  kv_write_kernel<<<(unsigned)n_tokens, 128, 0, (cudaStream_t)stream>>>((const bf16*)k, (const bf16*)v, c->kpool + per_layer * layer,
+                                                                      c->vpool + per_layer * layer,
+                                                                      c->page_table_dev + (size_t)seq * c->max_pages, d.num_kv_heads, pos0, n_tokens);
+  CKL();
+  c->launches++;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a-3: LM decode
+// ------------------------------------------------------------------------------------------------
+static int enqueue_lm_head(const L& l, const float* hidden, float* logits, int32_t* tokens) {
+  vv_ctx* c = l.c;
+  lm_head_argmax_kernel<<<c->d.max_batch, 256, 0, l.s>>>(hidden, c->head_valid, c->valid_ids_dev, c->d.n_valid_ids, c->d.hidden_size, logits, tokens);
+  CKL();
+  c->launches++;
+  return 0;
+}
+
+static int enqueue_lm_decode(const L& l, const float* embeds, float* hidden, float* logits, int32_t* tokens) {
+  vv_ctx* c = l.c;
+  const auto& d = c->d;
+  const int H = d.hidden_size, I = d.intermediate_size, M = 2 * d.max_batch, nq = d.num_q_heads * HD;
+  CK(cudaMemcpyAsync(c->s_h, embeds, (size_t)M * H * 4, cudaMemcpyDeviceToDevice, l.s));
+  const size_t per_layer = (size_t)c->n_pages * d.num_kv_heads * KV_PAGE * HD;
+  const float scale = 1.0f / sqrtf((float)HD);
+  for (int li = 0; li < d.num_layers; ++li) {
+    const LmLayer& y = c->lm[li];
+    GemvP p = mk(y.wqkv, y.bqkv, c->s_h, H, c->s_qkv, c->Nqkv, M, c->Nqkv, H);
+    p.pro = PRO_RMSNORM; p.pro_w = y.ln1; p.pro_eps = d.rms_norm_eps;
+    RET(linear(l, p));
+    KvView kv;
+    kv.kpool = c->kpool + per_layer * li; kv.vpool = c->vpool + per_layer * li;
+    kv.page_table = c->page_table_dev; kv.max_pages = c->max_pages; kv.kv_len = c->kv_len_dev; kv.row_mode = c->row_mode_dev;
+    kv.kv_heads = d.num_kv_heads; kv.q_heads = d.num_q_heads;
+    rope_append_kernel<<<M, 256, 0, l.s>>>(c->s_qkv, c->s_qrot, kv, c->inv_freq);
+    CKL();
+    attn_partial_kernel<<<dim3(c->nsplit, d.num_kv_heads, M), 128, 0, l.s>>>(c->s_qrot, kv, c->s_pacc, c->s_pml, c->nsplit, scale);
+    CKL();
+    attn_combine_kernel<<<dim3(d.num_q_heads, M), 128, 0, l.s>>>(c->s_pacc, c->s_pml, c->row_mode_dev, c->s_attn, d.num_q_heads, c->nsplit);
+    CKL();
+    c->launches += 3;
+    p = mk(y.wo, nullptr, c->s_attn, nq, c->s_h, H, M, H, nq);
+    p.epi = EPI_RESID; p.res = c->s_h; p.ldres = H;
+    RET(linear(l, p));
+    p = mk(y.wgu, nullptr, c->s_h, H, c->s_act, I, M, 2 * I, H);
+    p.pro = PRO_RMSNORM; p.pro_w = y.ln2; p.pro_eps = d.rms_norm_eps; p.epi = EPI_SWIGLU;
+    RET(linear(l, p));
+    p = mk(y.wdown, nullptr, c->s_act, I, c->s_h, H, M, H, I);
+    p.epi = EPI_RESID; p.res = c->s_h; p.ldres = H;
+    RET(linear(l, p));
+  }
+  rows_norm_kernel<<<(M + 7) / 8, 256, 0, l.s>>>(c->s_h, c->lm_norm, hidden, M, H, d.rms_norm_eps);
+  CKL();
+  c->launches++;
+  return enqueue_lm_head(l, hidden, logits, tokens);
+}
+
+extern "C" int vv_lm_decode(vv_ctx* c, const float* embeds, float* hidden, float* logits, int32_t* tokens, void* stream) {
+  if (!c || !c->kpool) return fail(VV_ERR_STATE, "vv_lm_decode: KV pool not initialised");
+  CK(cudaSetDevice(c->device));
+  for (int s = 0; s < 2 * c->d.max_batch; ++s) RET(vv_kv_reserve(c, s, c->kv_len_host[s] + 1, stream));
+  char key[256];
+  snprintf(key, sizeof key, "lm:%p:%p:%p:%p", (const void*)embeds, (void*)hidden, (void*)logits, (void*)tokens);
+  return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_lm_decode(l, embeds, hidden, logits, tokens); });
+}
+extern "C" int vv_lm_head(vv_ctx* c, const float* hidden, float* logits, int32_t* tokens, void* stream) {
+  if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
+  L l{c, (cudaStream_t)stream};
+  return enqueue_lm_head(l, hidden, logits, tokens);
+}
+struct Toks { int v[16]; };
+__global__ void embed_gather_val_kernel(const bf16* __restrict__ table, Toks t, float* __restrict__ out, int H) {
+  const bf16* row = table + (size_t)t.v[blockIdx.x] * H;
+  for (int k = threadIdx.x; k < H; k += blockDim.x) out[(size_t)blockIdx.x * H + k] = __bfloat162float(row[k]);
+}
+extern "C" int vv_embed_tokens(vv_ctx* c, const int32_t* tokens_host, int n, float* out, void* stream) {
+  if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
+  if (n < 1 || n > 16) return fail(VV_ERR_INVALID, "vv_embed_tokens: n must be in [1,16]");
+  Toks t;
+  for (int i = 0; i < 16; ++i) {
+    t.v[i] = i < n ? tokens_host[i] : 0;
+    if (t.v[i] < 0 || t.v[i] >= c->d.vocab_size) return fail(VV_ERR_INVALID, "token id %d out of range", t.v[i]);
+  }
+  embed_gather_val_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(c->embed, t, out, c->d.hidden_size);
+  CKL();
+  c->launches++;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a-4: diffusion sampler
+// ------------------------------------------------------------------------------------------------
+extern "C" int vv_set_diffusion_steps(vv_ctx* c, int n_steps, const float* timesteps, const float* coef, void* stream) {
+  if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
+  if (n_steps < 1 || n_steps > c->d.max_diffusion_steps) return fail(VV_ERR_INVALID, "n_steps %d outside [1,%d]", n_steps, c->d.max_diffusion_steps);
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int H = c->d.hidden_size;
+  std::vector<DpmCoef> cf(n_steps);
+  for (int i = 0; i < n_steps; ++i) {
+    cf[i].a0 = coef[i * 6 + 0]; cf[i].s0 = coef[i * 6 + 1]; cf[i].ks = coef[i * 6 + 2]; cf[i].kx = coef[i * 6 + 3];
+    cf[i].rinv = coef[i * 6 + 4]; cf[i].order = (int)coef[i * 6 + 5];
+  }
+  CK(cudaStreamSynchronize(s));
+  CK(cudaMemcpy(c->coef_dev, cf.data(), sizeof(DpmCoef) * n_steps, cudaMemcpyHostToDevice));
+  float* tdev = c->s_t1;   // reuse as staging for the timesteps (n floats) before it is overwritten below
+  CK(cudaMemcpy(tdev, timesteps, sizeof(float) * n_steps, cudaMemcpyHostToDevice));
+  timestep_feat_kernel<<<n_steps, 256, 0, s>>>(tdev, c->tfreqs, c->s_tfeat, n_steps);
+  CKL();
+  CK(cudaStreamSynchronize(s));
+  L l{c, s};
+  GemvP p = mk(c->h_t0, nullptr, c->s_tfeat, 256, c->s_t1, H, n_steps, H, 256);
+  p.epi = EPI_SILU;
+  RET(linear(l, p));
+  p = mk(c->h_t2, nullptr, c->s_t1, H, c->temb, H, n_steps, H, H);
+  RET(linear(l, p));
+  CK(cudaStreamSynchronize(s));
+  c->n_steps = n_steps;
+  // programs captured with another step count are stale
+  for (auto it = c->graphs.begin(); it != c->graphs.end();) {
+    if (it->first.rfind("tail:", 0) == 0 || it->first.rfind("diff:", 0) == 0) { cudaGraphExecDestroy(it->second.exec); it = c->graphs.erase(it); }
+    else ++it;
+  }
+  return 0;
+}
+
+static int enqueue_diffusion(const L& l, const float* cond, const float* noise, float cfg, float* latent_out) {
+  vv_ctx* c = l.c;
+  const auto& d = c->d;
+  const int H = d.hidden_size, F = d.head_ffn_dim, B = d.max_batch, M = 2 * B, LH = d.head_layers, N = c->n_steps;
+  if (N < 1) return fail(VV_ERR_STATE, "vv_set_diffusion_steps not called");
+  const int modld = (3 * LH + 2) * H;
+  GemvP p = mk(c->h_cond, nullptr, cond, H, c->s_condp, H, M, H, H);
+  RET(linear(l, p));
+  {
+    const long long n = (long long)N * M * H;
+    head_cond_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, l.s>>>(c->s_condp, c->temb, c->s_call, N, M, H);
+    CKL();
+    dpm_update_proj_kernel<<<B, 256, 0, l.s>>>(c->s_z, c->s_x0, c->s_v, noise, c->coef_dev, -1, cfg, c->h_noisy, c->s_hx, nullptr, B, H, 1);
+    CKL();
+    c->launches += 2;
+  }
+  for (int i = 0; i < N; ++i) {
+    p = mk(c->h_mod, nullptr, c->s_call + (size_t)i * M * H, H, c->s_mod, modld, M, modld, H);
+    RET(linear(l, p));
+    for (int li = 0; li < LH; ++li) {
+      const HeadLayer& hl = c->head[li];
+      p = mk(hl.wgu, nullptr, c->s_hx, H, c->s_hg, F, M, 2 * F, H);
+      p.pro = PRO_ADALN; p.pro_w = hl.norm; p.pro_eps = d.head_rms_eps;
+      p.pro_shift = c->s_mod + (size_t)li * 3 * H; p.pro_scale = c->s_mod + (size_t)li * 3 * H + H; p.pro_ld = modld;
+      p.epi = EPI_SWIGLU;
+      RET(linear(l, p));
+      p = mk(hl.wdown, nullptr, c->s_hg, F, c->s_hx, H, M, H, F);
+      p.epi = EPI_GATED_RESID; p.epi_a = c->s_mod + (size_t)li * 3 * H + 2 * H; p.epi_lda = modld; p.res = c->s_hx; p.ldres = H;
+      RET(linear(l, p));
+    }
+    p = mk(c->h_final, nullptr, c->s_hx, H, c->s_v, 64, M, 64, H);
+    p.pro = PRO_ADALN; p.pro_w = nullptr; p.pro_eps = d.head_rms_eps;
+    p.pro_shift = c->s_mod + (size_t)LH * 3 * H; p.pro_scale = c->s_mod + (size_t)LH * 3 * H + H; p.pro_ld = modld;
+    RET(linear(l, p));
+    const bool last = (i == N - 1);
+    dpm_update_proj_kernel<<<B, 256, 0, l.s>>>(c->s_z, c->s_x0, c->s_v, noise, c->coef_dev, i, cfg, c->h_noisy, c->s_hx,
+                                               last ? latent_out : nullptr, B, H, last ? 0 : 1);
+    CKL();
+    c->launches++;
+  }
+  return 0;
+}
+
+extern "C" int vv_diffusion_sample(vv_ctx* c, const float* cond, const float* noise, const int32_t* active, float cfg, float* latent_out,
+                                   void* stream) {
+  (void)active;   // rows are independent; inactive rows are computed and ignored (static shapes keep the program graph-replayable)
+  if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
+  CK(cudaSetDevice(c->device));
+  char key[256];
+  snprintf(key, sizeof key, "diff:%p:%p:%p:%a", (const void*)cond, (const void*)noise, (void*)latent_out, cfg);
+  return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_diffusion(l, cond, noise, cfg, latent_out); });
+}
+
+// ------------------------------------------------------------------------------------------------
+// a-5 / a-6: streaming codec
+// ------------------------------------------------------------------------------------------------
+static int assemble(const L& l, const float* src, const float* hist, float* win, float* next, int B, int T, int ctx, int C,
+                    const float* norm_w, float eps, float alpha, float beta) {
+  const int rows = B * (ctx + T);
+  assemble_window_kernel<<<(rows + 7) / 8, 256, 0, l.s>>>(src, hist, win, next, B, T, ctx, C, norm_w, eps, alpha, beta);
+  CKL();
+  l.c->launches++;
+  return 0;
+}
+
+// one Block1D over x [B,T,C] (in `xin`), result in `xout` (may not alias xin)
+static int enqueue_block(const L& l, const Block& b, const float* xin, float* xout, int B, int T, float eps) {
+  vv_ctx* c = l.c;
+  const int C = b.C, M = B * T;
+  RET(assemble(l, xin, b.hist, c->s_win, b.next, B, T, 6, C, b.norm_w, eps, 1.f, 0.f));
+  {
+    const long long n = (long long)M * C;
+    dwconv_res_kernel<<<(unsigned)((n + 255) / 256), 256, 0, l.s>>>(xin, c->s_win, b.dw_w, b.dw_b, b.gamma, xout, B, T, C);
+    CKL();
+    c->launches++;
+  }
+  GemvP p;
+  if (M <= 16) {
+    p = mk(b.w1, b.b1, xout, C, c->s_u, 4 * C, M, 4 * C, C);
+    p.pro = PRO_RMSNORM; p.pro_w = b.ffn_norm_w; p.pro_eps = eps; p.epi = EPI_GELU;
+    RET(linear(l, p));
+  } else {
+    rows_norm_kernel<<<(M + 7) / 8, 256, 0, l.s>>>(xout, b.ffn_norm_w, c->s_xn, M, C, eps);
+    CKL();
+    c->launches++;
+    p = mk(b.w1, b.b1, c->s_xn, C, c->s_u, 4 * C, M, 4 * C, C);
+    p.epi = EPI_GELU;
+    RET(linear(l, p));
+  }
+  p = mk(b.w2, b.b2, c->s_u, 4 * C, xout, C, M, C, 4 * C);
+  p.epi = EPI_GAMMA_RESID; p.epi_a = b.ffn_gamma; p.res = xout; p.ldres = C;
+  return linear(l, p);
+}
+
+static int conv_apply(const L& l, const ConvL& cv, const float* win, float* y, int B, int T_out, int T_in) {
+  // rows (b,t) read window rows [t*stride, t*stride + k) of a [ctx+T_in, Cin] window
+  RowMap xm; xm.T = T_out; xm.bs = (long long)(cv.ctx + T_in) * cv.Cin; xm.rs = (long long)cv.stride * cv.Cin;
+  const int M = B * T_out;
+  if (cv.wf) {
+    const long long n = (long long)M * cv.N;
+    conv_naive_kernel<<<(unsigned)((n + 255) / 256), 256, 0, l.s>>>(cv.wf, cv.bias, win, xm, y, M, cv.N, cv.K);
+    CKL();
+    l.c->launches++;
+    return 0;
+  }
+  GemvP p = mk(cv.w, cv.bias, win, 0, y, cv.N, M, cv.N, cv.K);
+  p.xmap = xm;
+  return linear(l, p);
+}
+
+static int enqueue_decode(const L& l, const float* latent, const int32_t* active, float* audio) {
+  vv_ctx* c = l.c;
+  const auto& d = c->d;
+  Codec& k = c->dec;
+  const int B = d.max_batch, ns = d.n_stages;
+  float *xa = c->s_xa, *xb = c->s_xb;
+  // stem: window over the last 7 (un-scaled) latent frames; un-scaling latent/scale - bias (:636) is folded in
+  RET(assemble(l, latent, k.convs[0].hist, c->s_win, k.convs[0].next, B, 1, 6, 64, nullptr, 0.f, 1.0f / c->speech_scale, -c->speech_bias));
+  RET(conv_apply(l, k.convs[0], c->s_win, xa, B, 1, 1));
+  for (int i = 0; i < ns; ++i) {
+    if (i > 0) {
+      const ConvL& cv = k.convs[i];
+      const int Tin = k.T[i - 1];
+      RET(assemble(l, xa, cv.hist, c->s_win, cv.next, B, Tin, 1, cv.Cin, nullptr, 0.f, 1.f, 0.f));
+      RowMap xm; xm.T = Tin; xm.bs = (long long)(1 + Tin) * cv.Cin; xm.rs = cv.Cin;
+      GemvP p = mk(cv.w, cv.bias, c->s_win, 0, xb, cv.N, B * Tin, cv.N, cv.K);
+      p.xmap = xm;
+      RET(linear(l, p));
+      std::swap(xa, xb);
+    }
+    for (const Block& b : k.stages[i]) { RET(enqueue_block(l, b, xa, xb, B, k.T[i], d.codec_eps)); std::swap(xa, xb); }
+  }
+  const ConvL& hd = k.convs[ns];
+  const int T = k.T[ns - 1];
+  RET(assemble(l, xa, hd.hist, c->s_win, hd.next, B, T, 6, hd.Cin, nullptr, 0.f, 1.f, 0.f));
+  RET(conv_apply(l, hd, c->s_win, audio, B, T, T));
+  advance_kernel<<<dim3(k.n_segs, B), 256, 0, l.s>>>(k.segs_dev, active);
+  CKL();
+  c->launches++;
+  return 0;
+}
+
+static int enqueue_encode(const L& l, const float* audio, const int32_t* active, float* feat) {
+  vv_ctx* c = l.c;
+  const auto& d = c->d;
+  Codec& k = c->enc;
+  const int B = d.max_batch, ns = d.n_stages;
+  float *xa = c->s_xa, *xb = c->s_xb;
+  int hop = k.T[0];
+  RET(assemble(l, audio, k.convs[0].hist, c->s_win, k.convs[0].next, B, hop, 6, 1, nullptr, 0.f, 1.f, 0.f));
+  RET(conv_apply(l, k.convs[0], c->s_win, xa, B, hop, hop));
+  for (int i = 0; i < ns; ++i) {
+    if (i > 0) {
+      const ConvL& cv = k.convs[i];
+      const int Tin = k.T[i - 1];
+      RET(assemble(l, xa, cv.hist, c->s_win, cv.next, B, Tin, cv.ctx, cv.Cin, nullptr, 0.f, 1.f, 0.f));
+      RET(conv_apply(l, cv, c->s_win, xb, B, k.T[i], Tin));
+      std::swap(xa, xb);
+    }
+    for (const Block& b : k.stages[i]) { RET(enqueue_block(l, b, xa, xb, B, k.T[i], d.codec_eps)); std::swap(xa, xb); }
+  }
+  const ConvL& hd = k.convs[ns];
+  RET(assemble(l, xa, hd.hist, c->s_win, hd.next, B, 1, 6, hd.Cin, nullptr, 0.f, 1.f, 0.f));
+  RET(conv_apply(l, hd, c->s_win, feat, B, 1, 1));
+  advance_kernel<<<dim3(k.n_segs, B), 256, 0, l.s>>>(k.segs_dev, active);
+  CKL();
+  c->launches++;
+  return 0;
+}
+
+static int enqueue_connect(const L& l, const float* latent, const float* sem, const int32_t* active, float* embeds) {
+  vv_ctx* c = l.c;
+  const auto& d = c->d;
+  const int H = d.hidden_size, B = d.max_batch;
+  GemvP p = mk(c->ca_fc1, c->ca_b1, latent, 64, c->s_c1, H, B, H, 64);
+  RET(linear(l, p));
+  p = mk(c->ca_fc2, c->ca_b2, c->s_c1, H, c->s_e, H, B, H, H);
+  p.pro = PRO_RMSNORM; p.pro_w = c->ca_n; p.pro_eps = 1e-6f;
+  RET(linear(l, p));
+  p = mk(c->cs_fc1, c->cs_b1, sem, d.semantic_vae_dim, c->s_c1, H, B, H, d.semantic_vae_dim);
+  RET(linear(l, p));
+  p = mk(c->cs_fc2, c->cs_b2, c->s_c1, H, c->s_e, H, B, H, H);
+  p.pro = PRO_RMSNORM; p.pro_w = c->cs_n; p.pro_eps = 1e-6f; p.epi = EPI_RESID; p.res = c->s_e; p.ldres = H;
+  RET(linear(l, p));
+  select_embeds_kernel<<<B, 256, 0, l.s>>>(embeds, c->s_e, active, B, H);
+  CKL();
+  c->launches++;
+  return 0;
+}
+
+extern "C" int vv_codec_decode_frame(vv_ctx* c, const float* latent, const int32_t* active, float* audio_out, void* stream) {
+  if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
+  CK(cudaSetDevice(c->device));
+  char key[256];
+  snprintf(key, sizeof key, "dec:%p:%p:%p", (const void*)latent, (const void*)active, (void*)audio_out);
+  return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_decode(l, latent, active, audio_out); });
+}
+extern "C" int vv_semantic_encode_frame(vv_ctx* c, const float* audio, const int32_t* active, float* feat_out, void* stream) {
+  if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
+  CK(cudaSetDevice(c->device));
+  char key[256];
+  snprintf(key, sizeof key, "enc:%p:%p:%p", (const void*)audio, (const void*)active, (void*)feat_out);
+  return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_encode(l, audio, active, feat_out); });
+}
+extern "C" int vv_connect(vv_ctx* c, const float* latent, const float* sem, const int32_t* active, float* embeds, void* stream) {
+  if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
+  CK(cudaSetDevice(c->device));
+  L l{c, (cudaStream_t)stream};
+  return enqueue_connect(l, latent, sem, active, embeds);
+}
+extern "C" int vv_frame_tail(vv_ctx* c, const float* hidden, const float* noise, const int32_t* active, float cfg, float* latent_out,
+                             float* audio_out, float* embeds, void* stream) {
+  if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
+  CK(cudaSetDevice(c->device));
+  char key[320];
+  snprintf(key, sizeof key, "tail:%p:%p:%p:%p:%p:%p:%a", (const void*)hidden, (const void*)noise, (const void*)active, (void*)latent_out,
+           (void*)audio_out, (void*)embeds, cfg);
+  return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) {
+    RET(enqueue_diffusion(l, hidden, noise, cfg, latent_out));
+    RET(enqueue_decode(l, latent_out, active, audio_out));
+    RET(enqueue_encode(l, audio_out, active, c->s_feat));
+    return enqueue_connect(l, latent_out, c->s_feat, active, embeds);
+  });
+}
+
+struct Rows { int v[16]; };
+__global__ void state_zero_val_kernel(const StateSeg* __restrict__ segs, Rows r) {
+  const int b = r.v[blockIdx.y];
+  const StateSeg s = segs[blockIdx.x];
+  float* dd = s.hist + (size_t)b * s.n;
+  for (int i = threadIdx.x; i < s.n; i += blockDim.x) dd[i] = 0.f;
+}
+extern "C" int vv_codec_state_zero(vv_ctx* c, const int32_t* rows_host, int n, void* stream) {
+  if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
+  if (n < 1) return 0;
+  if (n > c->d.max_batch) return fail(VV_ERR_INVALID, "too many rows");
+  Rows r;
+  for (int i = 0; i < 16; ++i) r.v[i] = i < n ? rows_host[i] : 0;
+  for (int i = 0; i < n; ++i) if (r.v[i] < 0 || r.v[i] >= c->d.max_batch) return fail(VV_ERR_INVALID, "row %d out of range", r.v[i]);
+  cudaStream_t s = (cudaStream_t)stream;
+  state_zero_val_kernel<<<dim3(c->dec.n_segs, n), 256, 0, s>>>(c->dec.segs_dev, r);
+  CKL();
+  state_zero_val_kernel<<<dim3(c->enc.n_segs, n), 256, 0, s>>>(c->enc.segs_dev, r);
+  CKL();
+  c->launches += 2;
+  return 0;
+}
+extern "C" int vv_codec_state_reset(vv_ctx* c, void* stream) {
+  if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
+  int rows[8];
+  for (int i = 0; i < c->d.max_batch; ++i) rows[i] = i;
+  return vv_codec_state_zero(c, rows, c->d.max_batch, stream);
+}
+
+extern "C" int vv_debug_gemv(vv_ctx* c, const void* w, const float* bias, const float* x, float* y, int M, int N, int K, int prologue,
+                             const float* pro_w, float eps, int epilogue, void* stream) {
+  if (!c) return fail(VV_ERR_INVALID, "null ctx");
+  CK(cudaSetDevice(c->device));
+  L l{c, (cudaStream_t)stream};
+  const int ldy = epilogue == EPI_SWIGLU ? N / 2 : N;
+  GemvP p = mk((const bf16*)w, bias, x, K, y, ldy, M, N, K);
+  p.pro = prologue; p.pro_w = pro_w; p.pro_eps = eps; p.epi = epilogue;
+  if (epilogue == EPI_RESID) { p.res = y; p.ldres = N; }
+  return linear(l, p);
+}

@@ -1,0 +1,309 @@
+"""`VibeVoiceForConditionalGenerationInference` -- the reference's public generation surface
+(`vibevoice/modular/modeling_vibevoice_inference.py:68-717`) on top of the B200 engine.
+
+Same constructor / `from_pretrained` / `set_ddpm_inference_steps` / `generate(**kwargs)` contract and the
+same `VibeVoiceGenerationOutput`, so `demo/inference_from_file.py:280-431` runs against this class.  The loop
+body keeps the reference's integer/boolean bookkeeping on the host, verbatim in meaning
+(`:432-675`), and replaces every tensor op by one of five C-ABI calls:
+
+    self(**model_inputs)            :480-482   -> Engine.lm_decode   (positive + negative rows, one weight pass)
+    negative forward + KV shifting  :576-624   -> same call; vv_kv_commit advances the negative stream only on diffusion tokens
+    sample_speech_tokens            :629-633 \\
+    acoustic_tokenizer.decode       :637-643  |-> Engine.frame_tail (one captured CUDA graph)
+    semantic_tokenizer.encode       :658-664  |
+    connectors                      :667-672 /
+"""
+from __future__ import annotations
+
+import glob
+import json
+import os
+from dataclasses import dataclass
+from types import SimpleNamespace
+from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .configuration import VibeVoiceConfig
+from .engine import Engine
+
+
+@dataclass
+class VibeVoiceGenerationOutput:
+    """`modeling_vibevoice_inference.py:38-51`."""
+    sequences: torch.LongTensor = None
+    speech_outputs: Optional[List[Optional[torch.Tensor]]] = None
+    reach_max_step_sample: Optional[torch.BoolTensor] = None
+
+
+class ForcedTokenScript:
+    """Accepted as (an element of) `logits_processor`: per-row token scripts that override the constrained argmax,
+    e.g. "speech_diffusion x F then EOS" (BASELINE.md section 3).  The reference achieves the same with a
+    `LogitsProcessor` that adds +inf to the wanted id; full-vocab logits do not exist on this path (only the
+    4-5 ids that survive `VibeVoiceTokenConstraintProcessor`, :53-66, are ever computed)."""
+
+    def __init__(self, scripts: Sequence[Sequence[int]]):
+        self.scripts = [list(s) for s in scripts]
+
+    def token(self, row: int, step: int) -> int:
+        s = self.scripts[row]
+        return s[min(step, len(s) - 1)]
+
+
+class VibeVoiceForConditionalGenerationInference:
+    def __init__(self, config: VibeVoiceConfig, tokenizer_ids=None, max_batch: int = 1, device: int = 0,
+                 max_diffusion_steps: int = 64):
+        self.config = config
+        self._tok = tokenizer_ids
+        self._device_index = device
+        self._max_batch = max_batch
+        self._max_steps = max_diffusion_steps
+        self.engine: Optional[Engine] = None
+        self._pending: List[Tuple[str, torch.Tensor]] = []
+        self.ddpm_inference_steps = config.diffusion_head_config.ddpm_num_inference_steps
+        self.dtype = torch.bfloat16
+        self._kv_tokens = 0
+        # attribute surface other reference code pokes at (demo/inference_from_file.py:367-368, gradio_demo.py:142-146)
+        self.model = SimpleNamespace(
+            language_model=SimpleNamespace(config=config.decoder_config),
+            noise_scheduler=None, prediction_head=None, acoustic_connector=None, semantic_connector=None,
+            speech_scaling_factor=torch.tensor(float("nan")), speech_bias_factor=torch.tensor(float("nan")))
+
+    # ---- construction ---------------------------------------------------------------------------------
+    def _ensure_engine(self, valid_ids):
+        if self.engine is None:
+            self.engine = Engine(self.config, valid_ids, self._max_batch, self._device_index, self._max_steps)
+            self.model.noise_scheduler = self.engine.scheduler
+        return self.engine
+
+    @staticmethod
+    def _valid_ids(tok) -> List[int]:
+        v = [tok.speech_start_id, tok.speech_end_id, tok.speech_diffusion_id, tok.eos_token_id]   # :405-413
+        if getattr(tok, "bos_token_id", None) is not None:
+            v.append(tok.bos_token_id)
+        return sorted(set(int(x) for x in v))
+
+    def load_state_dict(self, state_dict, tokenizer_ids=None, strict: bool = True):
+        """Same keys as the reference module tree (`modeling_vibevoice.py:119-142`)."""
+        tok = tokenizer_ids or self._tok
+        if tok is None:
+            raise ValueError("tokenizer ids (speech_start/end/diffusion/eos) are needed before weights are packed")
+        self._tok = tok
+        eng = self._ensure_engine(self._valid_ids(tok))
+        items = state_dict.items() if isinstance(state_dict, dict) else state_dict
+        scale = bias = None
+        for name, t in items:
+            if name == "model.speech_scaling_factor":
+                scale = float(t); self.model.speech_scaling_factor = torch.tensor(scale)
+            elif name == "model.speech_bias_factor":
+                bias = float(t); self.model.speech_bias_factor = torch.tensor(bias)
+            else:
+                eng.load_tensor(name, t)
+        eng.finalize(scale, bias)
+        return self
+
+    @classmethod
+    def from_pretrained(cls, path: str, torch_dtype=None, device_map=None, attn_implementation=None, tokenizer=None,
+                        max_batch: int = 1, **kw):
+        """HF checkpoint directory (config.json + *.safetensors), as `demo/inference_from_file.py:295-332` calls it.
+        `torch_dtype` / `attn_implementation` are accepted for drop-in compatibility; storage is bf16 and attention is
+        the built-in paged split-KV kernel."""
+        from safetensors import safe_open
+        cfg = VibeVoiceConfig.from_pretrained(path)
+        dev = 0
+        if isinstance(device_map, str) and device_map.startswith("cuda:"):
+            dev = int(device_map.split(":")[1])
+        if tokenizer is None:
+            from .synth import SynthTokenizer
+            tokenizer = SynthTokenizer(cfg.decoder_config.vocab_size)
+        m = cls(cfg, tokenizer, max_batch=max_batch, device=dev)
+
+        def it():
+            files = sorted(glob.glob(os.path.join(path, "*.safetensors")))
+            if not files:
+                raise FileNotFoundError("no *.safetensors under %s" % path)
+            for f in files:
+                with safe_open(f, framework="pt", device="cpu") as sf:
+                    for k in sf.keys():
+                        yield k, sf.get_tensor(k)
+        m.load_state_dict(it(), tokenizer)
+        return m
+
+    def eval(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    @property
+    def device(self):
+        return torch.device("cuda", self._device_index)
+
+    def set_ddpm_inference_steps(self, num_steps=None):
+        """`:146-147`."""
+        self.ddpm_inference_steps = num_steps or self.config.diffusion_head_config.ddpm_num_inference_steps
+
+    # ---- generate ----------------------------------------------------------------------------------------
+    def _reserve_kv(self, total_tokens: int):
+        eng = self.engine
+        if eng.kv_pages == 0:
+            eng.kv_init(total_tokens)
+        elif eng.kv_pages * 64 < total_tokens:
+            raise N.VVError("KV pool too small for this call: %d tokens needed, %d available; create the model with a "
+                            "larger first generate() or call engine.kv_init explicitly" % (total_tokens, eng.kv_pages * 64))
+
+    @torch.no_grad()
+    def generate(self, inputs=None, generation_config=None, logits_processor=None, stopping_criteria=None,
+                 prefix_allowed_tokens_fn=None, synced_gpus=None, assistant_model=None, audio_streamer=None,
+                 negative_prompt_ids=None, negative_prompt_attention_mask=None, speech_tensors=None, speech_masks=None,
+                 speech_input_mask=None, is_prefill: bool = True, return_speech: bool = True, cfg_scale: float = 1.0,
+                 stop_check_fn: Optional[Callable[[], bool]] = None, tqdm_class=None, **kwargs) -> VibeVoiceGenerationOutput:
+        """`modeling_vibevoice_inference.py:326-695` (greedy; `refresh_negative=True`)."""
+        tokenizer = kwargs.pop("tokenizer", None) or self._tok
+        kwargs.pop("parsed_scripts", None); kwargs.pop("all_speakers_list", None)
+        max_length_times = kwargs.pop("max_length_times", 2)
+        verbose = kwargs.get("verbose", False)
+        if generation_config is not None and dict(generation_config).get("do_sample", False):
+            raise NotImplementedError("do_sample=True (multinomial over the valid ids) is a 'next' row (SURVEY 8f-3)")
+        if not kwargs.get("refresh_negative", True):
+            raise NotImplementedError("refresh_negative=False is a 'next' row (SURVEY 8f-3)")
+        if is_prefill and speech_tensors is not None:
+            raise NotImplementedError("voice-prompt prefill (acoustic encoder, a-9) is not on the CUDA path yet; pass is_prefill=False")
+        forced: Optional[ForcedTokenScript] = None
+        if logits_processor is not None:
+            procs = logits_processor if isinstance(logits_processor, (list, tuple)) else [logits_processor]
+            for p in procs:
+                if isinstance(p, ForcedTokenScript):
+                    forced = p
+                else:
+                    raise NotImplementedError("arbitrary LogitsProcessor objects need full-vocab logits, which this path never "
+                                              "materialises; use ForcedTokenScript")
+        input_ids = kwargs["input_ids"] if "input_ids" in kwargs else inputs
+        input_ids = torch.as_tensor(input_ids).cpu().long()
+        attention_mask = kwargs.get("attention_mask", None)
+        attention_mask = torch.ones_like(input_ids) if attention_mask is None else torch.as_tensor(attention_mask).cpu().long()
+        eng = self.engine
+        if eng is None or not eng.finalized:
+            raise N.VVError("weights not loaded")
+        dc = self.config.decoder_config
+        b, L0 = input_ids.shape
+        B = eng.B
+        if b > B:
+            raise ValueError("batch %d exceeds the engine's max_batch %d" % (b, B))
+        tok = tokenizer
+        start_id, end_id, diff_id, eos_id = tok.speech_start_id, tok.speech_end_id, tok.speech_diffusion_id, tok.eos_token_id
+
+        if kwargs.get("max_new_tokens", None) is None:
+            kwargs["max_new_tokens"] = dc.max_position_embeddings - L0                      # :372-373
+        max_length = L0 + int(kwargs["max_new_tokens"])
+        init_len = attention_mask.sum(dim=-1)                                              # :402
+        max_steps = min(max_length - L0, int(max_length_times * L0))                       # :421
+        max_step_per_sample = torch.min(max_length - init_len, (max_length_times * init_len).long())   # :422
+        self._reserve_kv(int(b * (L0 + max_steps + 2) + b * (max_steps + 2)))
+        eng.set_diffusion_steps(int(self.ddpm_inference_steps))
+        eng.codec_state_reset()
+        for s in range(2 * B):
+            eng.kv_set_len(s, 0)
+
+        finished = np.zeros(B, dtype=bool); finished[b:] = True
+        reach_max = np.zeros(B, dtype=bool)
+        seqs = [input_ids[i].tolist() for i in range(b)]
+        audio_chunks: List[List[torch.Tensor]] = [[] for _ in range(b)]
+        pad_tok = eos_id
+
+        # ---- prompt prefill through the decode kernel (left-padded rows start late) ----------------------
+        lens = init_len.tolist() + [0] * (B - b)
+        Lmax = L0
+        for t in range(Lmax):
+            toks, adv = [], []
+            for r in range(B):
+                live = r < b and t >= Lmax - lens[r] and bool(attention_mask[r, t])
+                toks.append(int(input_ids[r, t]) if live else pad_tok)
+                adv.append(1 if live else 0)
+            last = t == Lmax - 1
+            eng.embed_tokens(toks + ([start_id] * B if last else toks), eng.embeds)          # neg rows: [<speech_start>] at pos 0 (:379-386)
+            eng.lm_decode()
+            if not last:
+                eng.kv_commit(adv + [0] * B)
+        pending_adv_pos = adv                                                               # committed once tokens are known
+
+        iterator = range(max_steps)
+        if kwargs.get("show_progress_bar", False):
+            from tqdm import tqdm
+            iterator = (tqdm_class or tqdm)(iterator, desc="Generating", leave=False)
+        step_done = False
+        for step in iterator:
+            if stop_check_fn is not None and stop_check_fn():                               # :434-440
+                if audio_streamer is not None:
+                    audio_streamer.end()
+                break
+            if audio_streamer is not None and hasattr(audio_streamer, "finished_flags") and any(audio_streamer.finished_flags):
+                break                                                                       # :443-447
+            if finished[:b].all():                                                          # :449-452
+                break
+            if len(seqs[0]) >= max_length:                                                  # :454-459
+                reach_max[:b] |= ~finished[:b]
+                break
+            if step > 0:
+                eng.lm_decode()                                                             # :480-482 (+ speculative negative rows)
+            toks_dev, _ = eng.read_tokens()
+            next_tokens = toks_dev.astype(np.int64).copy()
+            if forced is not None:
+                for r in range(b):
+                    next_tokens[r] = forced.token(r, step)
+            next_tokens[finished] = eos_id                                                   # :500
+            for r in range(b):
+                seqs[r].append(int(next_tokens[r]))                                          # :501
+            new_eos = (next_tokens == eos_id) & ~finished                                    # :519-528
+            if new_eos.any():
+                finished |= new_eos
+                if verbose:
+                    print(f"Samples {np.nonzero(new_eos)[0].tolist()} reached EOS token at step {step + 1}.", flush=True)
+                if audio_streamer is not None:
+                    audio_streamer.end(torch.as_tensor(np.nonzero(new_eos)[0]))
+            mlr = np.zeros(B, dtype=bool)
+            mlr[:b] = (step >= max_step_per_sample.numpy()) & ~finished[:b]                  # :531-539
+            if mlr.any():
+                finished |= mlr; reach_max |= mlr
+                if audio_streamer is not None:
+                    audio_streamer.end(torch.as_tensor(np.nonzero(mlr)[0]))
+            end_rows = np.nonzero(next_tokens[:b] == end_id)[0]                               # :542-546
+            if end_rows.size:
+                eng.codec_state_zero(end_rows.tolist())
+            start_rows = np.nonzero(~finished[:b] & (next_tokens[:b] == start_id))[0]         # :549-565
+            diff_mask = np.zeros(B, dtype=bool)
+            diff_mask[:b] = ~finished[:b] & (next_tokens[:b] == diff_id)                      # :573
+            diff_rows = np.nonzero(diff_mask)[0]
+            # KV bookkeeping: positive rows always keep their entry; negative rows only when the token is a diffusion token
+            adv_pos = pending_adv_pos if step == 0 else [1] * b + [0] * (B - b)
+            eng.kv_commit(list(adv_pos) + [1 if diff_mask[r] else 0 for r in range(B)])
+            for r in start_rows.tolist():
+                eng.kv_set_len(B + r, 0)                                                      # negative stream restarts at [<speech_start>]
+            tl = [int(t) for t in next_tokens]
+            eng.embed_tokens(tl + tl, eng.embeds)                                             # :569 (negative rows see the same input, :579-581)
+            if diff_rows.size:
+                n = int(diff_rows.size)
+                noise = torch.randn(2 * n, self.config.acoustic_vae_dim)[:n]                  # CPU global RNG, rows [:n] used (:701-704)
+                eng.upload_frame_inputs(noise, diff_rows.tolist())
+                eng.frame_tail(cfg_scale)                                                     # :626-672
+                with torch.cuda.stream(eng.stream):
+                    chunk = eng.audio[diff_rows.tolist()].clone()                              # [n, 3200]
+                for i, r in enumerate(diff_rows.tolist()):
+                    audio_chunks[r].append(chunk[i:i + 1])                                    # :646-650
+                if audio_streamer is not None:
+                    eng.sync()
+                    audio_streamer.put(chunk.unsqueeze(1), torch.as_tensor(diff_rows))         # :653-655
+        if audio_streamer is not None:
+            audio_streamer.end()                                                              # :677-678
+        eng.sync()
+        outs: List[Optional[torch.Tensor]] = []
+        with torch.cuda.stream(eng.stream):
+            for ch in audio_chunks:
+                outs.append(torch.cat(ch, dim=-1) if ch else None)                            # :680-689
+        eng.sync()
+        L = max(len(s) for s in seqs)
+        sequences = torch.tensor([s + [pad_tok] * (L - len(s)) for s in seqs], dtype=torch.long)
+        return VibeVoiceGenerationOutput(sequences=sequences, speech_outputs=outs if return_speech else None,
+                                         reach_max_step_sample=torch.as_tensor(reach_max[:b].copy()))
