@@ -179,8 +179,8 @@ def preset_config(name: str) -> VibeVoiceConfig:
         d["decoder_config"]["num_hidden_layers"] = 4 if big else 2
         d["decoder_config"]["head_dim"] = 128
         for k in ("acoustic_tokenizer_config", "semantic_tokenizer_config"):
-            d[k]["encoder_n_filters"] = 8 if big else 4
+            d[k]["encoder_n_filters"] = 16 if big else 8
             d[k]["encoder_depths"] = "2-1-1-1-1-1-2" if big else "1-1-1-1-1-1-2"
-        d["acoustic_tokenizer_config"]["decoder_n_filters"] = 8 if big else 4
+        d["acoustic_tokenizer_config"]["decoder_n_filters"] = 16 if big else 8
         return VibeVoiceConfig.from_dict(d)
     raise ValueError("unknown preset %r" % name)
