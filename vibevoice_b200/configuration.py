@@ -171,6 +171,10 @@ def preset_config(name: str) -> VibeVoiceConfig:
         return VibeVoiceConfig.from_dict(_preset(1536, 8960, 12, 2, 65536, 151936, True))
     if name in ("7b", "7B", "vibevoice-7b"):
         return VibeVoiceConfig.from_dict(_preset(3584, 18944, 28, 4, 32768, 152064, False))
+    if name in ("1.5b-l2", "7b-l2"):
+        d = _preset(1536, 8960, 12, 2, 65536, 4096, True) if name == "1.5b-l2" else _preset(3584, 18944, 28, 4, 32768, 4096, False)
+        d["decoder_config"]["num_hidden_layers"] = 2
+        return VibeVoiceConfig.from_dict(d)
     if name in ("tiny", "small"):
         # same topology (7 codec stages, ratios, GQA, 4 head layers), narrow widths
         big = name == "small"

@@ -112,8 +112,11 @@ VV_DEVINL void epi_store(const GemvP& p, int m, int n, float v) {
 
 // ---------------------------------------------------------------------------------------------
 // GEMV: y[m, n] = epi( sum_k W[n,k] * pro(x)[m,k] + bias[n] ),  M <= 16 (blocks of MB rows).
-// CTA = 8 warps arranged as WR row-quads x WK k-splits.  The staged activation block lives in
-// shared memory (fp32), weights stream from HBM straight into registers (16 B / lane / load).
+// CTA = 8 warps arranged as WR row-quads x WK k-splits; persistent over row-quad tasks.
+//  * weights stream from HBM straight into registers, 16 B / lane / load, software-pipelined one
+//    256-element chunk ahead; the first chunk of a CTA's first task is requested BEFORE the
+//    activation block is staged, so the HBM latency of the weights overlaps the prologue;
+//  * the staged activation block pro(x) lives in shared memory (fp32, bank-conflict-free planes).
 // ---------------------------------------------------------------------------------------------
 template <int MB>
 __global__ void __launch_bounds__(256) gemv_kernel(GemvP p) {
@@ -128,19 +131,43 @@ __global__ void __launch_bounds__(256) gemv_kernel(GemvP p) {
   const int WK = p.WK, WR = 8 / WK;
   const int wr = warp / WK, wk = warp % WK;
   const int ntasks = (N + 4 * WR - 1) / (4 * WR);
-  const int nchunks_full = K >> 8;
-  const bool has_tail = (K & 255) != 0;
+  const int nchunks = (K + 255) >> 8;
+  const int klane = lane * 8;
+
+  auto load_chunk = [&](uint4 (&wv)[4], const bf16* const (&wrow)[4], int c) {
+    if ((c << 8) + klane < K) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) wv[r] = ldg_stream(wrow[r] + (c << 8));
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) wv[r] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  auto set_rows = [&](const bf16* (&wrow)[4], int task) {
+    const int r0 = (task * WR + wr) * 4;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) wrow[r] = p.W + (size_t)min(r0 + r, N - 1) * K + klane;
+  };
 
   for (int m0 = 0; m0 < p.M; m0 += MB) {
     __syncthreads();
+    int task = blockIdx.x;
+    const bf16* wrow[4];
+    uint4 cur[4], nxt[4];
+    int c = wk;
+    if (task < ntasks) {
+      set_rows(wrow, task);
+      if (c < nchunks) load_chunk(cur, wrow, c);     // in flight while the activations are staged
+    }
     // ---- stage pro(x) for rows m0..m0+MB-1 ----
     const bool need_inv = (p.pro == PRO_RMSNORM || p.pro == PRO_ADALN);
+    const int K4 = K >> 2;
     if (need_inv) {
       for (int m = 0; m < MB; ++m) {
         float ss = 0.f;
         if (m0 + m < p.M) {
-          const float* xr = p.x + p.xmap.off(m0 + m);
-          for (int k = tid; k < K; k += 256) { float v = xr[k]; ss += v * v; }
+          const float4* xr = reinterpret_cast<const float4*>(p.x + p.xmap.off(m0 + m));
+          for (int q = tid; q < K4; q += 256) { const float4 v = xr[q]; ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
         }
         ss = warp_sum(ss);
         if (lane == 0) s_part[warp] = ss;
@@ -157,80 +184,69 @@ __global__ void __launch_bounds__(256) gemv_kernel(GemvP p) {
       const bool valid = (m0 + m < p.M);
       const float* xr = p.x + (valid ? p.xmap.off(m0 + m) : 0);
       const float inv = need_inv ? s_inv[m] : 1.f;
-      for (int k = tid; k < Kp; k += 256) {
-        float v = 0.f;
+      for (int q = tid; q < (Kp >> 2); q += 256) {
+        const int k = q << 2;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid && k < K) {
-          v = xr[k];
-          if (p.pro == PRO_RMSNORM) v = v * inv * p.pro_w[k];
-          else if (p.pro == PRO_ADALN) {
-            float w = p.pro_w ? p.pro_w[k] : 1.f;
-            long long o = (long long)(m0 + m) * p.pro_ld + k;
-            v = v * inv * w * (1.f + p.pro_scale[o]) + p.pro_shift[o];
-          } else if (p.pro == PRO_SILU) v = silu_f(v);
+          v = *reinterpret_cast<const float4*>(xr + k);
+          if (p.pro == PRO_RMSNORM) {
+            const float4 w = *reinterpret_cast<const float4*>(p.pro_w + k);
+            v.x *= inv * w.x; v.y *= inv * w.y; v.z *= inv * w.z; v.w *= inv * w.w;
+          } else if (p.pro == PRO_ADALN) {
+            float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (p.pro_w) w = *reinterpret_cast<const float4*>(p.pro_w + k);
+            const long long o = (long long)(m0 + m) * p.pro_ld + k;
+            const float4 sc = *reinterpret_cast<const float4*>(p.pro_scale + o);
+            const float4 sh = *reinterpret_cast<const float4*>(p.pro_shift + o);
+            v.x = v.x * inv * w.x * (1.f + sc.x) + sh.x; v.y = v.y * inv * w.y * (1.f + sc.y) + sh.y;
+            v.z = v.z * inv * w.z * (1.f + sc.z) + sh.z; v.w = v.w * inv * w.w * (1.f + sc.w) + sh.w;
+          } else if (p.pro == PRO_SILU) {
+            v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
+          }
         }
-        xs[m * Kp + xs_pos(k)] = v;
+        *reinterpret_cast<float4*>(xs + m * Kp + xs_pos(k)) = v;
       }
     }
     __syncthreads();
 
     int parity = 0;
-    for (int task = blockIdx.x; task < ntasks; task += gridDim.x, parity ^= 1) {
-      const int r0 = (task * WR + wr) * 4;
-      const bf16* wrow[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) wrow[r] = p.W + (size_t)min(r0 + r, N - 1) * K + lane * 8;
+    while (task < ntasks) {
       float acc[4][MB];
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int m = 0; m < MB; ++m) acc[r][m] = 0.f;
-
-      if (r0 < N) {
-#pragma unroll 2
-        for (int c = wk; c < nchunks_full; c += WK) {
-          uint4 wv[4];
+      while (c < nchunks) {
+        const int cn = c + WK;
+        if (cn < nchunks) load_chunk(nxt, wrow, cn);
+        float xv[MB][8];
 #pragma unroll
-          for (int r = 0; r < 4; ++r) wv[r] = ldg_stream(wrow[r] + (c << 8));
-          float xv[MB][8];
-#pragma unroll
-          for (int m = 0; m < MB; ++m) {
-            const float4 a = *reinterpret_cast<const float4*>(xs + m * Kp + (c << 8) + (lane << 2));
-            const float4 b = *reinterpret_cast<const float4*>(xs + m * Kp + (c << 8) + 128 + (lane << 2));
-            xv[m][0] = a.x; xv[m][1] = a.y; xv[m][2] = a.z; xv[m][3] = a.w;
-            xv[m][4] = b.x; xv[m][5] = b.y; xv[m][6] = b.z; xv[m][7] = b.w;
-          }
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            float wf[8];
-            bf16x8_unpack(wv[r], wf);
-#pragma unroll
-            for (int m = 0; m < MB; ++m)
-#pragma unroll
-              for (int j = 0; j < 8; ++j) acc[r][m] = fmaf(wf[j], xv[m][j], acc[r][m]);
-          }
+        for (int m = 0; m < MB; ++m) {
+          const float4 a = *reinterpret_cast<const float4*>(xs + m * Kp + (c << 8) + (lane << 2));
+          const float4 b = *reinterpret_cast<const float4*>(xs + m * Kp + (c << 8) + 128 + (lane << 2));
+          xv[m][0] = a.x; xv[m][1] = a.y; xv[m][2] = a.z; xv[m][3] = a.w;
+          xv[m][4] = b.x; xv[m][5] = b.y; xv[m][6] = b.z; xv[m][7] = b.w;
         }
-        if (has_tail && wk == (nchunks_full % WK)) {
-          const int c = nchunks_full;
-          if ((c << 8) + lane * 8 < K) {
-            uint4 wv[4];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) wv[r] = ldg_stream(wrow[r] + (c << 8));
+        for (int r = 0; r < 4; ++r) {
+          float wf[8];
+          bf16x8_unpack(cur[r], wf);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              float wf[8];
-              bf16x8_unpack(wv[r], wf);
+          for (int m = 0; m < MB; ++m)
 #pragma unroll
-              for (int m = 0; m < MB; ++m) {
-                const float4 a = *reinterpret_cast<const float4*>(xs + m * Kp + (c << 8) + (lane << 2));
-                const float4 b = *reinterpret_cast<const float4*>(xs + m * Kp + (c << 8) + 128 + (lane << 2));
-                acc[r][m] = fmaf(wf[0], a.x, acc[r][m]); acc[r][m] = fmaf(wf[1], a.y, acc[r][m]);
-                acc[r][m] = fmaf(wf[2], a.z, acc[r][m]); acc[r][m] = fmaf(wf[3], a.w, acc[r][m]);
-                acc[r][m] = fmaf(wf[4], b.x, acc[r][m]); acc[r][m] = fmaf(wf[5], b.y, acc[r][m]);
-                acc[r][m] = fmaf(wf[6], b.z, acc[r][m]); acc[r][m] = fmaf(wf[7], b.w, acc[r][m]);
-              }
-            }
-          }
+            for (int j = 0; j < 8; ++j) acc[r][m] = fmaf(wf[j], xv[m][j], acc[r][m]);
         }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) cur[r] = nxt[r];
+        c = cn;
+      }
+      // next task's first chunk goes out before this task's reduction
+      const int this_task = task;
+      task += gridDim.x;
+      c = wk;
+      if (task < ntasks) {
+        set_rows(wrow, task);
+        if (c < nchunks) load_chunk(cur, wrow, c);
       }
       // ---- reduce: lanes -> lane 0; k-split warps -> shared ----
 #pragma unroll
@@ -249,7 +265,7 @@ __global__ void __launch_bounds__(256) gemv_kernel(GemvP p) {
       if (p.epi == EPI_SWIGLU) {
         if (tid < WR * 2 * MB) {
           const int q = tid / (2 * MB), pr = (tid / MB) % 2, m = tid % MB;
-          const int n0 = (task * WR + q) * 4 + pr * 2;
+          const int n0 = (this_task * WR + q) * 4 + pr * 2;
           if (n0 + 1 < N && m0 + m < p.M) {
             float g = 0.f, u = 0.f;
             for (int s = 0; s < WK; ++s) {
@@ -263,7 +279,7 @@ __global__ void __launch_bounds__(256) gemv_kernel(GemvP p) {
       } else {
         if (tid < WR * 4 * MB) {
           const int q = tid / (4 * MB), r = (tid / MB) % 4, m = tid % MB;
-          const int n = (task * WR + q) * 4 + r;
+          const int n = (this_task * WR + q) * 4 + r;
           if (n < N && m0 + m < p.M) {
             float v = 0.f;
             for (int s = 0; s < WK; ++s) v += rbuf[(q * WK + s) * (4 * MB) + r * MB + m];
@@ -272,6 +288,7 @@ __global__ void __launch_bounds__(256) gemv_kernel(GemvP p) {
           }
         }
       }
+      parity ^= 1;
       // double-buffered `red`: the next task writes the other half, the one after is fenced by
       // the next __syncthreads, so no trailing barrier is needed here.
     }
@@ -336,6 +353,124 @@ __global__ void __launch_bounds__(256) gemm_tiled_kernel(GemvP p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core GEMM for the codec stages with many rows (M > 8): C[M,N] = A[M,K] * W[N,K]^T.
+// A is fp32 in global memory and is split on the fly into bf16 hi + bf16 lo (A = hi + lo up to
+// 2^-16 relative), W is bf16, so two bf16 MMAs per tile reproduce the fp32-activation result of
+// the GEMV path to ~1e-5 while running on the tensor pipe.  CTA tile 32 x 64 x 64, 4 warps, W
+// streamed with a 3-stage cp.async ring, A register-prefetched one k-step ahead.
+// (mma.sync m16n8k16; the tcgen05/TMEM version of this kernel is the planned replacement.)
+// ---------------------------------------------------------------------------------------------
+VV_DEVINL void cp_async16(void* smem, const void* gmem, int src_bytes) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gmem), "r"(src_bytes));
+}
+VV_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+template <int N_> VV_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_)); }
+VV_DEVINL void ldmatrix_x4(unsigned (&r)[4], const void* smem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(sa));
+}
+VV_DEVINL void mma_bf16_16816(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+VV_DEVINL unsigned pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<unsigned*>(&v);
+}
+
+constexpr int MM_BM = 32, MM_BN = 64, MM_BK = 64, MM_ST = 3, MM_LD = MM_BK + 8;   // +8 bf16 = 16 B row pad (ldmatrix conflict-free)
+__global__ void __launch_bounds__(128) gemm_mma_kernel(GemvP p) {
+  __shared__ __align__(16) bf16 Ah[MM_BM][MM_LD];
+  __shared__ __align__(16) bf16 Al[MM_BM][MM_LD];
+  __shared__ __align__(16) bf16 Ws[MM_ST][MM_BN][MM_LD];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bm = blockIdx.y * MM_BM, bn = blockIdx.x * MM_BN;
+  const int K = p.K, nk = (K + MM_BK - 1) / MM_BK;
+  // A loader: thread -> row tid/4, 16 consecutive k at (tid%4)*16
+  const int ar = tid >> 2, ac = (tid & 3) * 16;
+  const float* arow = (bm + ar < p.M) ? p.x + p.xmap.off(bm + ar) : nullptr;
+  // W loader: 64 rows x 64 k bf16 = 512 x 16 B; thread handles 4 of them
+  auto load_w = [&](int stage, int kt) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 128, r = idx >> 3, c = (idx & 7) * 8;
+      const int n = bn + r, k = kt * MM_BK + c;
+      const bool ok = (n < p.N) && (k < K);
+      cp_async16(&Ws[stage][r][c], p.W + (size_t)(ok ? n : 0) * K + (ok ? k : 0), ok ? 16 : 0);
+    }
+  };
+  float4 areg[4];
+  auto load_a = [&](int kt) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = kt * MM_BK + ac + i * 4;
+      areg[i] = (arow && k < K) ? *reinterpret_cast<const float4*>(arow + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto store_a = [&]() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float v[4] = {areg[i].x, areg[i].y, areg[i].z, areg[i].w};
+      float h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { h[j] = __bfloat162float(__float2bfloat16_rn(v[j])); l[j] = v[j] - h[j]; }
+      *reinterpret_cast<uint2*>(&Ah[ar][ac + i * 4]) = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
+      *reinterpret_cast<uint2*>(&Al[ar][ac + i * 4]) = make_uint2(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]));
+    }
+  };
+  float acc[2][2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+
+#pragma unroll
+  for (int s_ = 0; s_ < MM_ST - 1; ++s_) { if (s_ < nk) load_w(s_, s_); cp_async_commit(); }
+  load_a(0);
+  for (int kt = 0; kt < nk; ++kt) {
+    __syncthreads();                       // previous step's readers of Ah/Al and of the stage about to be refilled are done
+    store_a();
+    if (kt + MM_ST - 1 < nk) load_w((kt + MM_ST - 1) % MM_ST, kt + MM_ST - 1);
+    cp_async_commit();
+    if (kt + 1 < nk) load_a(kt + 1);
+    cp_async_wait<MM_ST - 1>();            // stage kt has landed
+    __syncthreads();
+    const int st = kt % MM_ST;
+#pragma unroll
+    for (int kk = 0; kk < MM_BK; kk += 16) {
+      unsigned ah[2][4], al[2][4], bw[4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        ldmatrix_x4(ah[mt], &Ah[mt * 16 + (lane & 15)][kk + (lane >> 4) * 8]);
+        ldmatrix_x4(al[mt], &Al[mt * 16 + (lane & 15)][kk + (lane >> 4) * 8]);
+      }
+      // B fragments for this warp's two n-tiles (16 rows of W): lanes 0-7 n0..7 @k, 8-15 n0..7 @k+8, 16-23 n8..15 @k, 24-31 n8..15 @k+8
+      ldmatrix_x4(bw, &Ws[st][warp * 16 + (lane & 7) + ((lane >> 4) << 3)][kk + ((lane >> 3) & 1) * 8]);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma_bf16_16816(acc[mt][0], ah[mt], bw[0], bw[1]);
+        mma_bf16_16816(acc[mt][0], al[mt], bw[0], bw[1]);
+        mma_bf16_16816(acc[mt][1], ah[mt], bw[2], bw[3]);
+        mma_bf16_16816(acc[mt][1], al[mt], bw[2], bw[3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int m = bm + mt * 16 + (lane >> 2) + (q >> 1) * 8;
+        const int n = bn + warp * 16 + nt * 8 + (lane & 3) * 2 + (q & 1);
+        if (m < p.M && n < p.N) epi_store(p, m, n, acc[mt][nt][q] + (p.bias ? p.bias[n] : 0.f));
+      }
+}
+
 // thread-per-output small-K product with fp32 weights (encoder stem conv 1->32 k7, decoder head conv 32->1 k7)
 __global__ void conv_naive_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ x,
                                   RowMap xmap, float* __restrict__ y, int M, int N, int K) {
@@ -397,6 +532,58 @@ __global__ void assemble_window_kernel(const float* __restrict__ src, const floa
       if (hn) hn[c] = v;
     }
   }
+}
+
+// block-per-row variants for wide channels (C >= 512, few rows): the single-warp versions are a latency chain
+__global__ void __launch_bounds__(256) assemble_window_block_kernel(const float* __restrict__ src, const float* __restrict__ hist,
+                                                                    float* __restrict__ win, float* __restrict__ hist_next, int B, int T,
+                                                                    int ctx, int C, const float* __restrict__ norm_w, float eps, float alpha,
+                                                                    float beta) {
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const int R = ctx + T;
+  const int b = row / R, j = row % R;
+  float* wr = win + ((size_t)b * R + j) * C;
+  float* hn = (j >= T) ? hist_next + ((size_t)b * ctx + (j - T)) * C : nullptr;
+  __shared__ float sp[8];
+  if (j < ctx) {
+    const float* hr = hist + ((size_t)b * ctx + j) * C;
+    for (int c = tid; c < C; c += 256) { float v = hr[c]; wr[c] = v; if (hn) hn[c] = v; }
+  } else {
+    const float* sr = src + ((size_t)b * T + (j - ctx)) * C;
+    float inv = 1.f;
+    if (norm_w) {
+      float ss = 0.f;
+      for (int c = tid; c < C; c += 256) { float v = sr[c]; ss += v * v; }
+      ss = warp_sum(ss);
+      if ((tid & 31) == 0) sp[tid >> 5] = ss;
+      __syncthreads();
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += sp[i];
+      inv = rsqrtf(t / (float)C + eps);
+    }
+    for (int c = tid; c < C; c += 256) {
+      float v = norm_w ? sr[c] * inv * norm_w[c] : sr[c] * alpha + beta;
+      wr[c] = v;
+      if (hn) hn[c] = v;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) rows_norm_block_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
+                                                              int C, float eps) {
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const float* xr = x + (size_t)row * C;
+  __shared__ float sp[8];
+  float ss = 0.f;
+  for (int c = tid; c < C; c += 256) { float v = xr[c]; ss += v * v; }
+  ss = warp_sum(ss);
+  if ((tid & 31) == 0) sp[tid >> 5] = ss;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += sp[i];
+  const float inv = rsqrtf(t / (float)C + eps);
+  for (int c = tid; c < C; c += 256) y[(size_t)row * C + c] = xr[c] * inv * (w ? w[c] : 1.f);
 }
 
 // out = x + gamma * (bias + sum_j w[j][c] * win[t+j][c])   (depthwise causal conv k=7 + layer scale + residual)
@@ -480,7 +667,8 @@ __global__ void rope_append_kernel(const float* __restrict__ qkv, float* __restr
   }
 }
 
-// split-KV partial attention: CTA = (split, kv head, sequence); 4 warps; 32-token tiles staged in smem.
+// split-KV partial attention: CTA = (split, kv head, sequence); 4 warps; 32-token K/V tiles double-buffered in
+// shared memory with cp.async so the next tile streams from HBM while the current one is being consumed.
 constexpr int ATT_TILE = 32;
 constexpr int ATT_MAXG = 8;     // q heads per kv head (6 for 1.5B, 7 for 7B)
 __global__ void __launch_bounds__(128) attn_partial_kernel(const float* __restrict__ q_rot, KvView kv, float* __restrict__ part_acc,
@@ -494,30 +682,36 @@ __global__ void __launch_bounds__(128) attn_partial_kernel(const float* __restri
   const int t_begin = s * tps, t_end = min(ntiles, (s + 1) * tps);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  __shared__ __align__(16) bf16 Ks[ATT_TILE][HD + 8];
-  __shared__ __align__(16) bf16 Vs[ATT_TILE][HD + 8];
+  __shared__ __align__(16) bf16 Ks[2][ATT_TILE][HD + 8];
+  __shared__ __align__(16) bf16 Vs[2][ATT_TILE][HD + 8];
   __shared__ __align__(16) float qs[ATT_MAXG][HD];
   __shared__ float ps[ATT_MAXG][ATT_TILE];
 
+  auto prefetch = [&](int t, int buf) {
+    const int tok0 = t * ATT_TILE;
+    const int page = kv.page_table[(size_t)m * kv.max_pages + tok0 / KV_PAGE];
+    const size_t base = (((size_t)page * kv.kv_heads + g) * KV_PAGE + (tok0 % KV_PAGE)) * HD;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int idx = tid + it * 128;
+      const int r = idx >> 4, c = (idx & 15) * 8;
+      cp_async16(&Ks[buf][r][c], kv.kpool + base + (size_t)r * HD + c, 16);
+      cp_async16(&Vs[buf][r][c], kv.vpool + base + (size_t)r * HD + c, (tok0 + r < L) ? 16 : 0);   // zero-fill beyond the sequence
+    }
+  };
+  if (t_begin < t_end) prefetch(t_begin, 0);
+  cp_async_commit();
   for (int i = tid; i < G * HD; i += 128) qs[i / HD][i % HD] = q_rot[((size_t)m * kv.q_heads + g * G) * HD + i];
 
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 
   for (int t = t_begin; t < t_end; ++t) {
+    const int buf = (t - t_begin) & 1;
     const int tok0 = t * ATT_TILE;
-    const int page = kv.page_table[(size_t)m * kv.max_pages + tok0 / KV_PAGE];
-    const size_t base = (((size_t)page * kv.kv_heads + g) * KV_PAGE + (tok0 % KV_PAGE)) * HD;
-    __syncthreads();
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      const int idx = tid + it * 128;
-      const int r = idx >> 4, c = (idx & 15) * 8;
-      uint4 kk = ldg_stream(kv.kpool + base + (size_t)r * HD + c);
-      uint4 vv = (tok0 + r < L) ? ldg_stream(kv.vpool + base + (size_t)r * HD + c) : make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(&Ks[r][c]) = kk;
-      *reinterpret_cast<uint4*>(&Vs[r][c]) = vv;
-    }
+    if (t + 1 < t_end) prefetch(t + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
 #pragma unroll
     for (int hh = 0; hh < 2; ++hh) {
@@ -527,7 +721,7 @@ __global__ void __launch_bounds__(128) attn_partial_kernel(const float* __restri
 #pragma unroll
       for (int c = 0; c < HD; c += 8) {
         float kf[8];
-        bf16x8_unpack(*reinterpret_cast<const uint4*>(&Ks[lane][c]), kf);
+        bf16x8_unpack(*reinterpret_cast<const uint4*>(&Ks[buf][lane][c]), kf);
         const float4 qa = *reinterpret_cast<const float4*>(&qs[h][c]);
         const float4 qb = *reinterpret_cast<const float4*>(&qs[h][c + 4]);
         sc = fmaf(kf[0], qa.x, sc); sc = fmaf(kf[1], qa.y, sc); sc = fmaf(kf[2], qa.z, sc); sc = fmaf(kf[3], qa.w, sc);
@@ -547,7 +741,7 @@ __global__ void __launch_bounds__(128) attn_partial_kernel(const float* __restri
 #pragma unroll 8
       for (int tt = 0; tt < ATT_TILE; ++tt) {
         const float pv = ps[h][tt];
-        const uint2 v2 = *reinterpret_cast<const uint2*>(&Vs[tt][lane * 4]);
+        const uint2 v2 = *reinterpret_cast<const uint2*>(&Vs[buf][tt][lane * 4]);
         acc[hh][0] = fmaf(pv, __uint_as_float(v2.x << 16), acc[hh][0]);
         acc[hh][1] = fmaf(pv, __uint_as_float(v2.x & 0xffff0000u), acc[hh][1]);
         acc[hh][2] = fmaf(pv, __uint_as_float(v2.y << 16), acc[hh][2]);
@@ -555,6 +749,7 @@ __global__ void __launch_bounds__(128) attn_partial_kernel(const float* __restri
       }
       __syncwarp();
     }
+    __syncthreads();    // everyone is done with `buf` before the prefetch of tile t+2 overwrites it
   }
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
@@ -567,22 +762,36 @@ __global__ void __launch_bounds__(128) attn_partial_kernel(const float* __restri
   }
 }
 
+// merge the split partials: weights computed once per (row, head) in shared memory, then a flat weighted sum
 __global__ void __launch_bounds__(128) attn_combine_kernel(const float* __restrict__ part_acc, const float* __restrict__ part_ml,
                                                            const int* __restrict__ row_mode, float* __restrict__ out, int q_heads,
                                                            int nsplit) {
   const int h = blockIdx.x, m = blockIdx.y, d = threadIdx.x;
   if (!row_mode[m]) return;
   const size_t o = ((size_t)m * q_heads + h) * nsplit;
+  __shared__ float wsh[512];
+  __shared__ float red[4];
   float mx = -INFINITY;
-  for (int s = 0; s < nsplit; ++s) mx = fmaxf(mx, part_ml[(o + s) * 2]);
-  float num = 0.f, den = 0.f;
-  for (int s = 0; s < nsplit; ++s) {
+  for (int s = d; s < nsplit; s += 128) mx = fmaxf(mx, part_ml[(o + s) * 2]);
+  mx = warp_max(mx);
+  if ((d & 31) == 0) red[d >> 5] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float den = 0.f;
+  for (int s = d; s < nsplit; s += 128) {
     const float ms = part_ml[(o + s) * 2];
-    if (ms == -INFINITY) continue;
-    const float w = __expf(ms - mx);
-    num = fmaf(w, part_acc[(o + s) * HD + d], num);
+    const float w = (ms == -INFINITY) ? 0.f : __expf(ms - mx);
+    wsh[s] = w;
     den = fmaf(w, part_ml[(o + s) * 2 + 1], den);
   }
+  den = warp_sum(den);
+  if ((d & 31) == 0) red[d >> 5] = den;
+  __syncthreads();
+  den = red[0] + red[1] + red[2] + red[3];
+  float num = 0.f;
+#pragma unroll 8
+  for (int s = 0; s < nsplit; ++s) num = fmaf(wsh[s], part_acc[(o + s) * HD + d], num);
   out[((size_t)m * q_heads + h) * HD + d] = num / den;
 }
 
@@ -646,7 +855,10 @@ struct DpmCoef { float a0, s0, ks, kx, rinv; int order; };
 // Step `i` CFG + DPM-Solver++(2M) update of z from the head output v of step i, then (optionally)
 // the projection x = noisy_images_proj(z') for the next head evaluation, rows b and B+b.
 //   v = v_u + s (v_c - v_u); x0 = a0 z - s0 v; z' = ks z - kx x0 [- 0.5 kx rinv (x0 - x0_prev)]
-__global__ void __launch_bounds__(256) dpm_update_proj_kernel(float* __restrict__ z, float* __restrict__ x0_prev,
+// grid (B, H/256): every CTA recomputes the 64-element update from the read-only (z_in, x0_in) pair,
+// CTA y==0 publishes (z_out, x0_out); the ping-pong removes the cross-CTA read/write hazard.
+__global__ void __launch_bounds__(256) dpm_update_proj_kernel(const float* __restrict__ z_in, float* __restrict__ z_out,
+                                                              const float* __restrict__ x0_in, float* __restrict__ x0_out,
                                                               const float* __restrict__ v, const float* __restrict__ noise,
                                                               const DpmCoef* __restrict__ coef, int step, float cfg,
                                                               const bf16* __restrict__ w_noisy /*[H][64]*/, float* __restrict__ xout,
@@ -654,26 +866,29 @@ __global__ void __launch_bounds__(256) dpm_update_proj_kernel(float* __restrict_
   const int b = blockIdx.x, tid = threadIdx.x;
   __shared__ float zs[64];
   if (tid < 64) {
-    float zn;
+    float zn, x0 = 0.f;
     if (step < 0) {
       zn = noise[b * 64 + tid];                           // z_0 = CPU-RNG noise (:701)
     } else {
       const DpmCoef c = coef[step];
       const float vc = v[(size_t)b * 64 + tid], vu = v[(size_t)(B + b) * 64 + tid];
       const float vv = vu + cfg * (vc - vu);
-      const float zo = z[b * 64 + tid];
-      const float x0 = c.a0 * zo - c.s0 * vv;
+      const float zo = z_in[b * 64 + tid];
+      x0 = c.a0 * zo - c.s0 * vv;
       zn = c.ks * zo - c.kx * x0;
-      if (c.order == 2) zn -= 0.5f * c.kx * (c.rinv * (x0 - x0_prev[b * 64 + tid]));
-      x0_prev[b * 64 + tid] = x0;
+      if (c.order == 2) zn -= 0.5f * c.kx * (c.rinv * (x0 - x0_in[b * 64 + tid]));
     }
-    z[b * 64 + tid] = zn;
     zs[tid] = zn;
-    if (latent_out) latent_out[b * 64 + tid] = zn;
+    if (blockIdx.y == 0) {
+      z_out[b * 64 + tid] = zn;
+      x0_out[b * 64 + tid] = x0;
+      if (latent_out) latent_out[b * 64 + tid] = zn;
+    }
   }
   __syncthreads();
   if (!do_proj) return;
-  for (int n = tid; n < H; n += 256) {
+  const int n = blockIdx.y * 256 + tid;
+  if (n < H) {
     const uint4* wr = reinterpret_cast<const uint4*>(w_noisy + (size_t)n * 64);
     float acc = 0.f;
 #pragma unroll

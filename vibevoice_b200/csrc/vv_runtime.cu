@@ -160,19 +160,22 @@ static int gemv_occupancy(vv_ctx* c, int smem) {
 // y = epi(W * pro(x) + bias); dispatches GEMV (M <= 16) or the tiled GEMM.
 static int linear(const L& l, GemvP p) {
   if (p.K % 8 != 0) return fail(VV_ERR_INVALID, "linear: K=%d not a multiple of 8", p.K);
-  if (p.M > 16) {
-    if (p.pro != PRO_NONE || p.epi == EPI_SWIGLU) return fail(VV_ERR_INVALID, "gemm_tiled: prologue/swiglu unsupported");
-    dim3 grid((p.N + 63) / 64, (p.M + 63) / 64);
-    gemm_tiled_kernel<<<grid, 256, 0, l.s>>>(p);
+  if (((uintptr_t)p.x & 15) || (p.xmap.rs & 3) || (p.xmap.bs & 3)) return fail(VV_ERR_INVALID, "linear: activation rows must be 16-byte aligned");
+  if (p.M > 8 && p.pro == PRO_NONE && p.epi != EPI_SWIGLU) {
+    dim3 grid((p.N + MM_BN - 1) / MM_BN, (p.M + MM_BM - 1) / MM_BM);
+    gemm_mma_kernel<<<grid, 128, 0, l.s>>>(p);
     CKL();
     l.c->launches++;
     return 0;
   }
+  if (p.M > 16) return fail(VV_ERR_INVALID, "linear: M=%d > 16 needs PRO_NONE and a non-SWIGLU epilogue", p.M);
   int MB = p.M <= 1 ? 1 : (p.M <= 2 ? 2 : (p.M <= 4 ? 4 : 8));
   while (MB > 1 && gemv_smem_bytes(MB, p.K) > 200 * 1024) MB >>= 1;
   if (gemv_smem_bytes(MB, p.K) > 200 * 1024) return fail(VV_ERR_INVALID, "gemv: K=%d too large", p.K);
   int WR = 8;
   while (WR > 1 && (p.N + 4 * WR - 1) / (4 * WR) < 2 * l.c->sm_count) WR >>= 1;
+  const int nchunks = (p.K + 255) / 256;
+  while (WR < 8 && 8 / WR > nchunks) WR <<= 1;      // never more k-split warps than 256-element chunks
   p.WK = 8 / WR;
   const int ntasks = (p.N + 4 * WR - 1) / (4 * WR);
   const int smem = gemv_smem_bytes(MB, p.K);
@@ -588,8 +591,8 @@ extern "C" int vv_finalize_weights(vv_ctx* c) {
     RET(dmalloc(c, &c->s_hx, (size_t)M2 * H));
     RET(dmalloc(c, &c->s_hg, (size_t)M2 * F));
     RET(dmalloc(c, &c->s_v, (size_t)M2 * 64));
-    RET(dmalloc(c, &c->s_z, (size_t)B * 64));
-    RET(dmalloc(c, &c->s_x0, (size_t)B * 64));
+    RET(dmalloc(c, &c->s_z, (size_t)2 * B * 64));
+    RET(dmalloc(c, &c->s_x0, (size_t)2 * B * 64));
   }
   // ---------------- connectors ----------------
   {
@@ -869,7 +872,8 @@ static int enqueue_lm_decode(const L& l, const float* embeds, float* hidden, flo
     p.epi = EPI_RESID; p.res = c->s_h; p.ldres = H;
     RET(linear(l, p));
   }
-  rows_norm_kernel<<<(M + 7) / 8, 256, 0, l.s>>>(c->s_h, c->lm_norm, hidden, M, H, d.rms_norm_eps);
+  if (H >= 512) rows_norm_block_kernel<<<M, 256, 0, l.s>>>(c->s_h, c->lm_norm, hidden, H, d.rms_norm_eps);
+  else rows_norm_kernel<<<(M + 7) / 8, 256, 0, l.s>>>(c->s_h, c->lm_norm, hidden, M, H, d.rms_norm_eps);
   CKL();
   c->launches++;
   return enqueue_lm_head(l, hidden, logits, tokens);
@@ -956,7 +960,8 @@ static int enqueue_diffusion(const L& l, const float* cond, const float* noise, 
     const long long n = (long long)N * M * H;
     head_cond_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, l.s>>>(c->s_condp, c->temb, c->s_call, N, M, H);
     CKL();
-    dpm_update_proj_kernel<<<B, 256, 0, l.s>>>(c->s_z, c->s_x0, c->s_v, noise, c->coef_dev, -1, cfg, c->h_noisy, c->s_hx, nullptr, B, H, 1);
+    dpm_update_proj_kernel<<<dim3(B, (H + 255) / 256), 256, 0, l.s>>>(c->s_z + B * 64, c->s_z, c->s_x0 + B * 64, c->s_x0, c->s_v, noise,
+                                                                       c->coef_dev, -1, cfg, c->h_noisy, c->s_hx, nullptr, B, H, 1);
     CKL();
     c->launches += 2;
   }
@@ -979,8 +984,12 @@ static int enqueue_diffusion(const L& l, const float* cond, const float* noise, 
     p.pro_shift = c->s_mod + (size_t)LH * 3 * H; p.pro_scale = c->s_mod + (size_t)LH * 3 * H + H; p.pro_ld = modld;
     RET(linear(l, p));
     const bool last = (i == N - 1);
-    dpm_update_proj_kernel<<<B, 256, 0, l.s>>>(c->s_z, c->s_x0, c->s_v, noise, c->coef_dev, i, cfg, c->h_noisy, c->s_hx,
-                                               last ? latent_out : nullptr, B, H, last ? 0 : 1);
+    {
+      float *zi = c->s_z + (size_t)(i & 1) * B * 64, *zo = c->s_z + (size_t)((i + 1) & 1) * B * 64;
+      float *xi = c->s_x0 + (size_t)(i & 1) * B * 64, *xo = c->s_x0 + (size_t)((i + 1) & 1) * B * 64;
+      dpm_update_proj_kernel<<<dim3(B, last ? 1 : (H + 255) / 256), 256, 0, l.s>>>(zi, zo, xi, xo, c->s_v, noise, c->coef_dev, i, cfg, c->h_noisy,
+                                                                                  c->s_hx, last ? latent_out : nullptr, B, H, last ? 0 : 1);
+    }
     CKL();
     c->launches++;
   }
@@ -1003,7 +1012,8 @@ extern "C" int vv_diffusion_sample(vv_ctx* c, const float* cond, const float* no
 static int assemble(const L& l, const float* src, const float* hist, float* win, float* next, int B, int T, int ctx, int C,
                     const float* norm_w, float eps, float alpha, float beta) {
   const int rows = B * (ctx + T);
-  assemble_window_kernel<<<(rows + 7) / 8, 256, 0, l.s>>>(src, hist, win, next, B, T, ctx, C, norm_w, eps, alpha, beta);
+  if (C >= 512) assemble_window_block_kernel<<<rows, 256, 0, l.s>>>(src, hist, win, next, B, T, ctx, C, norm_w, eps, alpha, beta);
+  else assemble_window_kernel<<<(rows + 7) / 8, 256, 0, l.s>>>(src, hist, win, next, B, T, ctx, C, norm_w, eps, alpha, beta);
   CKL();
   l.c->launches++;
   return 0;
@@ -1021,12 +1031,13 @@ static int enqueue_block(const L& l, const Block& b, const float* xin, float* xo
     c->launches++;
   }
   GemvP p;
-  if (M <= 16) {
+  if (M <= 8) {
     p = mk(b.w1, b.b1, xout, C, c->s_u, 4 * C, M, 4 * C, C);
     p.pro = PRO_RMSNORM; p.pro_w = b.ffn_norm_w; p.pro_eps = eps; p.epi = EPI_GELU;
     RET(linear(l, p));
   } else {
-    rows_norm_kernel<<<(M + 7) / 8, 256, 0, l.s>>>(xout, b.ffn_norm_w, c->s_xn, M, C, eps);
+    if (C >= 512) rows_norm_block_kernel<<<M, 256, 0, l.s>>>(xout, b.ffn_norm_w, c->s_xn, C, eps);
+    else rows_norm_kernel<<<(M + 7) / 8, 256, 0, l.s>>>(xout, b.ffn_norm_w, c->s_xn, M, C, eps);
     CKL();
     c->launches++;
     p = mk(b.w1, b.b1, c->s_xn, C, c->s_u, 4 * C, M, 4 * C, C);

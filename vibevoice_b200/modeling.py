@@ -54,8 +54,11 @@ class ForcedTokenScript:
 
 class VibeVoiceForConditionalGenerationInference:
     def __init__(self, config: VibeVoiceConfig, tokenizer_ids=None, max_batch: int = 1, device: int = 0,
-                 max_diffusion_steps: int = 64):
+                 max_diffusion_steps: int = 64, torch_prefill: bool = False):
         self.config = config
+        self._torch_prefill = torch_prefill      # keep bf16 LM weights for the PyTorch prompt prefill (prefill.py)
+        self._prefill = None
+        self._lm_sd: Dict[str, torch.Tensor] = {}
         self._tok = tokenizer_ids
         self._device_index = device
         self._max_batch = max_batch
@@ -101,7 +104,12 @@ class VibeVoiceForConditionalGenerationInference:
                 bias = float(t); self.model.speech_bias_factor = torch.tensor(bias)
             else:
                 eng.load_tensor(name, t)
+                if self._torch_prefill and name.startswith("model.language_model."):
+                    self._lm_sd[name] = t.to(device=eng.device, dtype=torch.bfloat16)
         eng.finalize(scale, bias)
+        if self._torch_prefill:
+            from .prefill import TorchPrefill
+            self._prefill = TorchPrefill(self.config, self._lm_sd, eng.device)
         return self
 
     @classmethod
@@ -213,21 +221,40 @@ class VibeVoiceForConditionalGenerationInference:
         audio_chunks: List[List[torch.Tensor]] = [[] for _ in range(b)]
         pad_tok = eos_id
 
-        # ---- prompt prefill through the decode kernel (left-padded rows start late) ----------------------
         lens = init_len.tolist() + [0] * (B - b)
         Lmax = L0
-        for t in range(Lmax):
-            toks, adv = [], []
-            for r in range(B):
-                live = r < b and t >= Lmax - lens[r] and bool(attention_mask[r, t])
-                toks.append(int(input_ids[r, t]) if live else pad_tok)
-                adv.append(1 if live else 0)
-            last = t == Lmax - 1
-            eng.embed_tokens(toks + ([start_id] * B if last else toks), eng.embeds)          # neg rows: [<speech_start>] at pos 0 (:379-386)
+        use_torch_prefill = self._prefill is not None and kwargs.get("prefill_impl", "auto") != "decode"
+        if use_torch_prefill:
+            # ---- prompt prefill on library kernels (a-9 / f-2), KV handed to the paged pool ------------------------------
+            embw = self._lm_sd["model.language_model.embed_tokens.weight"]
+            hids = []
+            with torch.cuda.stream(eng.stream):
+                for r in range(b):
+                    ids_r = input_ids[r][attention_mask[r].bool()].to(eng.device)
+                    hids.append(self._prefill.run(eng, r, embw[ids_r]))
+                    eng.kv_set_len(r, int(lens[r]))
+            eng.embed_tokens([pad_tok] * B + [start_id] * B, eng.embeds)     # negative rows: [<speech_start>] at pos 0 (:379-386)
             eng.lm_decode()
-            if not last:
-                eng.kv_commit(adv + [0] * B)
-        pending_adv_pos = adv                                                               # committed once tokens are known
+            with torch.cuda.stream(eng.stream):
+                for r in range(b):
+                    eng.hidden[r].copy_(hids[r])
+            eng.lm_head(eng.hidden)
+            pending_adv_pos = [0] * B
+        else:
+            # ---- prompt prefill through the decode kernel (left-padded rows start late) ----------------------------------
+            adv = [0] * B
+            for t in range(Lmax):
+                toks, adv = [], []
+                for r in range(B):
+                    live = r < b and t >= Lmax - lens[r] and bool(attention_mask[r, t])
+                    toks.append(int(input_ids[r, t]) if live else pad_tok)
+                    adv.append(1 if live else 0)
+                last = t == Lmax - 1
+                eng.embed_tokens(toks + ([start_id] * B if last else toks), eng.embeds)      # neg rows: [<speech_start>] at pos 0
+                eng.lm_decode()
+                if not last:
+                    eng.kv_commit(adv + [0] * B)
+            pending_adv_pos = adv                                                           # committed once tokens are known
 
         iterator = range(max_steps)
         if kwargs.get("show_progress_bar", False):

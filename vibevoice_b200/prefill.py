@@ -28,7 +28,7 @@ class TorchPrefill:
         return (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)).to(x.dtype) * w
 
     @torch.no_grad()
-    def run(self, engine, seq: int, embeds: torch.Tensor, chunk: int = 4096) -> torch.Tensor:
+    def run(self, engine, seq: int, embeds: torch.Tensor, chunk: int = 1 << 30) -> torch.Tensor:
         """embeds [L, H] (any float dtype, on device) for ONE row -> writes KV for positions [0, L) of sequence `seq`,
         returns final-norm hidden of the last position, fp32 [H]."""
         dc, w = self.dc, self.w

@@ -214,3 +214,29 @@ class SynthTokenizer:
             self.speech_diffusion_id, self.pad_token_id = vocab_size - 2, vocab_size - 1
         self.bos_token_id = None
         self.pad_id = self.pad_token_id
+
+
+def iter_synth_state_dict_fast(cfg: VibeVoiceConfig, seed: int = 1234, device="cuda", parts=None):
+    """Same layout and scales as `iter_synth_state_dict`, generated directly on the GPU (device RNG, so values differ
+    from the CPU-seeded checkpoint).  Used by bench.py only, where weight *values* are irrelevant."""
+    specs = param_specs(cfg) if parts is None else param_specs(cfg, parts)
+    g = torch.Generator(device=device)
+    for name, shape, kind in specs:
+        g.manual_seed((zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
+        if kind in (W, E):
+            fan_in = 1
+            for s_ in shape[1:]:
+                fan_in *= s_
+            std = 0.02 if kind == E else min(0.05, 0.7 / max(fan_in, 1) ** 0.5)
+            if "convtr" in name:
+                std = min(0.05, 0.7 / (2.0 * shape[0]) ** 0.5)
+            t = torch.empty(shape, dtype=torch.bfloat16, device=device).normal_(0.0, std, generator=g)
+        elif kind == B:
+            t = torch.empty(shape, dtype=torch.float32, device=device).normal_(0.0, 0.02, generator=g)
+        elif kind == G:
+            t = torch.empty(shape, dtype=torch.float32, device=device).uniform_(0.2, 0.6, generator=g)
+        else:
+            t = torch.empty(shape, dtype=torch.float32, device=device).uniform_(0.5, 1.5, generator=g)
+        yield name, t
+    yield "model.speech_scaling_factor", torch.tensor(SPEECH_SCALING_FACTOR, dtype=torch.float32)
+    yield "model.speech_bias_factor", torch.tensor(SPEECH_BIAS_FACTOR, dtype=torch.float32)
