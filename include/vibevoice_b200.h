@@ -146,6 +146,8 @@ int64_t vv_launch_count(vv_ctx* ctx);     /* kernels launched by this ctx so far
 int vv_debug_gemv(vv_ctx* ctx, const void* w_bf16, const float* bias, const float* x, float* y, int M, int N, int K,
                   int prologue, const float* pro_w, float eps, int epilogue, void* stream);
 
+int vv_debug_barrier_bench(vv_ctx* ctx, int iters, int ctas_per_sm, float* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,7 @@ SYMBOLS = {
     "vv_codec_state_reset": (_I, [_P, _P]),
     "vv_frame_tail": (_I, [_P, _P, _P, _P, _F, _P, _P, _P, _P]),
     "vv_launch_count": (_L, [_P]),
+    "vv_debug_barrier_bench": (_I, [_P, _I, _I, C.POINTER(C.c_float)]),
     "vv_debug_gemv": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _F, _I, _P]),
 }
 

@@ -62,6 +62,12 @@ struct GemvP {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every hot-path kernel lets its successor start launching immediately
+// (`pdl_trigger`) and blocks on its predecessor's completion (`pdl_wait`) only right before it touches
+// activations -- weights never depend on a predecessor, so their first loads overlap the launch gap.
+VV_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+VV_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 VV_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -125,8 +131,7 @@ __global__ void __launch_bounds__(256) gemv_kernel(GemvP p) {
   const int Kp = (K + 255) & ~255;
   float* xs = smem_f;                   // [MB][Kp]
   float* red = smem_f + MB * Kp;        // [2][8 warps][4*MB]
-  __shared__ float s_inv[MB];
-  __shared__ float s_part[8];
+  __shared__ float s_part[MB][8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int WK = p.WK, WR = 8 / WK;
   const int wr = warp / WK, wk = warp % WK;
@@ -135,7 +140,7 @@ __global__ void __launch_bounds__(256) gemv_kernel(GemvP p) {
   const int klane = lane * 8;
 
   auto load_chunk = [&](uint4 (&wv)[4], const bf16* const (&wrow)[4], int c) {
-    if ((c << 8) + klane < K) {
+    if (c < nchunks && (c << 8) + klane < K) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) wv[r] = ldg_stream(wrow[r] + (c << 8));
     } else {
@@ -149,6 +154,7 @@ __global__ void __launch_bounds__(256) gemv_kernel(GemvP p) {
     for (int r = 0; r < 4; ++r) wrow[r] = p.W + (size_t)min(r0 + r, N - 1) * K + klane;
   };
 
+  pdl_trigger();
   for (int m0 = 0; m0 < p.M; m0 += MB) {
     __syncthreads();
     int task = blockIdx.x;
@@ -157,38 +163,43 @@ __global__ void __launch_bounds__(256) gemv_kernel(GemvP p) {
     int c = wk;
     if (task < ntasks) {
       set_rows(wrow, task);
-      if (c < nchunks) load_chunk(cur, wrow, c);     // in flight while the activations are staged
+      load_chunk(cur, wrow, c);            // two chunks per warp are in flight while the activations are staged
+      load_chunk(nxt, wrow, c + WK);
     }
-    // ---- stage pro(x) for rows m0..m0+MB-1 ----
+    pdl_wait();                            // predecessor's activations are complete and visible from here on
+    // ---- stage pro(x) for rows m0..m0+MB-1: one pass over x (values parked in registers across the norm reduction) ----
     const bool need_inv = (p.pro == PRO_RMSNORM || p.pro == PRO_ADALN);
     const int K4 = K >> 2;
-    if (need_inv) {
-      for (int m = 0; m < MB; ++m) {
-        float ss = 0.f;
-        if (m0 + m < p.M) {
-          const float4* xr = reinterpret_cast<const float4*>(p.x + p.xmap.off(m0 + m));
-          for (int q = tid; q < K4; q += 256) { const float4 v = xr[q]; ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
-        }
-        ss = warp_sum(ss);
-        if (lane == 0) s_part[warp] = ss;
-        __syncthreads();
-        if (tid == 0) {
-          float t = 0.f;
-          for (int i = 0; i < 8; ++i) t += s_part[i];
-          s_inv[m] = rsqrtf(t / (float)K + p.pro_eps);
-        }
-        __syncthreads();
-      }
-    }
+    constexpr int XR = 4;                  // float4 per thread per row kept in registers (covers K <= 4096)
+    const bool one_pass = (K4 <= XR * 256);
     for (int m = 0; m < MB; ++m) {
       const bool valid = (m0 + m < p.M);
       const float* xr = p.x + (valid ? p.xmap.off(m0 + m) : 0);
-      const float inv = need_inv ? s_inv[m] : 1.f;
-      for (int q = tid; q < (Kp >> 2); q += 256) {
-        const int k = q << 2;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 xv[XR];
+      float inv = 1.f;
+      if (need_inv) {
+        float ss = 0.f;
+        if (one_pass) {
+#pragma unroll
+          for (int i = 0; i < XR; ++i) {
+            const int q = tid + i * 256;
+            xv[i] = (valid && q < K4) ? *reinterpret_cast<const float4*>(xr + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ss += xv[i].x * xv[i].x + xv[i].y * xv[i].y + xv[i].z * xv[i].z + xv[i].w * xv[i].w;
+          }
+        } else if (valid) {
+          for (int q = tid; q < K4; q += 256) { const float4 v = *reinterpret_cast<const float4*>(xr + 4 * q); ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) s_part[m][warp] = ss;
+        __syncthreads();
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += s_part[m][i];
+        inv = rsqrtf(t / (float)K + p.pro_eps);
+      }
+      auto xform_store = [&](int k, float4 v, bool have) {
         if (valid && k < K) {
-          v = *reinterpret_cast<const float4*>(xr + k);
+          if (!have) v = *reinterpret_cast<const float4*>(xr + k);
           if (p.pro == PRO_RMSNORM) {
             const float4 w = *reinterpret_cast<const float4*>(p.pro_w + k);
             v.x *= inv * w.x; v.y *= inv * w.y; v.z *= inv * w.z; v.w *= inv * w.w;
@@ -203,9 +214,17 @@ __global__ void __launch_bounds__(256) gemv_kernel(GemvP p) {
           } else if (p.pro == PRO_SILU) {
             v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
           }
+        } else {
+          v = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         *reinterpret_cast<float4*>(xs + m * Kp + xs_pos(k)) = v;
+      };
+#pragma unroll
+      for (int i = 0; i < XR; ++i) {
+        const int q = tid + i * 256;
+        if (q < (Kp >> 2)) xform_store(q << 2, xv[i], need_inv && one_pass);
       }
+      for (int q = tid + XR * 256; q < (Kp >> 2); q += 256) xform_store(q << 2, make_float4(0.f, 0.f, 0.f, 0.f), false);
     }
     __syncthreads();
 
@@ -216,9 +235,21 @@ __global__ void __launch_bounds__(256) gemv_kernel(GemvP p) {
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int m = 0; m < MB; ++m) acc[r][m] = 0.f;
+      // residual / gate operands of this task's outputs are requested now, consumed after the reduction
+      float pre_res = 0.f, pre_gate = 1.f;
+      const bool has_res = (p.epi == EPI_RESID || p.epi == EPI_GATED_RESID || p.epi == EPI_GAMMA_RESID);
+      if (has_res && tid < WR * 4 * MB) {
+        const int q = tid / (4 * MB), r = (tid / MB) % 4, m = tid % MB;
+        const int n = (task * WR + q) * 4 + r;
+        if (n < N && m0 + m < p.M) {
+          pre_res = p.res[(long long)(m0 + m) * p.ldres + n];
+          if (p.epi == EPI_GATED_RESID) pre_gate = p.epi_a[(long long)(m0 + m) * p.epi_lda + n];
+          else if (p.epi == EPI_GAMMA_RESID) pre_gate = p.epi_a[n];
+        }
+      }
       while (c < nchunks) {
-        const int cn = c + WK;
-        if (cn < nchunks) load_chunk(nxt, wrow, cn);
+        uint4 nn[4];
+        load_chunk(nn, wrow, c + 2 * WK);
         float xv[MB][8];
 #pragma unroll
         for (int m = 0; m < MB; ++m) {
@@ -237,16 +268,17 @@ __global__ void __launch_bounds__(256) gemv_kernel(GemvP p) {
             for (int j = 0; j < 8; ++j) acc[r][m] = fmaf(wf[j], xv[m][j], acc[r][m]);
         }
 #pragma unroll
-        for (int r = 0; r < 4; ++r) cur[r] = nxt[r];
-        c = cn;
+        for (int r = 0; r < 4; ++r) { cur[r] = nxt[r]; nxt[r] = nn[r]; }
+        c += WK;
       }
-      // next task's first chunk goes out before this task's reduction
+      // next task's first chunks go out before this task's reduction
       const int this_task = task;
       task += gridDim.x;
       c = wk;
       if (task < ntasks) {
         set_rows(wrow, task);
-        if (c < nchunks) load_chunk(cur, wrow, c);
+        load_chunk(cur, wrow, c);
+        load_chunk(nxt, wrow, c + WK);
       }
       // ---- reduce: lanes -> lane 0; k-split warps -> shared ----
 #pragma unroll
@@ -284,7 +316,10 @@ __global__ void __launch_bounds__(256) gemv_kernel(GemvP p) {
             float v = 0.f;
             for (int s = 0; s < WK; ++s) v += rbuf[(q * WK + s) * (4 * MB) + r * MB + m];
             if (p.bias) v += p.bias[n];
-            epi_store(p, m0 + m, n, v);
+            if (has_res) v = pre_res + pre_gate * v;
+            else if (p.epi == EPI_GELU) v = gelu_erf_f(v);
+            else if (p.epi == EPI_SILU) v = silu_f(v);
+            p.y[(long long)(m0 + m) * p.ldy + n] = v;
           }
         }
       }
@@ -296,59 +331,224 @@ __global__ void __launch_bounds__(256) gemv_kernel(GemvP p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Tiled GEMM for M > 16 (codec stages with many time steps and narrow channels).
-// C[M,N] = A[M,K] (fp32, RowMap) * W[N,K]^T (bf16); 64x64 tile, BK = 16, 4x4 micro-tile / thread.
+// GEMV v3: same math / task mapping as gemv_kernel, but the weights are moved by the TMA engine.
+//   producer warp : cp.async.bulk (1-D bulk tensor-less TMA, SASS UBLKCP) of [rows x KT] weight slabs
+//                   into an S-stage shared-memory ring, completion signalled on `full` mbarriers;
+//                   it runs ahead across task boundaries and starts before the activations are staged,
+//                   so ~100 KB of weights are in flight per SM regardless of how short a task is.
+//   8 consumer warps: wait `full`, read their rows/k-chunks of the slab with conflict-free LDS.128,
+//                   FMA against the staged activations, release the stage on the `empty` mbarrier.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gemm_tiled_kernel(GemvP p) {
-  __shared__ float As[16][64 + 4];
-  __shared__ float Ws[16][64 + 4];
-  const int tid = threadIdx.x;
-  const int bm = blockIdx.y * 64, bn = blockIdx.x * 64;
-  const int tx = tid & 15, ty = tid >> 4;
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  const int lr = tid >> 2, lk = (tid & 3) * 4;   // 64 rows x 4 k-quads
-  const int am = bm + lr, wn = bn + lr;
-  const float* arow = (am < p.M) ? p.x + p.xmap.off(am) : nullptr;
-  const bf16* wrow = (wn < p.N) ? p.W + (size_t)wn * p.K : nullptr;
-  for (int k0 = 0; k0 < p.K; k0 += 16) {
-    float a[4] = {0.f, 0.f, 0.f, 0.f}, w[4] = {0.f, 0.f, 0.f, 0.f};
-    if (arow) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) if (k0 + lk + j < p.K) a[j] = arow[k0 + lk + j];
-    }
-    if (wrow) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) if (k0 + lk + j < p.K) w[j] = __bfloat162float(wrow[k0 + lk + j]);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { As[lk + j][lr] = a[j]; Ws[lk + j][lr] = w[j]; }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      float av[4], wv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { av[i] = As[kk][ty * 4 + i]; wv[i] = Ws[kk][tx * 4 + i]; }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
-    }
-    __syncthreads();
+VV_DEVINL unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+VV_DEVINL void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+VV_DEVINL void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+VV_DEVINL void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+VV_DEVINL void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok = 0;
+  const unsigned a = smem_u32(bar);
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
   }
+}
+VV_DEVINL void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+VV_DEVINL void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+constexpr int TMA_MAX_STAGES = 6;
+struct GemvTmaCfg { int KT; int stages; };   // slab width (elements, multiple of 256) and ring depth
+
+template <int MB>
+__global__ void __launch_bounds__(288) gemv_tma_kernel(GemvP p, GemvTmaCfg cfg) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int K = p.K, N = p.N;
+  const int Kp = (K + 255) & ~255;
+  const int WK = p.WK, WR = 8 / WK, RW = 4 * WR;
+  const int KT = cfg.KT, S = cfg.stages;
+  const int stage_elems = RW * KT;
+  bf16* ring = reinterpret_cast<bf16*>(smem_raw);                                   // [S][RW][KT]
+  float* xs = reinterpret_cast<float*>(smem_raw + (size_t)S * stage_elems * 2);     // [MB][Kp]
+  float* red = xs + MB * Kp;                                                        // [2][8][4*MB]
+  __shared__ unsigned long long full_bar[TMA_MAX_STAGES], empty_bar[TMA_MAX_STAGES];
+  __shared__ float s_inv[MB];
+  __shared__ float s_part[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ntasks = (N + RW - 1) / RW;
+  const int nslabs = (K + KT - 1) / KT;
+
+  if (tid == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  pdl_trigger();
+  if (warp == 8) {
+    // ===================== producer ===================== (weights only: never waits on the predecessor grid)
+    int it = 0;
+    for (int m0 = 0; m0 < p.M; m0 += MB) {
+      for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
+        for (int sl = 0; sl < nslabs; ++sl, ++it) {
+          const int st = it % S;
+          const unsigned ph = (unsigned)((it / S) & 1);
+          mbar_wait(&empty_bar[st], ph ^ 1u);
+          const int k0 = sl * KT;
+          const unsigned bytes = (unsigned)(min(KT, K - k0) * 2);
+          if (lane == 0) mbar_expect_tx(&full_bar[st], bytes * (unsigned)RW);
+          __syncwarp();
+          if (lane < RW) {
+            const int row = min(task * RW + lane, N - 1);
+            bulk_g2s(ring + (size_t)st * stage_elems + (size_t)lane * KT, p.W + (size_t)row * K + k0, bytes, &full_bar[st]);
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===================== consumers (warps 0..7) =====================
+  const int wr = warp / WK, wk = warp % WK;
+  const int cps = KT >> 8;               // 256-element chunks per slab
+  int it = 0;
+  pdl_wait();
+  for (int m0 = 0; m0 < p.M; m0 += MB) {
+    consumer_sync();
+    const bool need_inv = (p.pro == PRO_RMSNORM || p.pro == PRO_ADALN);
+    const int K4 = K >> 2;
+    if (need_inv) {
+      for (int m = 0; m < MB; ++m) {
+        float ss = 0.f;
+        if (m0 + m < p.M) {
+          const float4* xr = reinterpret_cast<const float4*>(p.x + p.xmap.off(m0 + m));
+          for (int q = tid; q < K4; q += 256) { const float4 v = xr[q]; ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) s_part[warp] = ss;
+        consumer_sync();
+        if (tid == 0) {
+          float t = 0.f;
+          for (int i = 0; i < 8; ++i) t += s_part[i];
+          s_inv[m] = rsqrtf(t / (float)K + p.pro_eps);
+        }
+        consumer_sync();
+      }
+    }
+    for (int m = 0; m < MB; ++m) {
+      const bool valid = (m0 + m < p.M);
+      const float* xr = p.x + (valid ? p.xmap.off(m0 + m) : 0);
+      const float inv = need_inv ? s_inv[m] : 1.f;
+      for (int q = tid; q < (Kp >> 2); q += 256) {
+        const int k = q << 2;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid && k < K) {
+          v = *reinterpret_cast<const float4*>(xr + k);
+          if (p.pro == PRO_RMSNORM) {
+            const float4 w = *reinterpret_cast<const float4*>(p.pro_w + k);
+            v.x *= inv * w.x; v.y *= inv * w.y; v.z *= inv * w.z; v.w *= inv * w.w;
+          } else if (p.pro == PRO_ADALN) {
+            float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (p.pro_w) w = *reinterpret_cast<const float4*>(p.pro_w + k);
+            const long long o = (long long)(m0 + m) * p.pro_ld + k;
+            const float4 sc = *reinterpret_cast<const float4*>(p.pro_scale + o);
+            const float4 sh = *reinterpret_cast<const float4*>(p.pro_shift + o);
+            v.x = v.x * inv * w.x * (1.f + sc.x) + sh.x; v.y = v.y * inv * w.y * (1.f + sc.y) + sh.y;
+            v.z = v.z * inv * w.z * (1.f + sc.z) + sh.z; v.w = v.w * inv * w.w * (1.f + sc.w) + sh.w;
+          } else if (p.pro == PRO_SILU) {
+            v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
+          }
+        }
+        *reinterpret_cast<float4*>(xs + m * Kp + xs_pos(k)) = v;
+      }
+    }
+    consumer_sync();
+
+    int parity = 0;
+    for (int task = blockIdx.x; task < ntasks; task += gridDim.x, parity ^= 1) {
+      float acc[4][MB];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = bm + ty * 4 + i;
-    if (m >= p.M) continue;
+      for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = bn + tx * 4 + j;
-      if (n >= p.N) continue;
-      float v = acc[i][j] + (p.bias ? p.bias[n] : 0.f);
-      epi_store(p, m, n, v);
+        for (int m = 0; m < MB; ++m) acc[r][m] = 0.f;
+      for (int sl = 0; sl < nslabs; ++sl, ++it) {
+        const int st = it % S;
+        mbar_wait(&full_bar[st], (unsigned)((it / S) & 1));
+        const bf16* slab = ring + (size_t)st * stage_elems + (size_t)(wr * 4) * KT;
+        const int k0 = sl * KT;
+        for (int cc = wk; cc < cps; cc += WK) {
+          const int kk = (cc << 8) + lane * 8;          // offset inside the slab
+          if (k0 + kk < K) {
+            uint4 wv[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) wv[r] = *reinterpret_cast<const uint4*>(slab + (size_t)r * KT + kk);
+            const int cg = (k0 >> 8) + cc;               // global chunk index
+            float xv[MB][8];
+#pragma unroll
+            for (int m = 0; m < MB; ++m) {
+              const float4 a = *reinterpret_cast<const float4*>(xs + m * Kp + (cg << 8) + (lane << 2));
+              const float4 b = *reinterpret_cast<const float4*>(xs + m * Kp + (cg << 8) + 128 + (lane << 2));
+              xv[m][0] = a.x; xv[m][1] = a.y; xv[m][2] = a.z; xv[m][3] = a.w;
+              xv[m][4] = b.x; xv[m][5] = b.y; xv[m][6] = b.z; xv[m][7] = b.w;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              float wf[8];
+              bf16x8_unpack(wv[r], wf);
+#pragma unroll
+              for (int m = 0; m < MB; ++m)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[r][m] = fmaf(wf[j], xv[m][j], acc[r][m]);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[st]);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int m = 0; m < MB; ++m) acc[r][m] = warp_sum(acc[r][m]);
+      float* rbuf = red + parity * (8 * 4 * MB);
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int m = 0; m < MB; ++m) rbuf[warp * (4 * MB) + r * MB + m] = acc[r][m];
+      }
+      consumer_sync();
+      if (p.epi == EPI_SWIGLU) {
+        if (tid < WR * 2 * MB) {
+          const int q = tid / (2 * MB), pr = (tid / MB) % 2, m = tid % MB;
+          const int n0 = (task * WR + q) * 4 + pr * 2;
+          if (n0 + 1 < N && m0 + m < p.M) {
+            float g = 0.f, u = 0.f;
+            for (int s_ = 0; s_ < WK; ++s_) {
+              g += rbuf[(q * WK + s_) * (4 * MB) + (pr * 2) * MB + m];
+              u += rbuf[(q * WK + s_) * (4 * MB) + (pr * 2 + 1) * MB + m];
+            }
+            if (p.bias) { g += p.bias[n0]; u += p.bias[n0 + 1]; }
+            p.y[(long long)(m0 + m) * p.ldy + (n0 >> 1)] = silu_f(g) * u;
+          }
+        }
+      } else {
+        if (tid < WR * 4 * MB) {
+          const int q = tid / (4 * MB), r = (tid / MB) % 4, m = tid % MB;
+          const int n = (task * WR + q) * 4 + r;
+          if (n < N && m0 + m < p.M) {
+            float v = 0.f;
+            for (int s_ = 0; s_ < WK; ++s_) v += rbuf[(q * WK + s_) * (4 * MB) + r * MB + m];
+            if (p.bias) v += p.bias[n];
+            epi_store(p, m0 + m, n, v);
+          }
+        }
+      }
     }
   }
 }
@@ -428,8 +628,10 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(GemvP p) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
 
+  pdl_trigger();
 #pragma unroll
   for (int s_ = 0; s_ < MM_ST - 1; ++s_) { if (s_ < nk) load_w(s_, s_); cp_async_commit(); }
+  pdl_wait();
   load_a(0);
   for (int kt = 0; kt < nk; ++kt) {
     __syncthreads();                       // previous step's readers of Ah/Al and of the stage about to be refilled are done
@@ -474,6 +676,8 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(GemvP p) {
 // thread-per-output small-K product with fp32 weights (encoder stem conv 1->32 k7, decoder head conv 32->1 k7)
 __global__ void conv_naive_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ x,
                                   RowMap xmap, float* __restrict__ y, int M, int N, int K) {
+  pdl_trigger();
+  pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)M * N) return;
   const int m = (int)(idx / N), n = (int)(idx % N);
@@ -487,6 +691,8 @@ __global__ void conv_naive_kernel(const float* __restrict__ W, const float* __re
 // y[m,:] = rmsnorm(x[m,:]) * w   (one warp per row)
 __global__ void rows_norm_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
                                  int M, int C, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -507,6 +713,8 @@ __global__ void rows_norm_kernel(const float* __restrict__ x, const float* __res
 __global__ void assemble_window_kernel(const float* __restrict__ src, const float* __restrict__ hist,
                                        float* __restrict__ win, float* __restrict__ hist_next, int B, int T, int ctx, int C,
                                        const float* __restrict__ norm_w, float eps, float alpha, float beta) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int R = ctx + T;
@@ -539,6 +747,8 @@ __global__ void __launch_bounds__(256) assemble_window_block_kernel(const float*
                                                                     float* __restrict__ win, float* __restrict__ hist_next, int B, int T,
                                                                     int ctx, int C, const float* __restrict__ norm_w, float eps, float alpha,
                                                                     float beta) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x, tid = threadIdx.x;
   const int R = ctx + T;
   const int b = row / R, j = row % R;
@@ -571,6 +781,8 @@ __global__ void __launch_bounds__(256) assemble_window_block_kernel(const float*
 }
 __global__ void __launch_bounds__(256) rows_norm_block_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
                                                               int C, float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x, tid = threadIdx.x;
   const float* xr = x + (size_t)row * C;
   __shared__ float sp[8];
@@ -590,6 +802,8 @@ __global__ void __launch_bounds__(256) rows_norm_block_kernel(const float* __res
 __global__ void dwconv_res_kernel(const float* __restrict__ x, const float* __restrict__ win, const float* __restrict__ w /*[7][C]*/,
                                   const float* __restrict__ bias, const float* __restrict__ gamma, float* __restrict__ out,
                                   int B, int T, int C) {
+  pdl_trigger();
+  pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * T * C) return;
   const int c = (int)(idx % C);
@@ -605,6 +819,8 @@ __global__ void dwconv_res_kernel(const float* __restrict__ x, const float* __re
 struct StateSeg { float* hist; float* next; int n; };   // n floats per batch row
 
 __global__ void advance_kernel(const StateSeg* __restrict__ segs, const int* __restrict__ active) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   if (active && !active[b]) return;
   const StateSeg s = segs[blockIdx.x];
@@ -637,6 +853,8 @@ struct KvView {
 // qkv [M, (q_heads + 2 kv_heads) * HD] fp32 (bias added) -> q_rot fp32, K/V (bf16) appended at kv_len[m]
 __global__ void rope_append_kernel(const float* __restrict__ qkv, float* __restrict__ q_rot, KvView kv,
                                    const float* __restrict__ inv_freq /*[HD/2]*/) {
+  pdl_trigger();
+  pdl_wait();
   const int m = blockIdx.x;
   if (!kv.row_mode[m]) return;
   const int pos = kv.kv_len[m];
@@ -673,6 +891,8 @@ constexpr int ATT_TILE = 32;
 constexpr int ATT_MAXG = 8;     // q heads per kv head (6 for 1.5B, 7 for 7B)
 __global__ void __launch_bounds__(128) attn_partial_kernel(const float* __restrict__ q_rot, KvView kv, float* __restrict__ part_acc,
                                                            float* __restrict__ part_ml, int nsplit, float scale) {
+  pdl_trigger();
+  pdl_wait();
   const int s = blockIdx.x, g = blockIdx.y, m = blockIdx.z;
   if (!kv.row_mode[m]) return;
   const int G = kv.q_heads / kv.kv_heads;
@@ -762,10 +982,164 @@ __global__ void __launch_bounds__(128) attn_partial_kernel(const float* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core split-KV partial attention (mma.sync m16n8k16, bf16 operands, fp32 accumulate).
+// The scalar kernel above is issue-bound (~1300 warp instructions per 32-token tile); here a warp needs ~110
+// per 16 tokens.  GQA trick: the 16 rows of the MMA "M" dimension hold the G <= 8 query heads of one KV group
+// TWICE -- rows 0..7 the bf16 high parts, rows 8..15 the bf16 low parts (q = hi + lo to 2^-16) -- so a single
+// MMA yields hi*K and lo*K, summed in registers; the same packing carries P = hi + lo through the P*V product.
+// CTA = 4 warps over 64-token K/V tiles (cp.async double-buffered); warp w owns tokens [16w, 16w+16) of every tile
+// with its own online-softmax state, merged through shared memory at the end.
+// ---------------------------------------------------------------------------------------------
+constexpr int AT2_TILE = 64, AT2_LD = HD + 8;
+constexpr int AT2_SMEM = 4 * AT2_TILE * AT2_LD * 2 + 16 * AT2_LD * 2;
+VV_DEVINL void ldmatrix_x4_trans(unsigned (&r)[4], const void* smem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(sa));
+}
+__global__ void __launch_bounds__(128) attn_partial_mma_kernel(const float* __restrict__ q_rot, KvView kv, float* __restrict__ part_acc,
+                                                               float* __restrict__ part_ml, int nsplit, float scale) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) unsigned char at_smem[];
+  typedef bf16 (*TileP)[AT2_TILE][AT2_LD];
+  TileP Ks = reinterpret_cast<TileP>(at_smem);
+  TileP Vs = reinterpret_cast<TileP>(at_smem + 2 * AT2_TILE * AT2_LD * 2);
+  bf16 (*Qs)[AT2_LD] = reinterpret_cast<bf16 (*)[AT2_LD]>(at_smem + 4 * AT2_TILE * AT2_LD * 2);
+  const int s = blockIdx.x, g = blockIdx.y, m = blockIdx.z;
+  if (!kv.row_mode[m]) return;
+  const int G = kv.q_heads / kv.kv_heads;
+  const int L = kv.kv_len[m] + 1;
+  const int ntiles = (L + AT2_TILE - 1) / AT2_TILE;
+  const int tps = (ntiles + nsplit - 1) / nsplit;
+  const int t_begin = s * tps, t_end = min(ntiles, (s + 1) * tps);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t obase = ((size_t)m * kv.q_heads + g * G) * nsplit + s;        // + h * nsplit per head
+  if (t_begin >= t_end) {                                                   // empty split: neutral partial
+    for (int i = tid; i < G * HD; i += 128) part_acc[(obase + (size_t)(i / HD) * nsplit) * HD + (i % HD)] = 0.f;
+    if (tid < G) { part_ml[(obase + (size_t)tid * nsplit) * 2] = -INFINITY; part_ml[(obase + (size_t)tid * nsplit) * 2 + 1] = 0.f; }
+    return;
+  }
+  auto prefetch = [&](int t, int buf) {
+    const int tok0 = t * AT2_TILE;
+    const int page = kv.page_table[(size_t)m * kv.max_pages + tok0 / KV_PAGE];
+    const size_t base = (((size_t)page * kv.kv_heads + g) * KV_PAGE + (tok0 % KV_PAGE)) * HD;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = tid + it * 128;
+      const int r = idx >> 4, c = (idx & 15) * 8;
+      cp_async16(&Ks[buf][r][c], kv.kpool + base + (size_t)r * HD + c, 16);
+      cp_async16(&Vs[buf][r][c], kv.vpool + base + (size_t)r * HD + c, (tok0 + r < L) ? 16 : 0);
+    }
+  };
+  prefetch(t_begin, 0);
+  cp_async_commit();
+  // Q: rows 0..7 = hi(q*scale) of heads 0..G-1, rows 8..15 = lo
+  for (int i = tid; i < 8 * HD; i += 128) {
+    const int h = i / HD, d = i % HD;
+    const float v = (h < G) ? q_rot[((size_t)m * kv.q_heads + g * G + h) * HD + d] * scale : 0.f;
+    const bf16 hi = __float2bfloat16_rn(v);
+    Qs[h][d] = hi;
+    Qs[h + 8][d] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+  __syncthreads();
+  unsigned qa[8][4];
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) ldmatrix_x4(qa[ks], &Qs[lane & 15][ks * 16 + (lane >> 4) * 8]);
+  float o[16][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { o[i][0] = 0.f; o[i][1] = 0.f; o[i][2] = 0.f; o[i][3] = 0.f; }
+  float m_run = -INFINITY, l_run = 0.f;
+
+  for (int t = t_begin; t < t_end; ++t) {
+    const int buf = (t - t_begin) & 1;
+    const int tok0 = t * AT2_TILE;
+    if (t + 1 < t_end) prefetch(t + 1, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    float sa[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      unsigned kb[4];
+      ldmatrix_x4(kb, &Ks[buf][warp * 16 + (lane & 7) + ((lane >> 4) << 3)][ks * 16 + ((lane >> 3) & 1) * 8]);
+      mma_bf16_16816(sa[0], qa[ks], kb[0], kb[1]);
+      mma_bf16_16816(sa[1], qa[ks], kb[2], kb[3]);
+    }
+    // head = lane/4; this lane holds tokens tb+{0,1} (n-tile 0) and tb+{8,9} (n-tile 1); hi-row + lo-row
+    const int tb = tok0 + warp * 16 + (lane & 3) * 2;
+    float sv[4] = {sa[0][0] + sa[0][2], sa[0][1] + sa[0][3], sa[1][0] + sa[1][2], sa[1][1] + sa[1][3]};
+    if (tb >= L) sv[0] = -INFINITY;
+    if (tb + 1 >= L) sv[1] = -INFINITY;
+    if (tb + 8 >= L) sv[2] = -INFINITY;
+    if (tb + 9 >= L) sv[3] = -INFINITY;
+    float mt = fmaxf(fmaxf(sv[0], sv[1]), fmaxf(sv[2], sv[3]));
+    mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 1));
+    mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 2));
+    const float mn = fmaxf(m_run, mt);
+    const float msafe = (mn == -INFINITY) ? 0.f : mn;
+    float pv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pv[i] = __expf(sv[i] - msafe);
+    const float corr = __expf(m_run - msafe);
+    float rs = pv[0] + pv[1] + pv[2] + pv[3];
+    rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+    rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+    l_run = l_run * corr + rs;
+    m_run = mn;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { o[i][0] *= corr; o[i][1] *= corr; o[i][2] *= corr; o[i][3] *= corr; }
+    float ph[4], pl[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ph[i] = __bfloat162float(__float2bfloat16_rn(pv[i])); pl[i] = pv[i] - ph[i]; }
+    unsigned pa[4] = {pack_bf16(ph[0], ph[1]), pack_bf16(pl[0], pl[1]), pack_bf16(ph[2], ph[3]), pack_bf16(pl[2], pl[3])};
+#pragma unroll
+    for (int np = 0; np < 8; ++np) {
+      unsigned vb[4];
+      ldmatrix_x4_trans(vb, &Vs[buf][warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][np * 16 + (lane >> 4) * 8]);
+      mma_bf16_16816(o[2 * np], pa, vb[0], vb[1]);
+      mma_bf16_16816(o[2 * np + 1], pa, vb[2], vb[3]);
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  // merge the 4 warps' partial (m, l, O) through shared memory (K/V buffers are free now)
+  float* mo = reinterpret_cast<float*>(at_smem);            // [4][8][HD]
+  float* mlw = mo + 4 * 8 * HD;                             // [4][8][2]
+  const int h = lane >> 2;
+#pragma unroll
+  for (int nt = 0; nt < 16; ++nt) {
+    const int d = nt * 8 + (lane & 3) * 2;
+    mo[(warp * 8 + h) * HD + d] = o[nt][0] + o[nt][2];
+    mo[(warp * 8 + h) * HD + d + 1] = o[nt][1] + o[nt][3];
+  }
+  if ((lane & 3) == 0) { mlw[(warp * 8 + h) * 2] = m_run; mlw[(warp * 8 + h) * 2 + 1] = l_run; }
+  __syncthreads();
+  for (int hh = 0; hh < G; ++hh) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) mx = fmaxf(mx, mlw[(w * 8 + hh) * 2]);
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float mw = mlw[(w * 8 + hh) * 2];
+      const float wgt = (mw == -INFINITY) ? 0.f : __expf(mw - mx);
+      num = fmaf(wgt, mo[(w * 8 + hh) * HD + tid], num);
+      den = fmaf(wgt, mlw[(w * 8 + hh) * 2 + 1], den);
+    }
+    const size_t oo = obase + (size_t)hh * nsplit;
+    part_acc[oo * HD + tid] = num;
+    if (tid == 0) { part_ml[oo * 2] = mx; part_ml[oo * 2 + 1] = den; }
+  }
+}
+
 // merge the split partials: weights computed once per (row, head) in shared memory, then a flat weighted sum
 __global__ void __launch_bounds__(128) attn_combine_kernel(const float* __restrict__ part_acc, const float* __restrict__ part_ml,
                                                            const int* __restrict__ row_mode, float* __restrict__ out, int q_heads,
                                                            int nsplit) {
+  pdl_trigger();
+  pdl_wait();
   const int h = blockIdx.x, m = blockIdx.y, d = threadIdx.x;
   if (!row_mode[m]) return;
   const size_t o = ((size_t)m * q_heads + h) * nsplit;
@@ -805,6 +1179,8 @@ __global__ void embed_gather_kernel(const bf16* __restrict__ table, const int* _
 __global__ void __launch_bounds__(256) lm_head_argmax_kernel(const float* __restrict__ hidden, const bf16* __restrict__ w_valid,
                                                              const int* __restrict__ valid_ids, int n_valid, int H,
                                                              float* __restrict__ logits, int* __restrict__ tokens) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ float red[8][8];
   float acc[8];
@@ -842,6 +1218,8 @@ __global__ void kv_commit_kernel(int* __restrict__ kv_len, const int* __restrict
 // c_all[i][r][:] = silu(condp[r][:] + temb[i][:])   for all steps i (sample-independent t-embedding)
 __global__ void head_cond_prep_kernel(const float* __restrict__ condp, const float* __restrict__ temb, float* __restrict__ c_all,
                                       int n_steps, int R, int H) {
+  pdl_trigger();
+  pdl_wait();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)n_steps * R * H) return;
   const int k = (int)(idx % H);
@@ -863,6 +1241,8 @@ __global__ void __launch_bounds__(256) dpm_update_proj_kernel(const float* __res
                                                               const DpmCoef* __restrict__ coef, int step, float cfg,
                                                               const bf16* __restrict__ w_noisy /*[H][64]*/, float* __restrict__ xout,
                                                               float* __restrict__ latent_out, int B, int H, int do_proj) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x;
   __shared__ float zs[64];
   if (tid < 64) {
@@ -906,6 +1286,8 @@ __global__ void __launch_bounds__(256) dpm_update_proj_kernel(const float* __res
 // embeds[b] = active[b] ? e_new[b] : embeds[b];  embeds[B+b] = embeds[b]  (negative stream is fed the same input, :579-581)
 __global__ void select_embeds_kernel(float* __restrict__ embeds, const float* __restrict__ e_new, const int* __restrict__ active,
                                      int B, int H) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.x;
   const bool a = active[b] != 0;
   for (int k = threadIdx.x; k < H; k += blockDim.x) {

@@ -6,6 +6,7 @@
 // sketches the C ABI this file implements.
 #include "../../include/vibevoice_b200.h"
 #include "vv_kernels.cuh"
+#include "vv_mega.cuh"
 
 #include <cuda_fp16.h>
 
@@ -81,6 +82,9 @@ struct vv_ctx {
   int device = 0;
   bool finalized = false;
   bool use_graphs = true;
+  bool use_tma = false;    // TMA-ring GEMV (gemv_tma_kernel) measured slower than the register-pipelined one; VV_TMA=1 selects it
+  bool use_pdl = true;
+  bool use_mma_attn = true;
   int sm_count = 148;
   std::map<std::string, RawTensor> raw;
   std::set<std::string> expected;
@@ -112,6 +116,10 @@ struct vv_ctx {
   float *s_e = nullptr, *s_c1 = nullptr, *s_feat = nullptr, *s_audio = nullptr, *s_latent = nullptr;
   int* s_tok = nullptr;
   std::map<std::string, GraphEntry> graphs;
+  struct Program { Op* ops_dev = nullptr; int n_ops = 0; int smem = 0; int MB = 0; int grid = 0; };
+  std::map<std::string, Program> programs;
+  GridBar* gridbar = nullptr;
+  bool use_mega = false;   // persistent program kernel (vv_mega.cuh): correct, but measured slower than kernel-per-stage graphs; VV_MEGA=1 selects it
   int64_t launches = 0;
   std::map<long long, int> occ_cache;
 };
@@ -119,6 +127,22 @@ struct vv_ctx {
 struct L {  // launcher
   vv_ctx* c; cudaStream_t s;
 };
+
+// every hot-path kernel goes through here: programmatic dependent launch (PDL) lets kernel N+1 be scheduled and run its
+// weight-only prologue while kernel N drains; inside CUDA-graph capture these become programmatic dependency edges.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(const L& l, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = l.s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = l.c->use_pdl ? 1 : 0;
+  l.c->launches++;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 // ------------------------------------------------------------------------------------------------
 template <class T>
@@ -139,9 +163,7 @@ static int launch_gemv_t(const L& l, GemvP& p, int grid, int smem) {
   static bool attr_set[8] = {false, false, false, false, false, false, false, false};
   (void)attr_set;
   CK(cudaFuncSetAttribute(gemv_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  gemv_kernel<MB><<<grid, 256, smem, l.s>>>(p);
-  CKL();
-  l.c->launches++;
+  CK(launch_k(l, gemv_kernel<MB>, dim3(grid), dim3(256), smem, p));
   return 0;
 }
 
@@ -157,15 +179,20 @@ static int gemv_occupancy(vv_ctx* c, int smem) {
   return occ;
 }
 
+template <int MB>
+static int launch_gemv_tma_t(const L& l, GemvP& p, GemvTmaCfg cfg, int grid, int smem) {
+  CK(cudaFuncSetAttribute(gemv_tma_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  CK(launch_k(l, gemv_tma_kernel<MB>, dim3(grid), dim3(288), smem, p, cfg));
+  return 0;
+}
+
 // y = epi(W * pro(x) + bias); dispatches GEMV (M <= 16) or the tiled GEMM.
 static int linear(const L& l, GemvP p) {
   if (p.K % 8 != 0) return fail(VV_ERR_INVALID, "linear: K=%d not a multiple of 8", p.K);
   if (((uintptr_t)p.x & 15) || (p.xmap.rs & 3) || (p.xmap.bs & 3)) return fail(VV_ERR_INVALID, "linear: activation rows must be 16-byte aligned");
   if (p.M > 8 && p.pro == PRO_NONE && p.epi != EPI_SWIGLU) {
     dim3 grid((p.N + MM_BN - 1) / MM_BN, (p.M + MM_BM - 1) / MM_BM);
-    gemm_mma_kernel<<<grid, 128, 0, l.s>>>(p);
-    CKL();
-    l.c->launches++;
+    CK(launch_k(l, gemm_mma_kernel, dim3(grid), dim3(128), 0, p));
     return 0;
   }
   if (p.M > 16) return fail(VV_ERR_INVALID, "linear: M=%d > 16 needs PRO_NONE and a non-SWIGLU epilogue", p.M);
@@ -178,6 +205,25 @@ static int linear(const L& l, GemvP p) {
   while (WR < 8 && 8 / WR > nchunks) WR <<= 1;      // never more k-split warps than 256-element chunks
   p.WK = 8 / WR;
   const int ntasks = (p.N + 4 * WR - 1) / (4 * WR);
+  if (l.c->use_tma) {
+    // TMA-fed ring: slab = [4*WR rows][KT], ~32 KB per stage, as many stages as fit beside the staged activations
+    const int Kp = (p.K + 255) & ~255;
+    GemvTmaCfg cfg;
+    cfg.KT = std::min(Kp, 16384 / (4 * WR));
+    const int stage_bytes = 4 * WR * cfg.KT * 2;
+    const int fixed = gemv_smem_bytes(MB, p.K) + 256;
+    cfg.stages = std::min(TMA_MAX_STAGES, (215 * 1024 - fixed) / stage_bytes);
+    if (cfg.stages >= 2) {
+      const int smem_t = cfg.stages * stage_bytes + fixed;
+      const int grid_t = std::min(ntasks, l.c->sm_count);
+      switch (MB) {
+        case 1: return launch_gemv_tma_t<1>(l, p, cfg, grid_t, smem_t);
+        case 2: return launch_gemv_tma_t<2>(l, p, cfg, grid_t, smem_t);
+        case 4: return launch_gemv_tma_t<4>(l, p, cfg, grid_t, smem_t);
+        default: return launch_gemv_tma_t<8>(l, p, cfg, grid_t, smem_t);
+      }
+    }
+  }
   const int smem = gemv_smem_bytes(MB, p.K);
   int occ = MB == 1 ? gemv_occupancy<1>(l.c, smem) : MB == 2 ? gemv_occupancy<2>(l.c, smem) : MB == 4 ? gemv_occupancy<4>(l.c, smem)
                                                                                                           : gemv_occupancy<8>(l.c, smem);
@@ -196,6 +242,61 @@ static GemvP mk(const bf16* W, const float* bias, const float* x, long long ldx,
   p.W = W; p.bias = bias; p.x = x; p.xmap = dense_rows(ldx); p.y = y; p.ldy = ldy; p.M = M; p.N = N; p.K = K;
   p.pro = PRO_NONE; p.epi = EPI_NONE; p.WK = 1;
   return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// persistent program kernel (vv_mega.cuh): host side
+// ------------------------------------------------------------------------------------------------
+static void gemv_cfg(vv_ctx* c, GemvP& p) {
+  int WR = 8;
+  while (WR > 1 && (p.N + 4 * WR - 1) / (4 * WR) < 2 * c->sm_count) WR >>= 1;
+  const int nchunks = (p.K + 255) / 256;
+  while (WR < 8 && 8 / WR > nchunks) WR <<= 1;
+  p.WK = 8 / WR;
+}
+static Op op_gemv(vv_ctx* c, GemvP p, bool barrier) {
+  Op o;
+  memset(&o, 0, sizeof o);
+  o.kind = OP_GEMV; o.barrier_before = barrier ? 1 : 0;
+  gemv_cfg(c, p);
+  o.g = p;
+  return o;
+}
+template <int MB>
+static int program_occ(int smem, int* occ) {
+  CK(cudaFuncSetAttribute(program_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, program_kernel<MB>, 256, smem));
+  return 0;
+}
+// returns 1 if the program cannot run as one resident grid (caller falls back to kernel-per-stage)
+static int finish_program(vv_ctx* c, const std::vector<Op>& ops, int M, vv_ctx::Program* pr) {
+  const int MB = M <= 2 ? 2 : (M <= 4 ? 4 : 8);
+  int smem = 2 * ATT_GROUP_SMEM;
+  for (const Op& o : ops)
+    if (o.kind == OP_GEMV) smem = std::max(smem, gemv_smem_bytes(MB, o.g.K));
+  if (smem > 200 * 1024) return 1;
+  int occ = 0;
+  if (MB == 2) RET(program_occ<2>(smem, &occ)); else if (MB == 4) RET(program_occ<4>(smem, &occ)); else RET(program_occ<8>(smem, &occ));
+  if (occ < 1) return 1;
+  pr->MB = MB; pr->smem = smem; pr->grid = c->sm_count * std::min(occ, 2); pr->n_ops = (int)ops.size();
+  RET(dmalloc(c, &pr->ops_dev, ops.size(), false));
+  CK(cudaMemcpy(pr->ops_dev, ops.data(), ops.size() * sizeof(Op), cudaMemcpyHostToDevice));
+  return 0;
+}
+static int launch_program(const L& l, const vv_ctx::Program& pr) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(pr.grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = pr.smem; cfg.stream = l.s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  const Op* ops = pr.ops_dev; int n = pr.n_ops; GridBar* gb = l.c->gridbar;
+  l.c->launches++;
+  if (pr.MB == 2) CK(cudaLaunchKernelEx(&cfg, program_kernel<2>, ops, n, gb));
+  else if (pr.MB == 4) CK(cudaLaunchKernelEx(&cfg, program_kernel<4>, ops, n, gb));
+  else CK(cudaLaunchKernelEx(&cfg, program_kernel<8>, ops, n, gb));
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -271,6 +372,14 @@ extern "C" int vv_create(const vv_model_desc* desc, int device, vv_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   const char* ng = getenv("VV_NO_GRAPH");
   c->use_graphs = !(ng && ng[0] == '1');
+  const char* nt = getenv("VV_TMA");
+  c->use_tma = (nt && nt[0] == '1');
+  const char* nm = getenv("VV_MEGA");
+  c->use_mega = (nm && nm[0] == '1');
+  const char* na = getenv("VV_SCALAR_ATTN");
+  c->use_mma_attn = !(na && na[0] == '1');
+  const char* np = getenv("VV_NO_PDL");
+  c->use_pdl = !(np && np[0] == '1');
   build_expected(c);
   *out = c;
   return 0;
@@ -587,7 +696,8 @@ extern "C" int vv_finalize_weights(vv_ctx* c) {
     RET(dmalloc(c, &c->s_t1, (size_t)NS * H));
     RET(dmalloc(c, &c->s_condp, (size_t)M2 * H));
     RET(dmalloc(c, &c->s_call, (size_t)NS * M2 * H));
-    RET(dmalloc(c, &c->s_mod, (size_t)M2 * modrows));
+    RET(dmalloc(c, &c->s_mod, (size_t)NS * M2 * modrows));
+    RET(dmalloc(c, &c->gridbar, 2));
     RET(dmalloc(c, &c->s_hx, (size_t)M2 * H));
     RET(dmalloc(c, &c->s_hg, (size_t)M2 * F));
     RET(dmalloc(c, &c->s_v, (size_t)M2 * 64));
@@ -833,9 +943,7 @@ extern "C" int vv_kv_write(vv_ctx* c, int seq, int layer, int64_t pos0, int64_t 
 // ------------------------------------------------------------------------------------------------
 static int enqueue_lm_head(const L& l, const float* hidden, float* logits, int32_t* tokens) {
   vv_ctx* c = l.c;
-  lm_head_argmax_kernel<<<c->d.max_batch, 256, 0, l.s>>>(hidden, c->head_valid, c->valid_ids_dev, c->d.n_valid_ids, c->d.hidden_size, logits, tokens);
-  CKL();
-  c->launches++;
+  CK(launch_k(l, lm_head_argmax_kernel, dim3(c->d.max_batch), dim3(256), 0, hidden, c->head_valid, c->valid_ids_dev, c->d.n_valid_ids, c->d.hidden_size, logits, tokens));
   return 0;
 }
 
@@ -855,13 +963,14 @@ static int enqueue_lm_decode(const L& l, const float* embeds, float* hidden, flo
     kv.kpool = c->kpool + per_layer * li; kv.vpool = c->vpool + per_layer * li;
     kv.page_table = c->page_table_dev; kv.max_pages = c->max_pages; kv.kv_len = c->kv_len_dev; kv.row_mode = c->row_mode_dev;
     kv.kv_heads = d.num_kv_heads; kv.q_heads = d.num_q_heads;
-    rope_append_kernel<<<M, 256, 0, l.s>>>(c->s_qkv, c->s_qrot, kv, c->inv_freq);
-    CKL();
-    attn_partial_kernel<<<dim3(c->nsplit, d.num_kv_heads, M), 128, 0, l.s>>>(c->s_qrot, kv, c->s_pacc, c->s_pml, c->nsplit, scale);
-    CKL();
-    attn_combine_kernel<<<dim3(d.num_q_heads, M), 128, 0, l.s>>>(c->s_pacc, c->s_pml, c->row_mode_dev, c->s_attn, d.num_q_heads, c->nsplit);
-    CKL();
-    c->launches += 3;
+    CK(launch_k(l, rope_append_kernel, dim3(M), dim3(256), 0, c->s_qkv, c->s_qrot, kv, c->inv_freq));
+    if (c->use_mma_attn) {
+      CK(cudaFuncSetAttribute(attn_partial_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM));
+      CK(launch_k(l, attn_partial_mma_kernel, dim3(c->nsplit, d.num_kv_heads, M), dim3(128), (size_t)AT2_SMEM, c->s_qrot, kv, c->s_pacc, c->s_pml, c->nsplit, scale));
+    } else {
+      CK(launch_k(l, attn_partial_kernel, dim3(c->nsplit, d.num_kv_heads, M), dim3(128), 0, c->s_qrot, kv, c->s_pacc, c->s_pml, c->nsplit, scale));
+    }
+    CK(launch_k(l, attn_combine_kernel, dim3(d.num_q_heads, M), dim3(128), 0, c->s_pacc, c->s_pml, c->row_mode_dev, c->s_attn, d.num_q_heads, c->nsplit));
     p = mk(y.wo, nullptr, c->s_attn, nq, c->s_h, H, M, H, nq);
     p.epi = EPI_RESID; p.res = c->s_h; p.ldres = H;
     RET(linear(l, p));
@@ -872,11 +981,51 @@ static int enqueue_lm_decode(const L& l, const float* embeds, float* hidden, flo
     p.epi = EPI_RESID; p.res = c->s_h; p.ldres = H;
     RET(linear(l, p));
   }
-  if (H >= 512) rows_norm_block_kernel<<<M, 256, 0, l.s>>>(c->s_h, c->lm_norm, hidden, H, d.rms_norm_eps);
-  else rows_norm_kernel<<<(M + 7) / 8, 256, 0, l.s>>>(c->s_h, c->lm_norm, hidden, M, H, d.rms_norm_eps);
-  CKL();
-  c->launches++;
+  if (H >= 512) CK(launch_k(l, rows_norm_block_kernel, dim3(M), dim3(256), 0, c->s_h, c->lm_norm, hidden, H, d.rms_norm_eps));
+  else CK(launch_k(l, rows_norm_kernel, dim3((M + 7) / 8), dim3(256), 0, c->s_h, c->lm_norm, hidden, M, H, d.rms_norm_eps));
   return enqueue_lm_head(l, hidden, logits, tokens);
+}
+
+static int build_lm_program(vv_ctx* c, const float* embeds, float* hidden, float* logits, int32_t* tokens, vv_ctx::Program* pr) {
+  const auto& d = c->d;
+  const int H = d.hidden_size, I = d.intermediate_size, M = 2 * d.max_batch, nq = d.num_q_heads * HD;
+  const size_t per_layer = (size_t)c->n_pages * d.num_kv_heads * KV_PAGE * HD;
+  std::vector<Op> ops;
+  for (int li = 0; li < d.num_layers; ++li) {
+    const LmLayer& y = c->lm[li];
+    const float* xin = li == 0 ? embeds : c->s_h;          // layer 0 reads the caller's embeddings; the residual stream lives in s_h
+    GemvP p = mk(y.wqkv, y.bqkv, xin, H, c->s_qkv, c->Nqkv, M, c->Nqkv, H);
+    p.pro = PRO_RMSNORM; p.pro_w = y.ln1; p.pro_eps = d.rms_norm_eps;
+    ops.push_back(op_gemv(c, p, li > 0));
+    Op a;
+    memset(&a, 0, sizeof a);
+    a.kind = OP_ATTN; a.barrier_before = 1;
+    a.a.qkv = c->s_qkv;
+    a.a.kv.kpool = c->kpool + per_layer * li; a.a.kv.vpool = c->vpool + per_layer * li;
+    a.a.kv.page_table = c->page_table_dev; a.a.kv.max_pages = c->max_pages; a.a.kv.kv_len = c->kv_len_dev; a.a.kv.row_mode = c->row_mode_dev;
+    a.a.kv.kv_heads = d.num_kv_heads; a.a.kv.q_heads = d.num_q_heads;
+    a.a.part_acc = c->s_pacc; a.a.part_ml = c->s_pml; a.a.attn_out = c->s_attn; a.a.inv_freq = c->inv_freq;
+    a.a.nsplit = c->nsplit; a.a.M = M; a.a.scale = 1.0f / sqrtf((float)HD);
+    ops.push_back(a);
+    a.kind = OP_COMBINE;
+    ops.push_back(a);
+    p = mk(y.wo, nullptr, c->s_attn, nq, c->s_h, H, M, H, nq);
+    p.epi = EPI_RESID; p.res = xin; p.ldres = H;
+    ops.push_back(op_gemv(c, p, true));
+    p = mk(y.wgu, nullptr, c->s_h, H, c->s_act, I, M, 2 * I, H);
+    p.pro = PRO_RMSNORM; p.pro_w = y.ln2; p.pro_eps = d.rms_norm_eps; p.epi = EPI_SWIGLU;
+    ops.push_back(op_gemv(c, p, true));
+    p = mk(y.wdown, nullptr, c->s_act, I, c->s_h, H, M, H, I);
+    p.epi = EPI_RESID; p.res = c->s_h; p.ldres = H;
+    ops.push_back(op_gemv(c, p, true));
+  }
+  Op f;
+  memset(&f, 0, sizeof f);
+  f.kind = OP_FINAL; f.barrier_before = 1;
+  f.f.h = c->s_h; f.f.norm_w = c->lm_norm; f.f.hidden = hidden; f.f.w_valid = c->head_valid; f.f.valid_ids = c->valid_ids_dev;
+  f.f.logits = logits; f.f.tokens = tokens; f.f.M = M; f.f.B = d.max_batch; f.f.H = H; f.f.n_valid = d.n_valid_ids; f.f.eps = d.rms_norm_eps;
+  ops.push_back(f);
+  return finish_program(c, ops, M, pr);
 }
 
 extern "C" int vv_lm_decode(vv_ctx* c, const float* embeds, float* hidden, float* logits, int32_t* tokens, void* stream) {
@@ -885,6 +1034,20 @@ extern "C" int vv_lm_decode(vv_ctx* c, const float* embeds, float* hidden, float
   for (int s = 0; s < 2 * c->d.max_batch; ++s) RET(vv_kv_reserve(c, s, c->kv_len_host[s] + 1, stream));
   char key[256];
   snprintf(key, sizeof key, "lm:%p:%p:%p:%p", (const void*)embeds, (void*)hidden, (void*)logits, (void*)tokens);
+  if (c->use_mega) {
+    auto it = c->programs.find(key);
+    if (it == c->programs.end()) {
+      vv_ctx::Program pr;
+      int r = build_lm_program(c, embeds, hidden, logits, tokens, &pr);
+      if (r < 0) return r;
+      if (r == 1) pr.n_ops = 0;                 // does not fit as one resident grid: kernel-per-stage path below
+      it = c->programs.emplace(key, pr).first;
+    }
+    if (it->second.n_ops > 0) {
+      L l{c, (cudaStream_t)stream};
+      return launch_program(l, it->second);
+    }
+  }
   return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_lm_decode(l, embeds, hidden, logits, tokens); });
 }
 extern "C" int vv_lm_head(vv_ctx* c, const float* hidden, float* logits, int32_t* tokens, void* stream) {
@@ -948,51 +1111,104 @@ extern "C" int vv_set_diffusion_steps(vv_ctx* c, int n_steps, const float* times
   return 0;
 }
 
-static int enqueue_diffusion(const L& l, const float* cond, const float* noise, float cfg, float* latent_out) {
+// head ops of one diffusion step (shared by the kernel-per-stage path and the program builder)
+static void head_step_gemvs(vv_ctx* c, int i, std::vector<GemvP>* out) {
+  const auto& d = c->d;
+  const int H = d.hidden_size, F = d.head_ffn_dim, M = 2 * d.max_batch, LH = d.head_layers;
+  const int modld = (3 * LH + 2) * H;
+  const float* mod = c->s_mod + (size_t)i * M * modld;
+  for (int li = 0; li < LH; ++li) {
+    const HeadLayer& hl = c->head[li];
+    GemvP p = mk(hl.wgu, nullptr, c->s_hx, H, c->s_hg, F, M, 2 * F, H);
+    p.pro = PRO_ADALN; p.pro_w = hl.norm; p.pro_eps = d.head_rms_eps;
+    p.pro_shift = mod + (size_t)li * 3 * H; p.pro_scale = mod + (size_t)li * 3 * H + H; p.pro_ld = modld;
+    p.epi = EPI_SWIGLU;
+    out->push_back(p);
+    p = mk(hl.wdown, nullptr, c->s_hg, F, c->s_hx, H, M, H, F);
+    p.epi = EPI_GATED_RESID; p.epi_a = mod + (size_t)li * 3 * H + 2 * H; p.epi_lda = modld; p.res = c->s_hx; p.ldres = H;
+    out->push_back(p);
+  }
+  GemvP p = mk(c->h_final, nullptr, c->s_hx, H, c->s_v, 64, M, 64, H);
+  p.pro = PRO_ADALN; p.pro_w = nullptr; p.pro_eps = d.head_rms_eps;
+  p.pro_shift = mod + (size_t)LH * 3 * H; p.pro_scale = mod + (size_t)LH * 3 * H + H; p.pro_ld = modld;
+  out->push_back(p);
+}
+static DpmOp dpm_op(vv_ctx* c, int i, const float* noise, float cfg, float* latent_out) {
+  const int B = c->d.max_batch, N = c->n_steps;
+  DpmOp o;
+  memset(&o, 0, sizeof o);
+  if (i < 0) { o.z_in = c->s_z + B * 64; o.z_out = c->s_z; o.x0_in = c->s_x0 + B * 64; o.x0_out = c->s_x0; }
+  else {
+    o.z_in = c->s_z + (size_t)(i & 1) * B * 64; o.z_out = c->s_z + (size_t)((i + 1) & 1) * B * 64;
+    o.x0_in = c->s_x0 + (size_t)(i & 1) * B * 64; o.x0_out = c->s_x0 + (size_t)((i + 1) & 1) * B * 64;
+  }
+  const bool last = (i == N - 1);
+  o.v = c->s_v; o.noise = noise; o.coef = c->coef_dev; o.w_noisy = c->h_noisy; o.xout = c->s_hx; o.latent_out = last ? latent_out : nullptr;
+  o.step = i; o.B = B; o.H = c->d.hidden_size; o.do_proj = last ? 0 : 1; o.cfg = cfg;
+  return o;
+}
+static int build_sampler_program(vv_ctx* c, const float* noise, float cfg, float* latent_out, vv_ctx::Program* pr) {
+  std::vector<Op> ops;
+  Op o;
+  memset(&o, 0, sizeof o);
+  o.kind = OP_DPM; o.barrier_before = 0; o.d = dpm_op(c, -1, noise, cfg, latent_out);
+  ops.push_back(o);
+  for (int i = 0; i < c->n_steps; ++i) {
+    std::vector<GemvP> g;
+    head_step_gemvs(c, i, &g);
+    for (auto& p : g) ops.push_back(op_gemv(c, p, true));
+    memset(&o, 0, sizeof o);
+    o.kind = OP_DPM; o.barrier_before = 1; o.d = dpm_op(c, i, noise, cfg, latent_out);
+    ops.push_back(o);
+  }
+  return finish_program(c, ops, 2 * c->d.max_batch, pr);
+}
+
+static int enqueue_diffusion(const L& l, const float* cond, const float* noise, float cfg, float* latent_out, const vv_ctx::Program* prog) {
   vv_ctx* c = l.c;
   const auto& d = c->d;
-  const int H = d.hidden_size, F = d.head_ffn_dim, B = d.max_batch, M = 2 * B, LH = d.head_layers, N = c->n_steps;
+  const int H = d.hidden_size, B = d.max_batch, M = 2 * B, LH = d.head_layers, N = c->n_steps;
   if (N < 1) return fail(VV_ERR_STATE, "vv_set_diffusion_steps not called");
   const int modld = (3 * LH + 2) * H;
   GemvP p = mk(c->h_cond, nullptr, cond, H, c->s_condp, H, M, H, H);
   RET(linear(l, p));
   {
     const long long n = (long long)N * M * H;
-    head_cond_prep_kernel<<<(unsigned)((n + 255) / 256), 256, 0, l.s>>>(c->s_condp, c->temb, c->s_call, N, M, H);
-    CKL();
-    dpm_update_proj_kernel<<<dim3(B, (H + 255) / 256), 256, 0, l.s>>>(c->s_z + B * 64, c->s_z, c->s_x0 + B * 64, c->s_x0, c->s_v, noise,
-                                                                       c->coef_dev, -1, cfg, c->h_noisy, c->s_hx, nullptr, B, H, 1);
-    CKL();
-    c->launches += 2;
+    CK(launch_k(l, head_cond_prep_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, c->s_condp, c->temb, c->s_call, N, M, H));
   }
+  // AdaLN modulation of ALL steps and layers in one tensor-core GEMM: c_all [N*M, H] x W_mod^T -> [N*M, (3L+2)H].
+  // (the reference recomputes Linear(silu(c)) inside every head call, diffusion_head.py:159, 185; c depends only on (cond, t_i))
+  p = mk(c->h_mod, nullptr, c->s_call, H, c->s_mod, modld, N * M, modld, H);
+  RET(linear(l, p));
+  if (prog && prog->n_ops > 0) return launch_program(l, *prog);
+  CK(launch_k(l, dpm_update_proj_kernel, dim3(B, (H + 255) / 256), dim3(256), 0, c->s_z + B * 64, c->s_z, c->s_x0 + B * 64, c->s_x0, c->s_v, noise,
+              c->coef_dev, -1, cfg, c->h_noisy, c->s_hx, nullptr, B, H, 1));
   for (int i = 0; i < N; ++i) {
-    p = mk(c->h_mod, nullptr, c->s_call + (size_t)i * M * H, H, c->s_mod, modld, M, modld, H);
-    RET(linear(l, p));
-    for (int li = 0; li < LH; ++li) {
-      const HeadLayer& hl = c->head[li];
-      p = mk(hl.wgu, nullptr, c->s_hx, H, c->s_hg, F, M, 2 * F, H);
-      p.pro = PRO_ADALN; p.pro_w = hl.norm; p.pro_eps = d.head_rms_eps;
-      p.pro_shift = c->s_mod + (size_t)li * 3 * H; p.pro_scale = c->s_mod + (size_t)li * 3 * H + H; p.pro_ld = modld;
-      p.epi = EPI_SWIGLU;
-      RET(linear(l, p));
-      p = mk(hl.wdown, nullptr, c->s_hg, F, c->s_hx, H, M, H, F);
-      p.epi = EPI_GATED_RESID; p.epi_a = c->s_mod + (size_t)li * 3 * H + 2 * H; p.epi_lda = modld; p.res = c->s_hx; p.ldres = H;
-      RET(linear(l, p));
-    }
-    p = mk(c->h_final, nullptr, c->s_hx, H, c->s_v, 64, M, 64, H);
-    p.pro = PRO_ADALN; p.pro_w = nullptr; p.pro_eps = d.head_rms_eps;
-    p.pro_shift = c->s_mod + (size_t)LH * 3 * H; p.pro_scale = c->s_mod + (size_t)LH * 3 * H + H; p.pro_ld = modld;
-    RET(linear(l, p));
+    std::vector<GemvP> g;
+    head_step_gemvs(c, i, &g);
+    for (auto& q : g) RET(linear(l, q));
     const bool last = (i == N - 1);
-    {
-      float *zi = c->s_z + (size_t)(i & 1) * B * 64, *zo = c->s_z + (size_t)((i + 1) & 1) * B * 64;
-      float *xi = c->s_x0 + (size_t)(i & 1) * B * 64, *xo = c->s_x0 + (size_t)((i + 1) & 1) * B * 64;
-      dpm_update_proj_kernel<<<dim3(B, last ? 1 : (H + 255) / 256), 256, 0, l.s>>>(zi, zo, xi, xo, c->s_v, noise, c->coef_dev, i, cfg, c->h_noisy,
-                                                                                  c->s_hx, last ? latent_out : nullptr, B, H, last ? 0 : 1);
-    }
-    CKL();
-    c->launches++;
+    const DpmOp o = dpm_op(c, i, noise, cfg, latent_out);
+    CK(launch_k(l, dpm_update_proj_kernel, dim3(B, last ? 1 : (H + 255) / 256), dim3(256), 0, o.z_in, o.z_out, o.x0_in, o.x0_out, o.v, noise, o.coef, i,
+                cfg, o.w_noisy, o.xout, o.latent_out, B, H, o.do_proj));
   }
+  return 0;
+}
+
+static int sampler_program(vv_ctx* c, const float* noise, float cfg, float* latent_out, const vv_ctx::Program** out) {
+  *out = nullptr;
+  if (!c->use_mega) return 0;
+  char key[256];
+  snprintf(key, sizeof key, "samp:%p:%p:%a:%d", (const void*)noise, (void*)latent_out, cfg, c->n_steps);
+  auto it = c->programs.find(key);
+  if (it == c->programs.end()) {
+    vv_ctx::Program pr;
+    int r = build_sampler_program(c, noise, cfg, latent_out, &pr);
+    if (r < 0) return r;
+    if (r == 1) pr.n_ops = 0;
+    it = c->programs.emplace(key, pr).first;
+  }
+  *out = &it->second;
   return 0;
 }
 
@@ -1003,7 +1219,9 @@ extern "C" int vv_diffusion_sample(vv_ctx* c, const float* cond, const float* no
   CK(cudaSetDevice(c->device));
   char key[256];
   snprintf(key, sizeof key, "diff:%p:%p:%p:%a", (const void*)cond, (const void*)noise, (void*)latent_out, cfg);
-  return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_diffusion(l, cond, noise, cfg, latent_out); });
+  const vv_ctx::Program* prog = nullptr;
+  RET(sampler_program(c, noise, cfg, latent_out, &prog));
+  return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_diffusion(l, cond, noise, cfg, latent_out, prog); });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1012,10 +1230,8 @@ extern "C" int vv_diffusion_sample(vv_ctx* c, const float* cond, const float* no
 static int assemble(const L& l, const float* src, const float* hist, float* win, float* next, int B, int T, int ctx, int C,
                     const float* norm_w, float eps, float alpha, float beta) {
   const int rows = B * (ctx + T);
-  if (C >= 512) assemble_window_block_kernel<<<rows, 256, 0, l.s>>>(src, hist, win, next, B, T, ctx, C, norm_w, eps, alpha, beta);
-  else assemble_window_kernel<<<(rows + 7) / 8, 256, 0, l.s>>>(src, hist, win, next, B, T, ctx, C, norm_w, eps, alpha, beta);
-  CKL();
-  l.c->launches++;
+  if (C >= 512) CK(launch_k(l, assemble_window_block_kernel, dim3(rows), dim3(256), 0, src, hist, win, next, B, T, ctx, C, norm_w, eps, alpha, beta));
+  else CK(launch_k(l, assemble_window_kernel, dim3((rows + 7) / 8), dim3(256), 0, src, hist, win, next, B, T, ctx, C, norm_w, eps, alpha, beta));
   return 0;
 }
 
@@ -1026,9 +1242,7 @@ static int enqueue_block(const L& l, const Block& b, const float* xin, float* xo
   RET(assemble(l, xin, b.hist, c->s_win, b.next, B, T, 6, C, b.norm_w, eps, 1.f, 0.f));
   {
     const long long n = (long long)M * C;
-    dwconv_res_kernel<<<(unsigned)((n + 255) / 256), 256, 0, l.s>>>(xin, c->s_win, b.dw_w, b.dw_b, b.gamma, xout, B, T, C);
-    CKL();
-    c->launches++;
+    CK(launch_k(l, dwconv_res_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, xin, c->s_win, b.dw_w, b.dw_b, b.gamma, xout, B, T, C));
   }
   GemvP p;
   if (M <= 8) {
@@ -1036,10 +1250,8 @@ static int enqueue_block(const L& l, const Block& b, const float* xin, float* xo
     p.pro = PRO_RMSNORM; p.pro_w = b.ffn_norm_w; p.pro_eps = eps; p.epi = EPI_GELU;
     RET(linear(l, p));
   } else {
-    if (C >= 512) rows_norm_block_kernel<<<M, 256, 0, l.s>>>(xout, b.ffn_norm_w, c->s_xn, C, eps);
-    else rows_norm_kernel<<<(M + 7) / 8, 256, 0, l.s>>>(xout, b.ffn_norm_w, c->s_xn, M, C, eps);
-    CKL();
-    c->launches++;
+    if (C >= 512) CK(launch_k(l, rows_norm_block_kernel, dim3(M), dim3(256), 0, xout, b.ffn_norm_w, c->s_xn, C, eps));
+    else CK(launch_k(l, rows_norm_kernel, dim3((M + 7) / 8), dim3(256), 0, xout, b.ffn_norm_w, c->s_xn, M, C, eps));
     p = mk(b.w1, b.b1, c->s_xn, C, c->s_u, 4 * C, M, 4 * C, C);
     p.epi = EPI_GELU;
     RET(linear(l, p));
@@ -1055,9 +1267,7 @@ static int conv_apply(const L& l, const ConvL& cv, const float* win, float* y, i
   const int M = B * T_out;
   if (cv.wf) {
     const long long n = (long long)M * cv.N;
-    conv_naive_kernel<<<(unsigned)((n + 255) / 256), 256, 0, l.s>>>(cv.wf, cv.bias, win, xm, y, M, cv.N, cv.K);
-    CKL();
-    l.c->launches++;
+    CK(launch_k(l, conv_naive_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, cv.wf, cv.bias, win, xm, y, M, cv.N, cv.K));
     return 0;
   }
   GemvP p = mk(cv.w, cv.bias, win, 0, y, cv.N, M, cv.N, cv.K);
@@ -1091,9 +1301,7 @@ static int enqueue_decode(const L& l, const float* latent, const int32_t* active
   const int T = k.T[ns - 1];
   RET(assemble(l, xa, hd.hist, c->s_win, hd.next, B, T, 6, hd.Cin, nullptr, 0.f, 1.f, 0.f));
   RET(conv_apply(l, hd, c->s_win, audio, B, T, T));
-  advance_kernel<<<dim3(k.n_segs, B), 256, 0, l.s>>>(k.segs_dev, active);
-  CKL();
-  c->launches++;
+  CK(launch_k(l, advance_kernel, dim3(k.n_segs, B), dim3(256), 0, k.segs_dev, active));
   return 0;
 }
 
@@ -1119,9 +1327,7 @@ static int enqueue_encode(const L& l, const float* audio, const int32_t* active,
   const ConvL& hd = k.convs[ns];
   RET(assemble(l, xa, hd.hist, c->s_win, hd.next, B, 1, 6, hd.Cin, nullptr, 0.f, 1.f, 0.f));
   RET(conv_apply(l, hd, c->s_win, feat, B, 1, 1));
-  advance_kernel<<<dim3(k.n_segs, B), 256, 0, l.s>>>(k.segs_dev, active);
-  CKL();
-  c->launches++;
+  CK(launch_k(l, advance_kernel, dim3(k.n_segs, B), dim3(256), 0, k.segs_dev, active));
   return 0;
 }
 
@@ -1139,9 +1345,7 @@ static int enqueue_connect(const L& l, const float* latent, const float* sem, co
   p = mk(c->cs_fc2, c->cs_b2, c->s_c1, H, c->s_e, H, B, H, H);
   p.pro = PRO_RMSNORM; p.pro_w = c->cs_n; p.pro_eps = 1e-6f; p.epi = EPI_RESID; p.res = c->s_e; p.ldres = H;
   RET(linear(l, p));
-  select_embeds_kernel<<<B, 256, 0, l.s>>>(embeds, c->s_e, active, B, H);
-  CKL();
-  c->launches++;
+  CK(launch_k(l, select_embeds_kernel, dim3(B), dim3(256), 0, embeds, c->s_e, active, B, H));
   return 0;
 }
 
@@ -1172,8 +1376,10 @@ extern "C" int vv_frame_tail(vv_ctx* c, const float* hidden, const float* noise,
   char key[320];
   snprintf(key, sizeof key, "tail:%p:%p:%p:%p:%p:%p:%a", (const void*)hidden, (const void*)noise, (const void*)active, (void*)latent_out,
            (void*)audio_out, (void*)embeds, cfg);
+  const vv_ctx::Program* prog = nullptr;
+  RET(sampler_program(c, noise, cfg, latent_out, &prog));
   return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) {
-    RET(enqueue_diffusion(l, hidden, noise, cfg, latent_out));
+    RET(enqueue_diffusion(l, hidden, noise, cfg, latent_out, prog));
     RET(enqueue_decode(l, latent_out, active, audio_out));
     RET(enqueue_encode(l, audio_out, active, c->s_feat));
     return enqueue_connect(l, latent_out, c->s_feat, active, embeds);
@@ -1219,4 +1425,29 @@ extern "C" int vv_debug_gemv(vv_ctx* c, const void* w, const float* bias, const 
   p.pro = prologue; p.pro_w = pro_w; p.pro_eps = eps; p.epi = epilogue;
   if (epilogue == EPI_RESID) { p.res = y; p.ldres = N; }
   return linear(l, p);
+}
+
+// time `iters` grid barriers of a cooperative launch with `per_sm` CTAs per SM (debug / profiling aid)
+extern "C" int vv_debug_barrier_bench(vv_ctx* c, int iters, int per_sm, float* ms_out) {
+  if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t s;
+  CK(cudaStreamCreate(&s));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(c->sm_count * per_sm); cfg.blockDim = dim3(256); cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  float* sink = c->s_v;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaLaunchKernelEx(&cfg, barrier_bench_kernel, c->gridbar, 10, sink));
+  CK(cudaEventRecord(e0, s));
+  CK(cudaLaunchKernelEx(&cfg, barrier_bench_kernel, c->gridbar, iters, sink));
+  CK(cudaEventRecord(e1, s));
+  CK(cudaStreamSynchronize(s));
+  CK(cudaEventElapsedTime(ms_out, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(s);
+  return 0;
 }
