@@ -167,10 +167,10 @@ def cpu_sample(O, w, cfg, tok, L0, frames, args, steps=1, warmup=1):
     of the right size -- a 61K-token CPU prefill alone would take minutes), 30 diffusion steps, cfg 1.3."""
     dc = cfg.decoder_config
     torch.manual_seed(0)
-    pos, neg = O.KVCache(dc.num_hidden_layers), O.KVCache(dc.num_hidden_layers)
+    cap = L0 + (warmup + steps) * frames + 8
+    pos, neg = O.KVCache(dc.num_hidden_layers, capacity=cap), O.KVCache(dc.num_hidden_layers, capacity=cap)
     for l in range(dc.num_hidden_layers):
-        pos.k[l] = torch.randn(dc.num_key_value_heads, L0, dc.head_dim) * 0.5
-        pos.v[l] = torch.randn(dc.num_key_value_heads, L0, dc.head_dim) * 0.5
+        pos.preload(l, torch.randn(dc.num_key_value_heads, L0, dc.head_dim) * 0.5, torch.randn(dc.num_key_value_heads, L0, dc.head_dim) * 0.5)
     e0 = w["model.language_model.embed_tokens.weight"][tok.speech_start_id]
     a, s = O.StreamState(1), O.StreamState(1)
     times = []

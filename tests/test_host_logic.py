@@ -1,0 +1,121 @@
+"""CPU tests: C-ABI surface, scheduler tables, prompt sharding + gather over gloo (world_size 2), config/synth plumbing."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """include/vibevoice_b200.h <-> libvibevoice_b200.so <-> ctypes table (no compute calls, no GPU needed)."""
+    from vibevoice_b200 import _native as N
+    hdr = open(os.path.join(ROOT, "include", "vibevoice_b200.h")).read()
+    declared = set(re.findall(r"\b(vv_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"vv_ctx", "vv_model_desc", "vv_status", "vv_dtype"}
+    assert len(declared) >= 25
+    lib = N.load_library()
+    for name in declared:
+        assert hasattr(lib, name), "missing export %s" % name
+    assert declared == set(N.SYMBOLS), (declared ^ set(N.SYMBOLS))
+    assert lib.vv_abi_version() == 1
+
+
+def test_compute_fails_loudly_without_gpu():
+    from vibevoice_b200 import _native as N
+    from vibevoice_b200.configuration import preset_config
+    from vibevoice_b200.engine import Engine
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(N.VVError):
+        Engine(preset_config("tiny"), [1, 2, 3, 4])
+
+
+@pytest.mark.parametrize("n", [5, 10, 20, 30])
+def test_product_schedule_equals_oracle_tables(n):
+    from oracle import vv_oracle as O
+    from vibevoice_b200.schedule import DPMSolverMultistepScheduler
+    s = DPMSolverMultistepScheduler(num_train_timesteps=1000, beta_schedule="cosine", prediction_type="v_prediction").set_timesteps(n)
+    t = O.dpm_tables(n)
+    assert np.array_equal(s.timesteps.numpy(), t.timesteps)
+    assert np.array_equal(s.sigmas.numpy(), t.sigmas)
+    for j, a in enumerate([t.a0, t.s0, t.ks, t.kx, t.rinv]):
+        assert np.array_equal(s.coef[:, j], a)
+    assert np.array_equal(s.coef[:, 5].astype(np.int32), t.order)
+
+
+def test_scheduler_rejects_variants_off_the_path():
+    from vibevoice_b200.schedule import DPMSolverMultistepScheduler
+    with pytest.raises(NotImplementedError):
+        DPMSolverMultistepScheduler(algorithm_type="sde-dpmsolver++")
+    s = DPMSolverMultistepScheduler()
+    s2 = DPMSolverMultistepScheduler.from_config(s.config)
+    assert s2.config.solver_order == 2
+
+
+def test_configs_match_the_shipped_jsons():
+    from vibevoice_b200.configuration import VibeVoiceConfig, preset_config
+    from vibevoice_b200.synth import param_specs
+    import math
+    for name, n_params in (("1.5b", 2704021985), ("7b", 9343355361)):
+        cfg = preset_config(name)
+        assert sum(math.prod(s) for _, s, _ in param_specs(cfg)) == n_params
+    c = preset_config("1.5b")
+    assert c.acoustic_tokenizer_config.decoder_depth_list == [8, 3, 3, 3, 3, 3, 3]
+    ref = "/root/reference/vibevoice/configs/qwen2.5_1.5b_64k.json"
+    if os.path.exists(ref):
+        r = VibeVoiceConfig.from_pretrained(ref)
+        assert r.decoder_config.hidden_size == 1536 and r.decoder_config.num_key_value_heads == 2
+        assert r.diffusion_head_config.head_layers == 4 and r.semantic_vae_dim == 128
+
+
+def test_shard_prompts():
+    from vibevoice_b200.distributed import shard_prompts
+    for n, w in ((32, 8), (7, 2), (3, 4), (0, 2)):
+        seen = []
+        for r in range(w):
+            seen += shard_prompts(n, r, w)
+        assert seen == list(range(n))
+    assert shard_prompts(32, 3, 8) == [12, 13, 14, 15]
+
+
+def _gather_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from vibevoice_b200.distributed import gather_waveforms, shard_prompts
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    mine = shard_prompts(5, rank, world)
+    wavs = [None if i == 3 else torch.full((1, 3200 * (i + 1)), float(i)) for i in mine]
+    res = gather_waveforms(wavs)
+    if rank == 0:
+        flat = [w for row in res for w in row]
+        q.put([(None if w is None else (tuple(w.shape), float(w.mean()))) for w in flat])
+    dist.destroy_process_group()
+
+
+def test_gather_waveforms_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 200
+    ps = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    out = q.get(timeout=120)
+    for p in ps:
+        p.join(60)
+        assert p.exitcode == 0
+    assert out == [((1, 3200), 0.0), ((1, 6400), 1.0), ((1, 9600), 2.0), None, ((1, 16000), 4.0)]
+
+
+def test_streamer_contract():
+    from vibevoice_b200.streamer import AudioStreamer
+    st = AudioStreamer(batch_size=2, stop_signal=None)
+    st.put(torch.ones(2, 1, 4), torch.tensor([0, 1]))
+    st.end(torch.tensor([1]))
+    assert st.finished_flags == [False, True]
+    st.put(torch.ones(1, 1, 4) * 2, torch.tensor([1]))          # ignored: finished
+    st.end()
+    assert [c.sum().item() for c in st.get_stream(0)] == [4.0]
+    assert len(list(st.get_stream(1))) == 1
