@@ -4,8 +4,9 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port) on host cores
 
-Workload (BASELINE.json configs[1]): VibeVoice-1.5B, 1 speaker, 61,440-token synthetic prompt, 4,095
-generated speech frames (context ends at 65,535), 30 diffusion steps, cfg 1.3, random-init weights, one prompt per GPU.
+Workload (BASELINE.json configs[1]): VibeVoice-1.5B, 1 speaker, 64K context = 63,488-token synthetic prompt +
+2,047 generated speech frames (context ends at 65,535 = max_position_embeddings - 1; 273 s of audio per step), 30 diffusion
+steps, cfg 1.3, random-init weights, one prompt per GPU.  (`--prompt-len 61440 --frames 4095` gives SURVEY's variant.)
 A "step" is one complete pass of the hot path over that prompt:
   value : K steps of the steady-state frame loop (LM decode pos+neg -> CFG diffusion sampler -> codec decode -> semantic
           encode -> connectors) with the prompt KV already resident in HBM; device-timed with CUDA events.
@@ -108,6 +109,30 @@ def log(msg):
     sys.stderr.flush()
 
 
+def usable_cores() -> int:
+    """Cores this process may actually use: scheduler affinity capped by the cgroup CPU quota (os.cpu_count() reports the
+    host's cores inside a container and oversubscribing them makes the CPU baseline pathologically slow)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    n = min(n, max(1, int(q / per + 0.5)))
+            break
+        except Exception:
+            continue
+    return max(1, n)
+
+
 def dist_env():
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     return rank, world, local
@@ -118,7 +143,7 @@ def workload(args):
     cfg = preset_config(args.model)
     maxpos = cfg.decoder_config.max_position_embeddings
     if args.model in ("1.5b", "7b"):
-        L0 = args.prompt_len if args.prompt_len is not None else (61440 if args.model == "1.5b" else 28672)
+        L0 = args.prompt_len if args.prompt_len is not None else (63488 if args.model == "1.5b" else 30720)
         F = args.frames if args.frames is not None else maxpos - 1 - L0
     else:
         L0 = args.prompt_len or 64
@@ -145,7 +170,7 @@ def run_reference(args):
     from oracle import vv_oracle as O
     from vibevoice_b200.synth import SynthTokenizer, synth_state_dict
     cfg, L0, F = workload(args)
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(usable_cores())
     tok = SynthTokenizer(cfg.decoder_config.vocab_size)
     t0 = time.time()
     w = {k: v.float() for k, v in synth_state_dict(cfg, 1234, torch.bfloat16, parts=("lm", "head", "acoustic_decoder", "semantic",
@@ -162,27 +187,35 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def cpu_sample(O, w, cfg, tok, L0, frames, args, steps=1, warmup=1):
-    """Bounded sample of the same workload on the CPU: `frames` steady-state frames at context L0 (synthetic KV prefix
-    of the right size -- a 61K-token CPU prefill alone would take minutes), 30 diffusion steps, cfg 1.3."""
+def cpu_sample(O, w, cfg, tok, L0, frames, args, steps=1, warmup=1, budget_s=25.0):
+    """Bounded sample of the same workload on the CPU: steady-state frames at context L0 (synthetic KV prefix of the right
+    size -- a 64K-token CPU prefill alone would take minutes), 30 diffusion steps, cfg 1.3.  Each step is `frames` frames; if
+    the first warm-up frame shows that the whole sample would exceed `budget_s`, frames/step drops to 1."""
     dc = cfg.decoder_config
     torch.manual_seed(0)
-    cap = L0 + (warmup + steps) * frames + 8
+    cap = L0 + (warmup + steps) * frames + 16
     pos, neg = O.KVCache(dc.num_hidden_layers, capacity=cap), O.KVCache(dc.num_hidden_layers, capacity=cap)
     for l in range(dc.num_hidden_layers):
         pos.preload(l, torch.randn(dc.num_key_value_heads, L0, dc.head_dim) * 0.5, torch.randn(dc.num_key_value_heads, L0, dc.head_dim) * 0.5)
     e0 = w["model.language_model.embed_tokens.weight"][tok.speech_start_id]
     a, s = O.StreamState(1), O.StreamState(1)
+    t = time.time()
+    O.steady_frames(w, cfg, tok, pos, neg, e0, 1, args.cfg_scale, args.diffusion_steps, a, s)      # untimed first-touch frame
+    t_frame = time.time() - t
+    if t_frame * frames * (warmup + steps) > budget_s:
+        frames = 1
+    if t_frame * (warmup + steps) > 4 * budget_s:
+        warmup = min(warmup, 1)
     times = []
     for it in range(warmup + steps):
         t = time.time()
         O.steady_frames(w, cfg, tok, pos, neg, e0, frames, args.cfg_scale, args.diffusion_steps, a, s)
         times.append(time.time() - t)
-        pos.truncate(L0); neg.truncate(0)
     el = sum(times[warmup:])
     return {"value": steps * frames * AUDIO_S_PER_FRAME / el, "ms_per_step": 1e3 * el / steps, "cores": torch.get_num_threads(),
-            "sample": "%d steady-state frames at ctx %d (synthetic KV prefix), %d diffusion steps, fp32, torch %d threads; "
-                      "%d timed step(s) after %d warm-up" % (frames, L0, args.diffusion_steps, torch.get_num_threads(), steps, warmup)}
+            "sample": "%d steady-state frame(s)/step at ctx %d (synthetic KV prefix), %d diffusion steps, fp32, torch %d threads "
+                      "(os.cpu_count %d); %d timed step(s) after %d warm-up" % (frames, L0, args.diffusion_steps, torch.get_num_threads(),
+                                                                                os.cpu_count() or 0, steps, warmup)}
 
 
 def config_dict(args, cfg, L0, F):
@@ -311,9 +344,10 @@ def run_b200(args):
         for _ in range(K):
             wav = e2e_step()
         if world > 1:   # the trivial result gather: waveforms to rank 0 over NCCL
-            mine = torch.stack([w_[0] for w_ in wav]).to(dev)
-            bufs = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
-            dist.gather(mine, bufs, dst=0)
+            from vibevoice_b200.distributed import gather_waveforms
+            gathered = gather_waveforms([w_.to(dev) for w_ in wav], device=dev, dst=0)
+            if rank == 0:
+                assert sum(len(r_) for r_ in gathered) == B * world
         ev1.record(eng.stream)
         barrier()
         ms_e2e = max(ev0.elapsed_time(ev1), (time.time() - t0) * 1e3 if world == 1 else 0.0)
@@ -333,7 +367,7 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import vv_oracle as O
-        torch.set_num_threads(os.cpu_count())
+        torch.set_num_threads(usable_cores())
         names = [n for n, _, _ in __import__("vibevoice_b200.synth", fromlist=["param_specs"]).param_specs(cfg, parts)]
         w = {}
         for name, t in iter_synth_state_dict_fast(cfg, 1234 + rank, device=dev, parts=parts):

@@ -188,7 +188,31 @@ def gen_lm(ns, preset="tiny"):
     return dict(preset=preset, ids=ids, step_embeds=steps, hidden=hs)
 
 
-GENERATORS = dict(scheduler=gen_scheduler, head=gen_head, codec=gen_codec, connector=gen_connector, lm=gen_lm)
+def gen_voice_prompt(ns, preset="tiny"):
+    """The reference's own `_process_speech_inputs` (modeling_vibevoice_inference.py:149-163) on two ragged voice prompts."""
+    cfg = preset_config(preset)
+    ac, _ = _tokenizer_models(ns, cfg)
+    sd = synth_state_dict(cfg, SEED, torch.float32, parts=("connectors",))
+    con = ns.modeling.SpeechConnector(64, cfg.decoder_config.hidden_size).eval()
+    con.load_state_dict(_sub(sd, "model.acoustic_connector."), strict=True)
+    from vibevoice_b200.synth import SPEECH_BIAS_FACTOR, SPEECH_SCALING_FACTOR
+    infer = sys.modules["vibevoice.modular.modeling_vibevoice_inference"].VibeVoiceForConditionalGenerationInference
+    fake = types.SimpleNamespace(model=types.SimpleNamespace(acoustic_tokenizer=ac, acoustic_connector=con,
+                                                             speech_bias_factor=torch.tensor(SPEECH_BIAS_FACTOR),
+                                                             speech_scaling_factor=torch.tensor(SPEECH_SCALING_FACTOR)))
+    g = torch.Generator().manual_seed(51)
+    wavs = torch.zeros(2, 3200 * 3 + 100)
+    wavs[0] = torch.randn(wavs.shape[1], generator=g) * 0.05
+    wavs[1, :3200 * 2 + 7] = torch.randn(3200 * 2 + 7, generator=g) * 0.05
+    masks = torch.zeros(2, 4, dtype=torch.bool)
+    masks[0, :4] = True
+    masks[1, :3] = True
+    torch.manual_seed(77)
+    feats, connected = infer._process_speech_inputs(fake, wavs, masks)
+    return dict(preset=preset, wavs=wavs, masks=masks, seed=77, features=feats.clone(), connected=connected.clone())
+
+
+GENERATORS = dict(voice_prompt=gen_voice_prompt, scheduler=gen_scheduler, head=gen_head, codec=gen_codec, connector=gen_connector, lm=gen_lm)
 
 
 def main():

@@ -144,8 +144,14 @@ def load_reference():
         raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
     _install_fake_diffusers()
     _patch_transformers()
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    # this repo ships a drop-in `vibevoice/` alias package; make sure the names below resolve to the REFERENCE tree
+    for name in [n for n in sys.modules if n == "vibevoice" or n.startswith("vibevoice.")]:
+        f = getattr(sys.modules[name], "__file__", "") or ""
+        if not f.startswith(REFERENCE_ROOT):
+            del sys.modules[name]
+    if REFERENCE_ROOT in sys.path:
+        sys.path.remove(REFERENCE_ROOT)
+    sys.path.insert(0, REFERENCE_ROOT)
     import importlib
 
     cfg = importlib.import_module("vibevoice.modular.configuration_vibevoice")

@@ -319,3 +319,91 @@ def test_generate_free_running_tokens(tiny2):
     first_tie = next((i for i, m in enumerate(margins) if m < 1e-3), len(margins))
     upto = min(n, ids.shape[1] + first_tie)
     assert torch.equal(out.sequences[:, :upto], ref.sequences[:, :upto])
+
+
+@pytest.fixture(scope="module")
+def real15():
+    """VibeVoice-1.5B layer shapes (H=1536, I=8960, 12/2 heads, full-size head and codec), 2 LM layers, small vocab."""
+    from vibevoice_b200.modeling import VibeVoiceForConditionalGenerationInference
+    cfg = preset_config("1.5b-l2")
+    tok = SynthTokenizer(cfg.decoder_config.vocab_size)
+    parts = ("lm", "head", "acoustic_decoder", "semantic", "connectors", "lm_head")
+    sd = synth_state_dict(cfg, SEED, torch.bfloat16, parts=parts)
+    m = VibeVoiceForConditionalGenerationInference(cfg, tok, max_batch=1)
+    m.load_state_dict(sd, tok)
+    yield m, cfg, tok, sd
+    m.engine.close()
+
+
+def test_real_shapes_closed_loop_vs_oracle(real15):
+    """Same closed-loop check as the tiny model but at the real 1.5B kernel shapes (K=1536/4608/8960 GEMVs, C up to 2048 codec,
+    T up to 3200, tensor-core GEMM and attention paths, 10 diffusion steps)."""
+    from oracle import vv_oracle as O
+    from vibevoice_b200.modeling import ForcedTokenScript
+    model, cfg, tok, sd = real15
+    dc = cfg.decoder_config
+    g = torch.Generator().manual_seed(5)
+    ids = torch.randint(0, dc.vocab_size - 20, (1, 70), generator=g)
+    ids[:, -1] = tok.speech_start_id
+    script = [_scripted(tok, "ddesdx")]
+    model.set_ddpm_inference_steps(10)
+    torch.manual_seed(0)
+    out = model.generate(input_ids=ids, tokenizer=tok, cfg_scale=1.3, is_prefill=False, logits_processor=[ForcedTokenScript(script)],
+                         max_new_tokens=12, show_progress_bar=False)
+    torch.manual_seed(0)
+    ref = O.generate(sd, cfg, ids, None, tok, cfg_scale=1.3, num_steps=10, max_new_tokens=12, forced_tokens=script, kv_bf16=True)
+    assert torch.equal(out.sequences, ref.sequences)
+    a, b = out.speech_outputs[0].cpu(), ref.speech_outputs[0]
+    assert a.shape == b.shape == (1, 3 * 3200)
+    e = rel_l2(a, b)
+    report("generate_real_shapes_1.5b", audio_rel_l2=e)
+    assert e < 1e-2, e
+
+
+def test_voice_prompt_and_torch_prefill_vs_oracle():
+    """a-9: voice-prompt prefill (acoustic encoder -> Gaussian sample -> connector -> scatter into the prompt) and the PyTorch
+    prompt prefill handing K/V to the paged pool, then the usual CUDA loop.  The prefill runs in bf16 on library kernels (like the
+    CUDA reference), the oracle in fp32 -> looser audio tolerance (5e-2), token bookkeeping still exact."""
+    from oracle import vv_oracle as O
+    from vibevoice_b200.modeling import ForcedTokenScript, VibeVoiceForConditionalGenerationInference
+    cfg = preset_config("tiny")
+    tok = SynthTokenizer(cfg.decoder_config.vocab_size)
+    sd = synth_state_dict(cfg, SEED, torch.bfloat16)
+    model = VibeVoiceForConditionalGenerationInference(cfg, tok, max_batch=1, torch_prefill=True)
+    model.load_state_dict(sd, tok)
+    g = torch.Generator().manual_seed(8)
+    L0 = 30
+    ids = torch.randint(0, cfg.decoder_config.vocab_size - 20, (1, L0), generator=g)
+    ids[:, -1] = tok.speech_start_id
+    sim = torch.zeros(1, L0, dtype=torch.bool)
+    sim[0, 5:9] = True
+    sim[0, 14:17] = True
+    ids[sim] = tok.speech_diffusion_id
+    wavs = torch.zeros(2, 3200 * 3 + 100)
+    wavs[0] = torch.randn(wavs.shape[1], generator=g) * 0.05
+    wavs[1, :3200 * 2 + 7] = torch.randn(3200 * 2 + 7, generator=g) * 0.05
+    masks = torch.zeros(2, 4, dtype=torch.bool)
+    masks[0, :4] = True
+    masks[1, :3] = True
+    noise = (torch.randn(2, generator=g), torch.randn(2, 4, 64, generator=g))
+    want_emb = O.voice_prompt_embeds(sd, cfg, wavs, masks, noise=noise)
+    got_emb = model._voice(wavs, masks, float(sd["model.speech_scaling_factor"]), float(sd["model.speech_bias_factor"]), noise=noise).cpu()
+    e = rel_l2(got_emb, want_emb)
+    report("voice_prompt_embeds", rel_l2=e)
+    assert e < 1e-4, e
+    script = [_scripted(tok, "dddx")]
+    model.set_ddpm_inference_steps(5)
+    torch.manual_seed(0)
+    out = model.generate(input_ids=ids, tokenizer=tok, cfg_scale=1.3, is_prefill=True, speech_tensors=wavs, speech_masks=masks,
+                         speech_input_mask=sim, _voice_noise=noise, logits_processor=[ForcedTokenScript(script)], max_new_tokens=8,
+                         show_progress_bar=False)
+    torch.manual_seed(0)
+    ref = O.generate(sd, cfg, ids, None, tok, cfg_scale=1.3, num_steps=5, max_new_tokens=8, forced_tokens=script, kv_bf16=True,
+                     speech_embeds=[(sim[0], want_emb)])
+    assert torch.equal(out.sequences, ref.sequences)
+    a, b = out.speech_outputs[0].cpu(), ref.speech_outputs[0]
+    assert a.shape == b.shape == (1, 9600)
+    e = rel_l2(a, b)
+    report("generate_voice_prompt_torch_prefill", audio_rel_l2=e)
+    assert e < 5e-2, e
+    model.engine.close()

@@ -88,3 +88,14 @@ def test_qwen2_prefill_and_decode(golden):
         hs = O.qwen2_forward(w, dc, emb[0], cache, len(cache))
         close(hs, g["hidden"][i + 1], rtol=1e-4, atol=1e-5)
     assert len(cache) == g["ids"].shape[1] + len(g["step_embeds"])
+
+
+def test_voice_prompt_embeds(golden):
+    """a-9: acoustic encoder + Gaussian sampling + connector against the reference's `_process_speech_inputs` (same CPU RNG stream)."""
+    g = golden("voice_prompt")
+    cfg = preset_config(g["preset"])
+    w = synth_state_dict(cfg, SEED, torch.float32, parts=("acoustic_encoder", "connectors"))
+    torch.manual_seed(g["seed"])
+    got = O.voice_prompt_embeds(w, cfg, g["wavs"], g["masks"])
+    assert got.shape == g["connected"].shape == (7, cfg.decoder_config.hidden_size)
+    close(got, g["connected"], rtol=1e-4, atol=1e-5)

@@ -59,6 +59,9 @@ class VibeVoiceForConditionalGenerationInference:
         self._torch_prefill = torch_prefill      # keep bf16 LM weights for the PyTorch prompt prefill (prefill.py)
         self._prefill = None
         self._lm_sd: Dict[str, torch.Tensor] = {}
+        self._voice_sd: Dict[str, torch.Tensor] = {}
+        self._voice = None
+        self._scale = self._bias = None
         self._tok = tokenizer_ids
         self._device_index = device
         self._max_batch = max_batch
@@ -106,10 +109,15 @@ class VibeVoiceForConditionalGenerationInference:
                 eng.load_tensor(name, t)
                 if self._torch_prefill and name.startswith("model.language_model."):
                     self._lm_sd[name] = t.to(device=eng.device, dtype=torch.bfloat16)
+                elif self._torch_prefill and (name.startswith("model.acoustic_tokenizer.encoder.") or name.startswith("model.acoustic_connector.")):
+                    self._voice_sd[name] = t.to(device=eng.device, dtype=torch.float32)
         eng.finalize(scale, bias)
+        self._scale, self._bias = scale, bias
         if self._torch_prefill:
-            from .prefill import TorchPrefill
+            from .prefill import TorchPrefill, TorchVoicePrompt
             self._prefill = TorchPrefill(self.config, self._lm_sd, eng.device)
+            if any(k.startswith("model.acoustic_tokenizer.encoder.") for k in self._voice_sd):
+                self._voice = TorchVoicePrompt(self.config, self._voice_sd, eng.device)
         return self
 
     @classmethod
@@ -177,8 +185,9 @@ class VibeVoiceForConditionalGenerationInference:
             raise NotImplementedError("do_sample=True (multinomial over the valid ids) is a 'next' row (SURVEY 8f-3)")
         if not kwargs.get("refresh_negative", True):
             raise NotImplementedError("refresh_negative=False is a 'next' row (SURVEY 8f-3)")
-        if is_prefill and speech_tensors is not None:
-            raise NotImplementedError("voice-prompt prefill (acoustic encoder, a-9) is not on the CUDA path yet; pass is_prefill=False")
+        use_voice = bool(is_prefill and speech_tensors is not None)
+        if use_voice and (self._voice is None or self._prefill is None):
+            raise N.VVError("voice-prompt prefill needs torch_prefill=True and the acoustic-encoder weights (a-9 runs on PyTorch library kernels)")
         forced: Optional[ForcedTokenScript] = None
         if logits_processor is not None:
             procs = logits_processor if isinstance(logits_processor, (list, tuple)) else [logits_processor]
@@ -229,9 +238,23 @@ class VibeVoiceForConditionalGenerationInference:
             embw = self._lm_sd["model.language_model.embed_tokens.weight"]
             hids = []
             with torch.cuda.stream(eng.stream):
+                voice_embeds = None
+                if use_voice:     # :216-224: acoustic encoder -> sample -> (x+bias)*scale -> connector, scattered at speech_input_mask
+                    voice_embeds = self._voice(torch.as_tensor(speech_tensors), torch.as_tensor(speech_masks).bool(), self._scale, self._bias,
+                                               noise=kwargs.get("_voice_noise"))
+                    sim = torch.as_tensor(speech_input_mask).bool().cpu()
+                    counts = sim.sum(dim=-1).tolist()
+                    offs = [0]
+                    for c_ in counts:
+                        offs.append(offs[-1] + int(c_))
                 for r in range(b):
-                    ids_r = input_ids[r][attention_mask[r].bool()].to(eng.device)
-                    hids.append(self._prefill.run(eng, r, embw[ids_r]))
+                    keep = attention_mask[r].bool()
+                    ids_r = input_ids[r][keep].to(eng.device)
+                    e = embw[ids_r]
+                    if voice_embeds is not None and counts[r]:
+                        e = e.clone()
+                        e[sim[r][keep].to(eng.device)] = voice_embeds[offs[r]:offs[r + 1]].to(e.dtype)
+                    hids.append(self._prefill.run(eng, r, e))
                     eng.kv_set_len(r, int(lens[r]))
             eng.embed_tokens([pad_tok] * B + [start_id] * B, eng.embeds)     # negative rows: [<speech_start>] at pos 0 (:379-386)
             eng.lm_decode()
