@@ -587,7 +587,12 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(GemvP p) {
   __shared__ __align__(16) bf16 Ws[MM_ST][MM_BN][MM_LD];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int bm = blockIdx.y * MM_BM, bn = blockIdx.x * MM_BN;
-  const int K = p.K, nk = (K + MM_BK - 1) / MM_BK;
+  const int K = p.K, nk_all = (K + MM_BK - 1) / MM_BK;
+  // split-K (gridDim.z > 1): only launched for in-place residual epilogues (y == res); each split atomically adds its
+  // scaled partial into y, split 0 also adds the bias.  Few-CTA, long-K shapes (codec FFN2) get z-times the parallelism.
+  const int kz = blockIdx.z, nz = gridDim.z;
+  const int kt0 = (int)(((long long)nk_all * kz) / nz), kt1 = (int)(((long long)nk_all * (kz + 1)) / nz);
+  const int nk = kt1 - kt0;
   // A loader: thread -> row tid/4, 16 consecutive k at (tid%4)*16
   const int ar = tid >> 2, ac = (tid & 3) * 16;
   const float* arow = (bm + ar < p.M) ? p.x + p.xmap.off(bm + ar) : nullptr;
@@ -596,7 +601,7 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(GemvP p) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int idx = tid + i * 128, r = idx >> 3, c = (idx & 7) * 8;
-      const int n = bn + r, k = kt * MM_BK + c;
+      const int n = bn + r, k = (kt0 + kt) * MM_BK + c;
       const bool ok = (n < p.N) && (k < K);
       cp_async16(&Ws[stage][r][c], p.W + (size_t)(ok ? n : 0) * K + (ok ? k : 0), ok ? 16 : 0);
     }
@@ -605,7 +610,7 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(GemvP p) {
   auto load_a = [&](int kt) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int k = kt * MM_BK + ac + i * 4;
+      const int k = (kt0 + kt) * MM_BK + ac + i * 4;
       areg[i] = (arow && k < K) ? *reinterpret_cast<const float4*>(arow + k) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
@@ -669,7 +674,16 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(GemvP p) {
       for (int q = 0; q < 4; ++q) {
         const int m = bm + mt * 16 + (lane >> 2) + (q >> 1) * 8;
         const int n = bn + warp * 16 + nt * 8 + (lane & 3) * 2 + (q & 1);
-        if (m < p.M && n < p.N) epi_store(p, m, n, acc[mt][nt][q] + (p.bias ? p.bias[n] : 0.f));
+        if (m < p.M && n < p.N) {
+          if (nz == 1) {
+            epi_store(p, m, n, acc[mt][nt][q] + (p.bias ? p.bias[n] : 0.f));
+          } else {
+            float v = acc[mt][nt][q] + ((kz == 0 && p.bias) ? p.bias[n] : 0.f);
+            if (p.epi == EPI_GAMMA_RESID) v *= p.epi_a[n];
+            else if (p.epi == EPI_GATED_RESID) v *= p.epi_a[(long long)m * p.epi_lda + n];
+            atomicAdd(p.y + (long long)m * p.ldy + n, v);
+          }
+        }
       }
 }
 
@@ -992,13 +1006,17 @@ __global__ void __launch_bounds__(128) attn_partial_kernel(const float* __restri
 // with its own online-softmax state, merged through shared memory at the end.
 // ---------------------------------------------------------------------------------------------
 constexpr int AT2_TILE = 64, AT2_LD = HD + 8;
-constexpr int AT2_SMEM = 4 * AT2_TILE * AT2_LD * 2 + 16 * AT2_LD * 2;
+constexpr int AT2_SMEM = 4 * AT2_TILE * AT2_LD * 2 + 16 * AT2_LD * 2 + 2 * HD * 2;
 VV_DEVINL void ldmatrix_x4_trans(unsigned (&r)[4], const void* smem) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(sa));
 }
-__global__ void __launch_bounds__(128) attn_partial_mma_kernel(const float* __restrict__ q_rot, KvView kv, float* __restrict__ part_acc,
-                                                               float* __restrict__ part_ml, int nsplit, float scale) {
+// `fused_rope`: q_src is the raw QKV projection [M, (nq+2nkv)*HD] (bias added); RoPE of q is applied while staging Q, and the
+// split that owns the newest token rotates k, rounds K/V to bf16, stores them into the paged pool and splices them into its
+// shared-memory tile (replaces rope_append_kernel: one launch and one q round trip less per layer).
+__global__ void __launch_bounds__(128) attn_partial_mma_kernel(const float* __restrict__ q_src, int fused_rope, const float* __restrict__ inv_freq,
+                                                               KvView kv, float* __restrict__ part_acc, float* __restrict__ part_ml, int nsplit,
+                                                               float scale) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(16) unsigned char at_smem[];
@@ -1006,10 +1024,13 @@ __global__ void __launch_bounds__(128) attn_partial_mma_kernel(const float* __re
   TileP Ks = reinterpret_cast<TileP>(at_smem);
   TileP Vs = reinterpret_cast<TileP>(at_smem + 2 * AT2_TILE * AT2_LD * 2);
   bf16 (*Qs)[AT2_LD] = reinterpret_cast<bf16 (*)[AT2_LD]>(at_smem + 4 * AT2_TILE * AT2_LD * 2);
+  bf16* knew = reinterpret_cast<bf16*>(at_smem + 4 * AT2_TILE * AT2_LD * 2 + 16 * AT2_LD * 2);
+  bf16* vnew = knew + HD;
   const int s = blockIdx.x, g = blockIdx.y, m = blockIdx.z;
   if (!kv.row_mode[m]) return;
   const int G = kv.q_heads / kv.kv_heads;
-  const int L = kv.kv_len[m] + 1;
+  const int pos = kv.kv_len[m];
+  const int L = pos + 1;
   const int ntiles = (L + AT2_TILE - 1) / AT2_TILE;
   const int tps = (ntiles + nsplit - 1) / nsplit;
   const int t_begin = s * tps, t_end = min(ntiles, (s + 1) * tps);
@@ -1035,12 +1056,51 @@ __global__ void __launch_bounds__(128) attn_partial_mma_kernel(const float* __re
   prefetch(t_begin, 0);
   cp_async_commit();
   // Q: rows 0..7 = hi(q*scale) of heads 0..G-1, rows 8..15 = lo
-  for (int i = tid; i < 8 * HD; i += 128) {
-    const int h = i / HD, d = i % HD;
-    const float v = (h < G) ? q_rot[((size_t)m * kv.q_heads + g * G + h) * HD + d] * scale : 0.f;
-    const bf16 hi = __float2bfloat16_rn(v);
-    Qs[h][d] = hi;
-    Qs[h + 8][d] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  const bool owner = fused_rope && (ntiles - 1 >= t_begin) && (ntiles - 1 < t_end);
+  if (!fused_rope) {
+    for (int i = tid; i < 8 * HD; i += 128) {
+      const int h = i / HD, d = i % HD;
+      const float v = (h < G) ? q_src[((size_t)m * kv.q_heads + g * G + h) * HD + d] * scale : 0.f;
+      const bf16 hi = __float2bfloat16_rn(v);
+      Qs[h][d] = hi;
+      Qs[h + 8][d] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+  } else {
+    const float* row = q_src + (size_t)m * (kv.q_heads + 2 * kv.kv_heads) * HD;
+    for (int i = tid; i < 8 * (HD / 2); i += 128) {
+      const int h = i / (HD / 2), d = i % (HD / 2);
+      float o1 = 0.f, o2 = 0.f;
+      if (h < G) {
+        float sn, cs;
+        sincosf((float)pos * inv_freq[d], &sn, &cs);
+        const float x1 = row[(g * G + h) * HD + d], x2 = row[(g * G + h) * HD + d + HD / 2];
+        o1 = (x1 * cs - x2 * sn) * scale;
+        o2 = (x2 * cs + x1 * sn) * scale;
+      }
+      const bf16 h1 = __float2bfloat16_rn(o1), h2 = __float2bfloat16_rn(o2);
+      Qs[h][d] = h1; Qs[h][d + HD / 2] = h2;
+      Qs[h + 8][d] = __float2bfloat16_rn(o1 - __bfloat162float(h1));
+      Qs[h + 8][d + HD / 2] = __float2bfloat16_rn(o2 - __bfloat162float(h2));
+    }
+    if (owner) {
+      const int page = kv.page_table[(size_t)m * kv.max_pages + pos / KV_PAGE];
+      const size_t oo = (((size_t)page * kv.kv_heads + g) * KV_PAGE + (pos % KV_PAGE)) * HD;
+      if (tid < HD / 2) {
+        const int d = tid;
+        float sn, cs;
+        sincosf((float)pos * inv_freq[d], &sn, &cs);
+        const float x1 = row[(kv.q_heads + g) * HD + d], x2 = row[(kv.q_heads + g) * HD + d + HD / 2];
+        const bf16 k1 = __float2bfloat16_rn(x1 * cs - x2 * sn), k2 = __float2bfloat16_rn(x2 * cs + x1 * sn);
+        knew[d] = k1; knew[d + HD / 2] = k2;
+        kv.kpool[oo + d] = k1; kv.kpool[oo + d + HD / 2] = k2;
+      } else {
+        for (int d = tid - HD / 2; d < HD; d += 64) {
+          const bf16 vv_ = __float2bfloat16_rn(row[(kv.q_heads + kv.kv_heads + g) * HD + d]);
+          vnew[d] = vv_;
+          kv.vpool[oo + d] = vv_;
+        }
+      }
+    }
   }
   __syncthreads();
   unsigned qa[8][4];
@@ -1058,6 +1118,11 @@ __global__ void __launch_bounds__(128) attn_partial_mma_kernel(const float* __re
     cp_async_commit();
     cp_async_wait<1>();
     __syncthreads();
+    if (owner && t == ntiles - 1) {              // splice the fresh K/V row over whatever the pool held when the tile was fetched
+      Ks[buf][pos - tok0][tid] = knew[tid];
+      Vs[buf][pos - tok0][tid] = vnew[tid];
+      __syncthreads();
+    }
     float sa[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
@@ -1134,21 +1199,23 @@ __global__ void __launch_bounds__(128) attn_partial_mma_kernel(const float* __re
   }
 }
 
-// merge the split partials: weights computed once per (row, head) in shared memory, then a flat weighted sum
+// merge the split partials: weights computed once per (row, head) in shared memory; warp w accumulates splits s = w (mod 4)
+// with one float4 (4 dims) per lane, the four warp sums are added through shared memory.
 __global__ void __launch_bounds__(128) attn_combine_kernel(const float* __restrict__ part_acc, const float* __restrict__ part_ml,
                                                            const int* __restrict__ row_mode, float* __restrict__ out, int q_heads,
                                                            int nsplit) {
   pdl_trigger();
   pdl_wait();
-  const int h = blockIdx.x, m = blockIdx.y, d = threadIdx.x;
+  const int h = blockIdx.x, m = blockIdx.y, d = threadIdx.x, lane = d & 31, warp = d >> 5;
   if (!row_mode[m]) return;
   const size_t o = ((size_t)m * q_heads + h) * nsplit;
   __shared__ float wsh[512];
   __shared__ float red[4];
+  __shared__ __align__(16) float part[4][HD];
   float mx = -INFINITY;
   for (int s = d; s < nsplit; s += 128) mx = fmaxf(mx, part_ml[(o + s) * 2]);
   mx = warp_max(mx);
-  if ((d & 31) == 0) red[d >> 5] = mx;
+  if (lane == 0) red[warp] = mx;
   __syncthreads();
   mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
   __syncthreads();
@@ -1160,13 +1227,19 @@ __global__ void __launch_bounds__(128) attn_combine_kernel(const float* __restri
     den = fmaf(w, part_ml[(o + s) * 2 + 1], den);
   }
   den = warp_sum(den);
-  if ((d & 31) == 0) red[d >> 5] = den;
+  if (lane == 0) red[warp] = den;
   __syncthreads();
   den = red[0] + red[1] + red[2] + red[3];
-  float num = 0.f;
-#pragma unroll 8
-  for (int s = 0; s < nsplit; ++s) num = fmaf(wsh[s], part_acc[(o + s) * HD + d], num);
-  out[((size_t)m * q_heads + h) * HD + d] = num / den;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int s = warp; s < nsplit; s += 4) {
+    const float w = wsh[s];
+    const float4 v = *reinterpret_cast<const float4*>(part_acc + (o + s) * HD + lane * 4);
+    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+  }
+  *reinterpret_cast<float4*>(&part[warp][lane * 4]) = acc;
+  __syncthreads();
+  out[((size_t)m * q_heads + h) * HD + d] = (part[0][d] + part[1][d] + part[2][d] + part[3][d]) / den;
 }
 
 __global__ void embed_gather_kernel(const bf16* __restrict__ table, const int* __restrict__ tokens, float* __restrict__ out, int H) {

@@ -85,6 +85,11 @@ struct vv_ctx {
   bool use_tma = false;    // TMA-ring GEMV (gemv_tma_kernel) measured slower than the register-pipelined one; VV_TMA=1 selects it
   bool use_pdl = true;
   bool use_mma_attn = true;
+  bool use_splitk = true;
+  bool fuse_rope = true;
+  int wr_tasks_min = 296;
+  int wr_force = 0;
+  int gemv_grid_cap = 0;
   int sm_count = 148;
   std::map<std::string, RawTensor> raw;
   std::set<std::string> expected;
@@ -192,6 +197,12 @@ static int linear(const L& l, GemvP p) {
   if (((uintptr_t)p.x & 15) || (p.xmap.rs & 3) || (p.xmap.bs & 3)) return fail(VV_ERR_INVALID, "linear: activation rows must be 16-byte aligned");
   if (p.M > 8 && p.pro == PRO_NONE && p.epi != EPI_SWIGLU) {
     dim3 grid((p.N + MM_BN - 1) / MM_BN, (p.M + MM_BM - 1) / MM_BM);
+    const bool inplace_res = (p.epi == EPI_RESID || p.epi == EPI_GAMMA_RESID || p.epi == EPI_GATED_RESID) && p.res == p.y && p.ldres == p.ldy;
+    const int nk = (p.K + MM_BK - 1) / MM_BK;
+    if (l.c->use_splitk && inplace_res && nk >= 8 && (int)(grid.x * grid.y) < l.c->sm_count) {
+      int z = std::min(std::min(nk / 2, 16), (2 * l.c->sm_count) / (int)(grid.x * grid.y));
+      grid.z = std::max(z, 1);
+    }
     CK(launch_k(l, gemm_mma_kernel, dim3(grid), dim3(128), 0, p));
     return 0;
   }
@@ -200,9 +211,10 @@ static int linear(const L& l, GemvP p) {
   while (MB > 1 && gemv_smem_bytes(MB, p.K) > 200 * 1024) MB >>= 1;
   if (gemv_smem_bytes(MB, p.K) > 200 * 1024) return fail(VV_ERR_INVALID, "gemv: K=%d too large", p.K);
   int WR = 8;
-  while (WR > 1 && (p.N + 4 * WR - 1) / (4 * WR) < 2 * l.c->sm_count) WR >>= 1;
+  while (WR > 1 && (p.N + 4 * WR - 1) / (4 * WR) < l.c->wr_tasks_min) WR >>= 1;
   const int nchunks = (p.K + 255) / 256;
   while (WR < 8 && 8 / WR > nchunks) WR <<= 1;      // never more k-split warps than 256-element chunks
+  if (l.c->wr_force) WR = l.c->wr_force;
   p.WK = 8 / WR;
   const int ntasks = (p.N + 4 * WR - 1) / (4 * WR);
   if (l.c->use_tma) {
@@ -228,6 +240,7 @@ static int linear(const L& l, GemvP p) {
   int occ = MB == 1 ? gemv_occupancy<1>(l.c, smem) : MB == 2 ? gemv_occupancy<2>(l.c, smem) : MB == 4 ? gemv_occupancy<4>(l.c, smem)
                                                                                                           : gemv_occupancy<8>(l.c, smem);
   int grid = std::min(ntasks, l.c->sm_count * occ);
+  if (l.c->gemv_grid_cap) grid = std::min(grid, l.c->gemv_grid_cap);
   switch (MB) {
     case 1: return launch_gemv_t<1>(l, p, grid, smem);
     case 2: return launch_gemv_t<2>(l, p, grid, smem);
@@ -378,6 +391,13 @@ extern "C" int vv_create(const vv_model_desc* desc, int device, vv_ctx** out) {
   c->use_mega = (nm && nm[0] == '1');
   const char* na = getenv("VV_SCALAR_ATTN");
   c->use_mma_attn = !(na && na[0] == '1');
+  c->wr_tasks_min = c->sm_count;      // measured (tools/bench_gemv.py): one task per SM beats two for the N=1536 shapes, neutral elsewhere
+  if (getenv("VV_WR_TASKS_MIN")) c->wr_tasks_min = atoi(getenv("VV_WR_TASKS_MIN"));
+  if (getenv("VV_WR_FORCE")) c->wr_force = atoi(getenv("VV_WR_FORCE"));
+  if (getenv("VV_GEMV_GRID_CAP")) c->gemv_grid_cap = atoi(getenv("VV_GEMV_GRID_CAP"));
+  if (getenv("VV_NO_FUSE_ROPE")) c->fuse_rope = false;
+  const char* ns = getenv("VV_NO_SPLITK");
+  c->use_splitk = !(ns && ns[0] == '1');
   const char* np = getenv("VV_NO_PDL");
   c->use_pdl = !(np && np[0] == '1');
   build_expected(c);
@@ -963,12 +983,19 @@ static int enqueue_lm_decode(const L& l, const float* embeds, float* hidden, flo
     kv.kpool = c->kpool + per_layer * li; kv.vpool = c->vpool + per_layer * li;
     kv.page_table = c->page_table_dev; kv.max_pages = c->max_pages; kv.kv_len = c->kv_len_dev; kv.row_mode = c->row_mode_dev;
     kv.kv_heads = d.num_kv_heads; kv.q_heads = d.num_q_heads;
-    CK(launch_k(l, rope_append_kernel, dim3(M), dim3(256), 0, c->s_qkv, c->s_qrot, kv, c->inv_freq));
-    if (c->use_mma_attn) {
+    if (c->use_mma_attn && c->fuse_rope) {
       CK(cudaFuncSetAttribute(attn_partial_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM));
-      CK(launch_k(l, attn_partial_mma_kernel, dim3(c->nsplit, d.num_kv_heads, M), dim3(128), (size_t)AT2_SMEM, c->s_qrot, kv, c->s_pacc, c->s_pml, c->nsplit, scale));
+      CK(launch_k(l, attn_partial_mma_kernel, dim3(c->nsplit, d.num_kv_heads, M), dim3(128), (size_t)AT2_SMEM, c->s_qkv, 1, c->inv_freq, kv, c->s_pacc,
+                  c->s_pml, c->nsplit, scale));
     } else {
-      CK(launch_k(l, attn_partial_kernel, dim3(c->nsplit, d.num_kv_heads, M), dim3(128), 0, c->s_qrot, kv, c->s_pacc, c->s_pml, c->nsplit, scale));
+      CK(launch_k(l, rope_append_kernel, dim3(M), dim3(256), 0, c->s_qkv, c->s_qrot, kv, c->inv_freq));
+      if (c->use_mma_attn) {
+        CK(cudaFuncSetAttribute(attn_partial_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM));
+        CK(launch_k(l, attn_partial_mma_kernel, dim3(c->nsplit, d.num_kv_heads, M), dim3(128), (size_t)AT2_SMEM, c->s_qrot, 0, c->inv_freq, kv, c->s_pacc,
+                    c->s_pml, c->nsplit, scale));
+      } else {
+        CK(launch_k(l, attn_partial_kernel, dim3(c->nsplit, d.num_kv_heads, M), dim3(128), 0, c->s_qrot, kv, c->s_pacc, c->s_pml, c->nsplit, scale));
+      }
     }
     CK(launch_k(l, attn_combine_kernel, dim3(d.num_q_heads, M), dim3(128), 0, c->s_pacc, c->s_pml, c->row_mode_dev, c->s_attn, d.num_q_heads, c->nsplit));
     p = mk(y.wo, nullptr, c->s_attn, nq, c->s_h, H, M, H, nq);
