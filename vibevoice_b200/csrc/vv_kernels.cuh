@@ -607,11 +607,16 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(GemvP p) {
     }
   };
   float4 areg[4];
+  float a_inv = 1.f;            // PRO_RMSNORM: row scale, applied together with the norm weight while converting A
   auto load_a = [&](int kt) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int k = (kt0 + kt) * MM_BK + ac + i * 4;
       areg[i] = (arow && k < K) ? *reinterpret_cast<const float4*>(arow + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.pro == PRO_RMSNORM && arow && k < K) {
+        const float4 wv = *reinterpret_cast<const float4*>(p.pro_w + k);
+        areg[i].x *= a_inv * wv.x; areg[i].y *= a_inv * wv.y; areg[i].z *= a_inv * wv.z; areg[i].w *= a_inv * wv.w;
+      }
     }
   };
   auto store_a = [&]() {
@@ -637,6 +642,13 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(GemvP p) {
 #pragma unroll
   for (int s_ = 0; s_ < MM_ST - 1; ++s_) { if (s_ < nk) load_w(s_, s_); cp_async_commit(); }
   pdl_wait();
+  if (p.pro == PRO_RMSNORM) {   // 4 threads share a row: each sums a quarter of it, combined with two shuffles
+    float ss = 0.f;
+    if (arow) for (int k = (tid & 3) * 4; k < K; k += 16) { const float4 v = *reinterpret_cast<const float4*>(arow + k); ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    a_inv = rsqrtf(ss / (float)K + p.pro_eps);
+  }
   load_a(0);
   for (int kt = 0; kt < nk; ++kt) {
     __syncthreads();                       // previous step's readers of Ah/Al and of the stage about to be refilled are done
@@ -828,6 +840,57 @@ __global__ void dwconv_res_kernel(const float* __restrict__ x, const float* __re
 #pragma unroll
   for (int j = 0; j < 7; ++j) acc = fmaf(w[j * C + c], wp[(size_t)j * C], acc);
   out[idx] = x[idx] + gamma[c] * acc;
+}
+
+// Fused Block1D mixer: out = x + gamma * (bias + depthwise_causal_conv7(RMSNorm(x) * wn)) in ONE launch (replaces
+// assemble_window(norm) + dwconv_res).  CTA = (batch row, tile of MIX_TT time steps), all channels; the 6 halo rows before the
+// tile are re-normalised from x (or taken from the streaming history for t < 0); the CTA(s) covering the last 6 time steps of
+// the frame also stage the next history.
+constexpr int MIX_TT = 8, MIX_CC = 256;
+// grid (time tiles of MIX_TT, batch, channel slabs of MIX_CC): enough CTAs even for T = 1 (C = 2048 -> 8 CTAs); every CTA
+// re-derives the row norms it needs (rows are L2-resident and short), so there is no cross-CTA dependency.
+__global__ void __launch_bounds__(256) mixer_fused_kernel(const float* __restrict__ x, const float* __restrict__ hist, float* __restrict__ hist_next,
+                                                          const float* __restrict__ wn, const float* __restrict__ w /*[7][C]*/,
+                                                          const float* __restrict__ bias, const float* __restrict__ gamma, float* __restrict__ out,
+                                                          int T, int C, float eps) {
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.y, t0 = blockIdx.x * MIX_TT, t1 = min(T, t0 + MIX_TT);
+  const int c0 = blockIdx.z * MIX_CC, c1 = min(C, c0 + MIX_CC), nc = c1 - c0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ float s_inv[MIX_TT + 6];
+  const float* xb = x + (size_t)b * T * C;
+  const float* hb = hist + (size_t)b * 6 * C;
+  for (int r = warp; r < (t1 - t0) + 6; r += 8) {               // row tau = t0 - 6 + r
+    const int tau = t0 - 6 + r;
+    float inv = 0.f;
+    if (tau >= 0) {
+      const float* xr = xb + (size_t)tau * C;
+      float ss = 0.f;
+      for (int c = lane; c < C; c += 32) { const float v = xr[c]; ss += v * v; }
+      ss = warp_sum(ss);
+      inv = rsqrtf(ss / (float)C + eps);
+    }
+    if (lane == 0) s_inv[r] = inv;
+  }
+  __syncthreads();
+  auto val = [&](int tau, int c) -> float {                      // normalised input at absolute time tau (tau >= -6)
+    return tau < 0 ? hb[(size_t)(tau + 6) * C + c] : xb[(size_t)tau * C + c] * s_inv[tau - t0 + 6] * wn[c];
+  };
+  const int n = (t1 - t0) * nc;
+  for (int i = tid; i < n; i += 256) {
+    const int c = c0 + i % nc, t = t0 + i / nc;
+    float acc = bias[c];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) acc = fmaf(w[j * C + c], val(t - 6 + j, c), acc);
+    out[((size_t)b * T + t) * C + c] = xb[(size_t)t * C + c] + gamma[c] * acc;
+  }
+  // next history = normalised rows T-6 .. T-1 (rows before the frame come from the old history)
+  for (int i = tid; i < 6 * nc; i += 256) {
+    const int c = c0 + i % nc, r = i / nc, tau = T - 6 + r;
+    const bool mine = (tau >= t0 && tau < t1) || (tau < 0 && blockIdx.x == 0);
+    if (mine) hist_next[((size_t)b * 6 + r) * C + c] = val(tau, c);
+  }
 }
 
 struct StateSeg { float* hist; float* next; int n; };   // n floats per batch row

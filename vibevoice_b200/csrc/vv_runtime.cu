@@ -87,6 +87,8 @@ struct vv_ctx {
   bool use_mma_attn = true;
   bool use_splitk = true;
   bool fuse_rope = true;
+  bool fuse_codec = false;  // fused mixer + norm-in-GEMM measured 5% slower than the separate small kernels (VV_FUSE_CODEC=1 to enable)
+  bf16* head_slab = nullptr; size_t head_slab_bytes = 0; size_t l2_persist_bytes = 0; size_t l2_window_max = 0;
   int wr_tasks_min = 296;
   int wr_force = 0;
   int gemv_grid_cap = 0;
@@ -131,6 +133,9 @@ struct vv_ctx {
 
 struct L {  // launcher
   vv_ctx* c; cudaStream_t s;
+  const void* win_base = nullptr;   // optional L2 access-policy window for this launch (persisting hits inside it)
+  size_t win_bytes = 0;
+  float win_ratio = 0.f;
 };
 
 // every hot-path kernel goes through here: programmatic dependent launch (PDL) lets kernel N+1 be scheduled and run its
@@ -140,11 +145,24 @@ static cudaError_t launch_k(const L& l, void (*kern)(KArgs...), dim3 grid, dim3 
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = l.s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (l.c->use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (l.win_bytes) {
+    attr[na].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[na].val.accessPolicyWindow.base_ptr = const_cast<void*>(l.win_base);
+    attr[na].val.accessPolicyWindow.num_bytes = l.win_bytes;
+    attr[na].val.accessPolicyWindow.hitRatio = l.win_ratio;
+    attr[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = l.c->use_pdl ? 1 : 0;
+  cfg.numAttrs = na;
   l.c->launches++;
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
@@ -195,7 +213,7 @@ static int launch_gemv_tma_t(const L& l, GemvP& p, GemvTmaCfg cfg, int grid, int
 static int linear(const L& l, GemvP p) {
   if (p.K % 8 != 0) return fail(VV_ERR_INVALID, "linear: K=%d not a multiple of 8", p.K);
   if (((uintptr_t)p.x & 15) || (p.xmap.rs & 3) || (p.xmap.bs & 3)) return fail(VV_ERR_INVALID, "linear: activation rows must be 16-byte aligned");
-  if (p.M > 8 && p.pro == PRO_NONE && p.epi != EPI_SWIGLU) {
+  if (p.M > 8 && (p.pro == PRO_NONE || p.pro == PRO_RMSNORM) && p.epi != EPI_SWIGLU) {
     dim3 grid((p.N + MM_BN - 1) / MM_BN, (p.M + MM_BM - 1) / MM_BM);
     const bool inplace_res = (p.epi == EPI_RESID || p.epi == EPI_GAMMA_RESID || p.epi == EPI_GATED_RESID) && p.res == p.y && p.ldres == p.ldy;
     const int nk = (p.K + MM_BK - 1) / MM_BK;
@@ -396,6 +414,7 @@ extern "C" int vv_create(const vv_model_desc* desc, int device, vv_ctx** out) {
   if (getenv("VV_WR_FORCE")) c->wr_force = atoi(getenv("VV_WR_FORCE"));
   if (getenv("VV_GEMV_GRID_CAP")) c->gemv_grid_cap = atoi(getenv("VV_GEMV_GRID_CAP"));
   if (getenv("VV_NO_FUSE_ROPE")) c->fuse_rope = false;
+  if (getenv("VV_FUSE_CODEC")) c->fuse_codec = true;
   const char* ns = getenv("VV_NO_SPLITK");
   c->use_splitk = !(ns && ns[0] == '1');
   const char* np = getenv("VV_NO_PDL");
@@ -682,23 +701,44 @@ extern "C" int vv_finalize_weights(vv_ctx* c) {
     const size_t modrows = (size_t)(3 * LH + 2) * H;
     RET(dmalloc(c, &c->h_mod, modrows * H, false));
     c->head.resize(LH);
+    // the per-step weights of all head layers live in ONE slab so a single L2 access-policy window can keep (part of) them
+    // resident across the N diffusion steps (they are re-read N times per frame; everything else streams once)
+    const size_t per_layer_el = (size_t)3 * F * H;
+    c->head_slab_bytes = per_layer_el * LH * 2;
+    RET(dmalloc(c, &c->head_slab, per_layer_el * LH, false));
     for (int l = 0; l < LH; ++l) {
       std::string q = S("%s.layers.%d", h.c_str(), l);
-      RawTensor *tg, *tu, *tm;
+      RawTensor *tg, *tu, *tm, *td;
       RET(need(c, q + ".ffn.gate_proj.weight", &tg, {F, H}));
       RET(need(c, q + ".ffn.up_proj.weight", &tu, {F, H}));
-      RET(dmalloc(c, &c->head[l].wgu, (size_t)2 * F * H, false));
+      c->head[l].wgu = c->head_slab + per_layer_el * l;
+      c->head[l].wdown = c->head[l].wgu + (size_t)2 * F * H;
       interleave_rows_kernel<<<4096, 256>>>((const bf16*)tg->p, (const bf16*)tu->p, c->head[l].wgu, (size_t)F, (size_t)H);
       CKL();
       CK(cudaDeviceSynchronize());
       *hb += (int64_t)2 * F * H * 2;
       drop(c, q + ".ffn.gate_proj.weight"); drop(c, q + ".ffn.up_proj.weight");
-      RET(take_bf16(c, q + ".ffn.down_proj.weight", {H, F}, &c->head[l].wdown, hb));
+      RET(need(c, q + ".ffn.down_proj.weight", &td, {H, F}));
+      CK(cudaMemcpy(c->head[l].wdown, td->p, (size_t)H * F * 2, cudaMemcpyDeviceToDevice));
+      *hb += (int64_t)H * F * 2;
+      drop(c, q + ".ffn.down_proj.weight");
       RET(take_f32(c, q + ".norm.weight", {H}, &c->head[l].norm, hb));
       RET(need(c, q + ".adaLN_modulation.1.weight", &tm, {3 * H, H}));
       CK(cudaMemcpy(c->h_mod + (size_t)l * 3 * H * H, tm->p, (size_t)3 * H * H * 2, cudaMemcpyDeviceToDevice));
       *hb += (int64_t)3 * H * H * 2;
       drop(c, q + ".adaLN_modulation.1.weight");
+    }
+    {
+      int maxp = 0, maxw = 0;
+      cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+      cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+      size_t want = 0;     // measured neutral on B200 (79 MB max set-aside, sampler is latency- not bandwidth-bound): opt-in via VV_L2_PERSIST_MB
+      if (getenv("VV_L2_PERSIST_MB")) want = (size_t)atoi(getenv("VV_L2_PERSIST_MB")) << 20;
+      c->l2_persist_bytes = std::min<size_t>(want, (size_t)maxp);
+      c->l2_window_max = (size_t)maxw;
+      if (c->l2_persist_bytes) CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->l2_persist_bytes));
+      if (getenv("VV_VERBOSE")) fprintf(stderr, "[vv] L2 persisting max %d MB, window max %d MB, using %zu MB for a %zu MB head slab\n", maxp >> 20,
+                                        maxw >> 20, c->l2_persist_bytes >> 20, c->head_slab_bytes >> 20);
     }
     RawTensor* tm;
     RET(need(c, h + ".final_layer.adaLN_modulation.1.weight", &tm, {2 * H, H}));
@@ -1210,10 +1250,16 @@ static int enqueue_diffusion(const L& l, const float* cond, const float* noise, 
   if (prog && prog->n_ops > 0) return launch_program(l, *prog);
   CK(launch_k(l, dpm_update_proj_kernel, dim3(B, (H + 255) / 256), dim3(256), 0, c->s_z + B * 64, c->s_z, c->s_x0 + B * 64, c->s_x0, c->s_v, noise,
               c->coef_dev, -1, cfg, c->h_noisy, c->s_hx, nullptr, B, H, 1));
+  L lh = l;
+  if (c->l2_persist_bytes && c->head_slab_bytes) {
+    lh.win_base = c->head_slab;
+    lh.win_bytes = std::min(c->head_slab_bytes, c->l2_window_max);
+    lh.win_ratio = std::min(1.0f, (float)c->l2_persist_bytes / (float)lh.win_bytes);
+  }
   for (int i = 0; i < N; ++i) {
     std::vector<GemvP> g;
     head_step_gemvs(c, i, &g);
-    for (auto& q : g) RET(linear(l, q));
+    for (auto& q : g) RET(linear(lh, q));
     const bool last = (i == N - 1);
     const DpmOp o = dpm_op(c, i, noise, cfg, latent_out);
     CK(launch_k(l, dpm_update_proj_kernel, dim3(B, last ? 1 : (H + 255) / 256), dim3(256), 0, o.z_in, o.z_out, o.x0_in, o.x0_out, o.v, noise, o.coef, i,
@@ -1266,13 +1312,15 @@ static int assemble(const L& l, const float* src, const float* hist, float* win,
 static int enqueue_block(const L& l, const Block& b, const float* xin, float* xout, int B, int T, float eps) {
   vv_ctx* c = l.c;
   const int C = b.C, M = B * T;
-  RET(assemble(l, xin, b.hist, c->s_win, b.next, B, T, 6, C, b.norm_w, eps, 1.f, 0.f));
-  {
+  if (c->fuse_codec) {
+    CK(launch_k(l, mixer_fused_kernel, dim3((T + MIX_TT - 1) / MIX_TT, B, (C + MIX_CC - 1) / MIX_CC), dim3(256), 0, xin, b.hist, b.next, b.norm_w, b.dw_w, b.dw_b, b.gamma, xout, T, C, eps));
+  } else {
+    RET(assemble(l, xin, b.hist, c->s_win, b.next, B, T, 6, C, b.norm_w, eps, 1.f, 0.f));
     const long long n = (long long)M * C;
     CK(launch_k(l, dwconv_res_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, xin, c->s_win, b.dw_w, b.dw_b, b.gamma, xout, B, T, C));
   }
   GemvP p;
-  if (M <= 8) {
+  if (M <= 8 || c->fuse_codec) {
     p = mk(b.w1, b.b1, xout, C, c->s_u, 4 * C, M, 4 * C, C);
     p.pro = PRO_RMSNORM; p.pro_w = b.ffn_norm_w; p.pro_eps = eps; p.epi = EPI_GELU;
     RET(linear(l, p));
