@@ -322,6 +322,41 @@ def run_b200(args):
                 "unit_of_work": "one speech frame = lm_decode graph + frame_tail graph",
                 "algorithmic_bytes_per_frame": int(abytes), "ms_per_frame": round(ms_frame, 4)}
 
+    # ---------------- dominant kernel alone (gemv_kernel<MB>: ~55% of kernel time, profiles/): algorithmic bytes / event time ----
+    def kernel_roofline():
+        import ctypes as C
+        from vibevoice_b200 import _native as NV
+        dc = cfg.decoder_config
+        N_, K_ = 2 * dc.intermediate_size, dc.hidden_size           # LM gate/up projection, the largest single weight stream per layer
+        M_ = 2 * B
+        ncopy = max(2, int(300e6 // (N_ * K_ * 2)) + 1)               # rotate through > L2-size of weights
+        Wt = torch.empty(ncopy, N_, K_, device=dev, dtype=torch.bfloat16).normal_(0, 0.02)
+        xt = torch.randn(M_, K_, device=dev)
+        nw = torch.rand(K_, device=dev) + 0.5
+        yt = torch.zeros(M_, N_ // 2, device=dev)
+        P = lambda t: C.c_void_p(t.data_ptr())
+
+        def run(n):
+            for i in range(n):
+                NV.check(eng.lib.vv_debug_gemv(eng.h, P(Wt[i % ncopy]), None, P(xt), P(yt), M_, N_, K_, NV.PRO_RMSNORM, P(nw), 1e-6,
+                                               NV.EPI_SWIGLU, eng.s))
+        run(20)
+        eng.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(eng.stream)
+        run(200)
+        e1.record(eng.stream)
+        eng.sync()
+        us = e0.elapsed_time(e1) * 1e3 / 200
+        ach = N_ * K_ * 2 / us / 1e3
+        return {"kernel": "gemv_kernel<%d> (LM gate/up, N=%d K=%d, fused RMSNorm + SwiGLU)" % (2 if M_ <= 2 else (4 if M_ <= 4 else 8), N_, K_),
+                "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                "algorithmic_bytes_per_launch": N_ * K_ * 2, "us_per_launch": round(us, 2),
+                "traffic": "55.11 MB dram read for 55.05 MB algorithmic (ncu --set full, profiles/r01_prof_gemv_raw.csv)" if args.model == "1.5b" else None,
+                "note": "back-to-back launches, weights rotated through >300 MB so L2 cannot serve them"}
+    roofline["dominant_kernel"] = kernel_roofline()
+    log("dominant-kernel roofline done")
+
     # ---------------- e2e: public generate() with host buffers ----------------
     e2e = None
     if not args.no_e2e:

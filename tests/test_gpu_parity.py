@@ -407,3 +407,52 @@ def test_voice_prompt_and_torch_prefill_vs_oracle():
     report("generate_voice_prompt_torch_prefill", audio_rel_l2=e)
     assert e < 5e-2, e
     model.engine.close()
+
+
+def test_tcgen05_gemm_forced_everywhere():
+    """gemm_tc5_kernel (tcgen05.mma + TMEM accumulator) is selected automatically only for wide GEMMs; force it for EVERY
+    M > 8 GEMM (VV_TC5=2) and re-check the GEMM-vs-torch cases and a closed codec loop through the tensor-core path."""
+    import ctypes as C
+    old = os.environ.get("VV_TC5")
+    os.environ["VV_TC5"] = "2"
+    try:
+        m, cfg, tok, sd = make_model("tiny", 1)
+    finally:
+        if old is None:
+            os.environ.pop("VV_TC5", None)
+        else:
+            os.environ["VV_TC5"] = old
+    eng = m.engine
+    P = lambda t: C.c_void_p(t.data_ptr())
+    for (M, N, K) in [(40, 2048, 512), (200, 1024, 256), (70, 96, 40), (60, 21504, 1536), (130, 200, 72)]:
+        g = torch.Generator().manual_seed(M + N + K)
+        W = (torch.randn(N, K, generator=g) * 0.05).to(torch.bfloat16)
+        x, bias = torch.randn(M, K, generator=g), torch.randn(N, generator=g) * 0.1
+        Wd, xd, bd = W.cuda(), x.cuda(), bias.cuda()
+        torch.cuda.synchronize()
+        for epi in (NV.EPI_NONE, NV.EPI_GELU, NV.EPI_RESID):
+            y = torch.full((M, N), 0.25, device="cuda")
+            torch.cuda.synchronize()
+            with torch.cuda.stream(eng.stream):
+                NV.check(eng.lib.vv_debug_gemv(eng.h, P(Wd), P(bd), P(xd), P(y), M, N, K, NV.PRO_NONE, None, 1e-5, epi, eng.s))
+            eng.sync()
+            ref = x @ W.float().T + bias
+            ref = torch.nn.functional.gelu(ref) if epi == NV.EPI_GELU else (ref + 0.25 if epi == NV.EPI_RESID else ref)
+            e = rel_l2(y, ref)
+            report("tc5_gemm", M=M, N=N, K=K, epi=epi, rel_l2=e)
+            assert e < 2e-5, (M, N, K, epi, e)
+    from oracle import vv_oracle as O
+    eng.codec_state_reset()
+    a, s_ = O.StreamState(1), O.StreamState(1)
+    g = torch.Generator().manual_seed(5)
+    scale, bias_f = float(sd["model.speech_scaling_factor"]), float(sd["model.speech_bias_factor"])
+    for f in range(3):
+        lat = torch.randn(1, 64, generator=g)
+        with torch.cuda.stream(eng.stream):
+            eng.latent.copy_(lat.cuda())
+        eng.upload_frame_inputs(torch.zeros(1, 64), [0])
+        eng.codec_decode(); eng.semantic_encode(); eng.sync()
+        audio = O.decoder_frame(sd, cfg.acoustic_tokenizer_config, (lat / scale - bias_f)[:, None, :], a, [0])
+        sem = O.encoder_frame(sd, cfg.semantic_tokenizer_config, audio, s_, [0])
+        assert rel_l2(eng.audio.cpu(), audio[:, 0]) < 2e-3 and rel_l2(eng.feat.cpu(), sem[:, 0]) < 2e-3
+    eng.close()

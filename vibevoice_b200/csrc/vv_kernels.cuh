@@ -699,6 +699,150 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(GemvP p) {
       }
 }
 
+// ---------------------------------------------------------------------------------------------
+// tcgen05 / TMEM GEMM (5th-gen tensor cores) for the M > 8 GEMMs: D^T[128 x 64] += W[128 x K] * A[64 x K]^T ("swap-AB":
+// the 128-row MMA M dimension is filled with weight rows, the MMA N dimension with up to 64 activation rows).
+//   * operands in shared memory, K-major, 128-byte swizzle (canonical UMMA layout ((8,n),2):((8,SBO),1), SBO = 1024 B);
+//     W tiles arrive by cp.async into swizzled positions, activations are split fp32 -> bf16 hi + bf16 lo on the fly and both
+//     halves are multiplied into the SAME accumulator (two MMAs), so the result keeps ~fp32-activation accuracy;
+//   * accumulator in TMEM (64 fp32 columns x 128 lanes), one elected thread issues tcgen05.mma, completion is tracked with
+//     tcgen05.commit on an mbarrier, two shared-memory stages are in flight;
+//   * epilogue: tcgen05.ld 32x32b (warp w owns TMEM lanes 32w..32w+31 = weight rows), fused bias / activation / residual.
+// SASS: UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UTCBAR (commit).
+// ---------------------------------------------------------------------------------------------
+constexpr int T5_BM = 128, T5_BN = 64, T5_BK = 64;
+constexpr int T5_STAGE = T5_BM * 128 + 2 * T5_BN * 128;          // W 16 KB + A_hi 8 KB + A_lo 8 KB
+constexpr int T5_NST = 3;                                       // shared-memory stages (weights are requested two k-blocks ahead)
+constexpr int T5_SMEM = T5_NST * T5_STAGE + 1024;               // + slack for 1024 B alignment
+
+VV_DEVINL unsigned long long umma_desc_sw128(unsigned smem_addr) {
+  return (unsigned long long)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+VV_DEVINL void tc5_mma(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned idesc, unsigned accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+VV_DEVINL void tc5_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(128) gemm_tc5_kernel(GemvP p) {
+  extern __shared__ unsigned char t5_raw[];
+  __shared__ unsigned long long mma_bar[T5_NST];
+  __shared__ unsigned tmem_base_s;
+  const unsigned raw_addr = smem_u32(t5_raw);
+  unsigned char* sm = t5_raw + ((1024u - (raw_addr & 1023u)) & 1023u);      // 1024 B aligned (swizzle atom)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bn = blockIdx.x * T5_BM;       // weight rows (output features) of this CTA
+  const int bm = blockIdx.y * T5_BN;       // activation rows
+  const int K = p.K, nk = (K + T5_BK - 1) / T5_BK;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((unsigned)T5_BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int i = 0; i < T5_NST; ++i) mbar_init(&mma_bar[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem_d = tmem_base_s;
+
+  // loaders --------------------------------------------------------------------------------------------
+  auto load_w = [&](int stage, int kb) {   // 128 rows x 8 chunks(16 B): 8 cp.async per thread into swizzled positions
+    unsigned char* wt = sm + stage * T5_STAGE;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = tid + i * 128, r = idx >> 3, c = idx & 7;
+      const int n = bn + r, k = kb * T5_BK + c * 8;
+      const bool ok = (n < p.N) && (k < K);
+      cp_async16(wt + r * 128 + ((c ^ (r & 7)) << 4), p.W + (size_t)(ok ? n : 0) * K + (ok ? k : 0), ok ? 16 : 0);
+    }
+  };
+  const int ar = tid >> 1, ac = (tid & 1) * 32;          // activation row (0..63) and first of 32 consecutive k
+  const float* arow = (bm + ar < p.M) ? p.x + p.xmap.off(bm + ar) : nullptr;
+  float4 areg[8];
+  auto load_a = [&](int kb) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = kb * T5_BK + ac + i * 4;
+      areg[i] = (arow && k < K) ? *reinterpret_cast<const float4*>(arow + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto store_a = [&](int stage) {
+    unsigned char* ah = sm + stage * T5_STAGE + T5_BM * 128;
+    unsigned char* al = ah + T5_BN * 128;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {                         // 4 chunks of 8 k each
+      const float v[8] = {areg[2 * j].x, areg[2 * j].y, areg[2 * j].z, areg[2 * j].w, areg[2 * j + 1].x, areg[2 * j + 1].y, areg[2 * j + 1].z, areg[2 * j + 1].w};
+      float h[8], l[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { h[q] = __bfloat162float(__float2bfloat16_rn(v[q])); l[q] = v[q] - h[q]; }
+      const int c = (ac >> 3) + j;
+      const unsigned off = ar * 128 + ((c ^ (ar & 7)) << 4);
+      *reinterpret_cast<uint4*>(ah + off) = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+      *reinterpret_cast<uint4*>(al + off) = make_uint4(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]), pack_bf16(l[4], l[5]), pack_bf16(l[6], l[7]));
+    }
+  };
+  // instruction descriptor: D=f32, A=B=bf16, both K-major, N=64, M=128
+  const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(T5_BN >> 3) << 17) | ((unsigned)(T5_BM >> 4) << 24);
+
+  pdl_trigger();
+  load_w(0, 0);
+  cp_async_commit();
+  if (nk > 1) load_w(1, 1);
+  cp_async_commit();
+  pdl_wait();
+  load_a(0);
+  for (int kb = 0; kb < nk; ++kb) {
+    const int st = kb % T5_NST;
+    cp_async_wait<1>();                                                 // W(kb) has landed (W(kb+1) may still be in flight)
+    store_a(st);                                                        // stage st was released by MMA(kb-3), waited for at iteration kb-2
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const unsigned wbase = smem_u32(sm + st * T5_STAGE);
+      const unsigned long long dw = umma_desc_sw128(wbase), dh = umma_desc_sw128(wbase + T5_BM * 128), dl = umma_desc_sw128(wbase + T5_BM * 128 + T5_BN * 128);
+#pragma unroll
+      for (int k = 0; k < T5_BK / 16; ++k) {               // UMMA_K = 16 bf16 = 32 B -> +2 in the 16-byte start-address field
+        tc5_mma(tmem_d, dw + 2 * k, dh + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        tc5_mma(tmem_d, dw + 2 * k, dl + 2 * k, idesc, 1u);
+      }
+      tc5_commit(&mma_bar[st]);
+    }
+    if (kb + 2 < nk) {
+      if (kb >= 1) mbar_wait(&mma_bar[(kb - 1) % T5_NST], (unsigned)(((kb - 1) / T5_NST) & 1));   // MMA(kb-1) released stage (kb+2)%3
+      load_w((kb + 2) % T5_NST, kb + 2);
+    }
+    cp_async_commit();
+    if (kb + 1 < nk) load_a(kb + 1);
+  }
+  mbar_wait(&mma_bar[(nk - 1) % T5_NST], (unsigned)(((nk - 1) / T5_NST) & 1));
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // epilogue: warp w owns TMEM lanes [32w, 32w+32) = weight rows n; columns = activation rows m
+  const int n = bn + warp * 32 + lane;
+  const float bias = (p.bias && n < p.N) ? p.bias[n] : 0.f;
+#pragma unroll
+  for (int c0 = 0; c0 < T5_BN; c0 += 8) {
+    unsigned r[8];
+    const unsigned taddr = tmem_d + ((unsigned)(warp * 32) << 16) + (unsigned)c0;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int m = bm + c0 + j;
+      if (m < p.M && n < p.N) epi_store(p, m, n, __uint_as_float(r[j]) + bias);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((unsigned)T5_BN) : "memory");
+}
+
 // thread-per-output small-K product with fp32 weights (encoder stem conv 1->32 k7, decoder head conv 32->1 k7)
 __global__ void conv_naive_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ x,
                                   RowMap xmap, float* __restrict__ y, int M, int N, int K) {

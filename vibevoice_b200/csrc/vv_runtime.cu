@@ -87,6 +87,7 @@ struct vv_ctx {
   bool use_mma_attn = true;
   bool use_splitk = true;
   bool fuse_rope = true;
+  int use_tc5 = 1;          // tcgen05/TMEM GEMM: 0 off, 1 auto (wide GEMMs), 2 every M > 8 GEMM (VV_TC5)
   bool fuse_codec = false;  // fused mixer + norm-in-GEMM measured 5% slower than the separate small kernels (VV_FUSE_CODEC=1 to enable)
   bf16* head_slab = nullptr; size_t head_slab_bytes = 0; size_t l2_persist_bytes = 0; size_t l2_window_max = 0;
   int wr_tasks_min = 296;
@@ -213,6 +214,14 @@ static int launch_gemv_tma_t(const L& l, GemvP& p, GemvTmaCfg cfg, int grid, int
 static int linear(const L& l, GemvP p) {
   if (p.K % 8 != 0) return fail(VV_ERR_INVALID, "linear: K=%d not a multiple of 8", p.K);
   if (((uintptr_t)p.x & 15) || (p.xmap.rs & 3) || (p.xmap.bs & 3)) return fail(VV_ERR_INVALID, "linear: activation rows must be 16-byte aligned");
+  // tcgen05/TMEM path: wide GEMMs that fill the chip with 128-row weight tiles (the all-steps AdaLN modulation GEMM:
+  // [N_steps*2B, H] x [(3L+2)H, H]^T = 168 CTAs on 1.5B); mode 2 forces it for every M > 8 GEMM (tests)
+  const int tc5_ctas = ((p.N + T5_BM - 1) / T5_BM) * ((p.M + T5_BN - 1) / T5_BN);
+  if (l.c->use_tc5 && p.M > 8 && p.pro == PRO_NONE && p.epi != EPI_SWIGLU && (l.c->use_tc5 == 2 || tc5_ctas >= 96)) {
+    CK(cudaFuncSetAttribute(gemm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM));
+    CK(launch_k(l, gemm_tc5_kernel, dim3((p.N + T5_BM - 1) / T5_BM, (p.M + T5_BN - 1) / T5_BN), dim3(128), (size_t)T5_SMEM, p));
+    return 0;
+  }
   if (p.M > 8 && (p.pro == PRO_NONE || p.pro == PRO_RMSNORM) && p.epi != EPI_SWIGLU) {
     dim3 grid((p.N + MM_BN - 1) / MM_BN, (p.M + MM_BM - 1) / MM_BM);
     const bool inplace_res = (p.epi == EPI_RESID || p.epi == EPI_GAMMA_RESID || p.epi == EPI_GATED_RESID) && p.res == p.y && p.ldres == p.ldy;
@@ -414,6 +423,7 @@ extern "C" int vv_create(const vv_model_desc* desc, int device, vv_ctx** out) {
   if (getenv("VV_WR_FORCE")) c->wr_force = atoi(getenv("VV_WR_FORCE"));
   if (getenv("VV_GEMV_GRID_CAP")) c->gemv_grid_cap = atoi(getenv("VV_GEMV_GRID_CAP"));
   if (getenv("VV_NO_FUSE_ROPE")) c->fuse_rope = false;
+  if (getenv("VV_TC5")) c->use_tc5 = atoi(getenv("VV_TC5"));
   if (getenv("VV_FUSE_CODEC")) c->fuse_codec = true;
   const char* ns = getenv("VV_NO_SPLITK");
   c->use_splitk = !(ns && ns[0] == '1');
