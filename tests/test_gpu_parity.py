@@ -73,9 +73,8 @@ def test_gemv_matches_torch(tiny2, M, N, K):
     nw = torch.rand(K, generator=g) + 0.5
     Wd, xd, bd, nwd = W.cuda(), x.cuda(), bias.cuda(), nw.cuda()
     P = lambda t: C.c_void_p(t.data_ptr())
-    cases = [(NV.PRO_NONE, NV.EPI_NONE), (NV.PRO_NONE, NV.EPI_GELU), (NV.PRO_NONE, NV.EPI_SILU)]
-    if M <= 16:
-        cases += [(NV.PRO_RMSNORM, NV.EPI_GELU), (NV.PRO_SILU, NV.EPI_NONE), (NV.PRO_RMSNORM, NV.EPI_SWIGLU), (NV.PRO_NONE, NV.EPI_RESID)]
+    cases = [(NV.PRO_NONE, NV.EPI_NONE), (NV.PRO_NONE, NV.EPI_GELU), (NV.PRO_NONE, NV.EPI_SILU), (NV.PRO_RMSNORM, NV.EPI_GELU),
+             (NV.PRO_SILU, NV.EPI_NONE), (NV.PRO_RMSNORM, NV.EPI_SWIGLU), (NV.PRO_NONE, NV.EPI_RESID)]
     for pro, epi in cases:
         if epi == NV.EPI_SWIGLU and N % 2:
             continue

@@ -616,6 +616,16 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(GemvP p) {
       if (p.pro == PRO_RMSNORM && arow && k < K) {
         const float4 wv = *reinterpret_cast<const float4*>(p.pro_w + k);
         areg[i].x *= a_inv * wv.x; areg[i].y *= a_inv * wv.y; areg[i].z *= a_inv * wv.z; areg[i].w *= a_inv * wv.w;
+      } else if (p.pro == PRO_ADALN && arow && k < K) {
+        float4 wv = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (p.pro_w) wv = *reinterpret_cast<const float4*>(p.pro_w + k);
+        const long long o = (long long)(bm + ar) * p.pro_ld + k;
+        const float4 sc = *reinterpret_cast<const float4*>(p.pro_scale + o);
+        const float4 sh = *reinterpret_cast<const float4*>(p.pro_shift + o);
+        areg[i].x = areg[i].x * a_inv * wv.x * (1.f + sc.x) + sh.x; areg[i].y = areg[i].y * a_inv * wv.y * (1.f + sc.y) + sh.y;
+        areg[i].z = areg[i].z * a_inv * wv.z * (1.f + sc.z) + sh.z; areg[i].w = areg[i].w * a_inv * wv.w * (1.f + sc.w) + sh.w;
+      } else if (p.pro == PRO_SILU && arow && k < K) {
+        areg[i].x = silu_f(areg[i].x); areg[i].y = silu_f(areg[i].y); areg[i].z = silu_f(areg[i].z); areg[i].w = silu_f(areg[i].w);
       }
     }
   };
@@ -642,7 +652,7 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(GemvP p) {
 #pragma unroll
   for (int s_ = 0; s_ < MM_ST - 1; ++s_) { if (s_ < nk) load_w(s_, s_); cp_async_commit(); }
   pdl_wait();
-  if (p.pro == PRO_RMSNORM) {   // 4 threads share a row: each sums a quarter of it, combined with two shuffles
+  if (p.pro == PRO_RMSNORM || p.pro == PRO_ADALN) {   // 4 threads share a row: each sums a quarter of it, combined with two shuffles
     float ss = 0.f;
     if (arow) for (int k = (tid & 3) * 4; k < K; k += 16) { const float4 v = *reinterpret_cast<const float4*>(arow + k); ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
     ss += __shfl_xor_sync(0xffffffffu, ss, 1);
@@ -686,7 +696,12 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(GemvP p) {
       for (int q = 0; q < 4; ++q) {
         const int m = bm + mt * 16 + (lane >> 2) + (q >> 1) * 8;
         const int n = bn + warp * 16 + nt * 8 + (lane & 3) * 2 + (q & 1);
-        if (m < p.M && n < p.N) {
+        if (p.epi == EPI_SWIGLU) {                 // (gate, up) = (even, odd) weight rows = (c0,c1) / (c2,c3) of one thread
+          if ((q & 1) == 0 && m < p.M && n + 1 < p.N) {
+            const float g_ = acc[mt][nt][q] + (p.bias ? p.bias[n] : 0.f), u_ = acc[mt][nt][q + 1] + (p.bias ? p.bias[n + 1] : 0.f);
+            p.y[(long long)m * p.ldy + (n >> 1)] = silu_f(g_) * u_;
+          }
+        } else if (m < p.M && n < p.N) {
           if (nz == 1) {
             epi_store(p, m, n, acc[mt][nt][q] + (p.bias ? p.bias[n] : 0.f));
           } else {

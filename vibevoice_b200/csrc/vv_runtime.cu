@@ -87,6 +87,7 @@ struct vv_ctx {
   bool use_mma_attn = true;
   bool use_splitk = true;
   bool fuse_rope = true;
+  int mma_min_rows = 9;     // M >= this -> tensor-core GEMM (all prologues/epilogues), below -> weight-streaming GEMV (measured: at M = 8 the GEMV streams weights 1.7x faster)
   int use_tc5 = 1;          // tcgen05/TMEM GEMM: 0 off, 1 auto (wide GEMMs), 2 every M > 8 GEMM (VV_TC5)
   bool fuse_codec = false;  // fused mixer + norm-in-GEMM measured 5% slower than the separate small kernels (VV_FUSE_CODEC=1 to enable)
   bf16* head_slab = nullptr; size_t head_slab_bytes = 0; size_t l2_persist_bytes = 0; size_t l2_window_max = 0;
@@ -222,7 +223,7 @@ static int linear(const L& l, GemvP p) {
     CK(launch_k(l, gemm_tc5_kernel, dim3((p.N + T5_BM - 1) / T5_BM, (p.M + T5_BN - 1) / T5_BN), dim3(128), (size_t)T5_SMEM, p));
     return 0;
   }
-  if (p.M > 8 && (p.pro == PRO_NONE || p.pro == PRO_RMSNORM) && p.epi != EPI_SWIGLU) {
+  if (p.M >= l.c->mma_min_rows) {
     dim3 grid((p.N + MM_BN - 1) / MM_BN, (p.M + MM_BM - 1) / MM_BM);
     const bool inplace_res = (p.epi == EPI_RESID || p.epi == EPI_GAMMA_RESID || p.epi == EPI_GATED_RESID) && p.res == p.y && p.ldres == p.ldy;
     const int nk = (p.K + MM_BK - 1) / MM_BK;
@@ -233,7 +234,6 @@ static int linear(const L& l, GemvP p) {
     CK(launch_k(l, gemm_mma_kernel, dim3(grid), dim3(128), 0, p));
     return 0;
   }
-  if (p.M > 16) return fail(VV_ERR_INVALID, "linear: M=%d > 16 needs PRO_NONE and a non-SWIGLU epilogue", p.M);
   int MB = p.M <= 1 ? 1 : (p.M <= 2 ? 2 : (p.M <= 4 ? 4 : 8));
   while (MB > 1 && gemv_smem_bytes(MB, p.K) > 200 * 1024) MB >>= 1;
   if (gemv_smem_bytes(MB, p.K) > 200 * 1024) return fail(VV_ERR_INVALID, "gemv: K=%d too large", p.K);
@@ -424,6 +424,7 @@ extern "C" int vv_create(const vv_model_desc* desc, int device, vv_ctx** out) {
   if (getenv("VV_GEMV_GRID_CAP")) c->gemv_grid_cap = atoi(getenv("VV_GEMV_GRID_CAP"));
   if (getenv("VV_NO_FUSE_ROPE")) c->fuse_rope = false;
   if (getenv("VV_TC5")) c->use_tc5 = atoi(getenv("VV_TC5"));
+  if (getenv("VV_MMA_MIN_ROWS")) c->mma_min_rows = atoi(getenv("VV_MMA_MIN_ROWS"));
   if (getenv("VV_FUSE_CODEC")) c->fuse_codec = true;
   const char* ns = getenv("VV_NO_SPLITK");
   c->use_splitk = !(ns && ns[0] == '1');
