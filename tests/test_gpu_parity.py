@@ -320,6 +320,31 @@ def test_generate_free_running_tokens(tiny2):
     assert torch.equal(out.sequences[:, :upto], ref.sequences[:, :upto])
 
 
+def test_generate_do_sample_vs_oracle(tiny2):
+    """`do_sample=True` (reference :493-496): multinomial over the constrained distribution.  Same generator seed on both sides;
+    the probabilities differ by ~1e-4, so the draws must agree unless a uniform lands within that distance of a bin edge."""
+    from oracle import vv_oracle as O
+    model, cfg, tok, sd = tiny2
+    dc = cfg.decoder_config
+    g = torch.Generator().manual_seed(12)
+    ids = torch.randint(0, dc.vocab_size - 20, (2, 7), generator=g)
+    ids[:, -1] = tok.speech_start_id
+    model.set_ddpm_inference_steps(4)
+    agree = 0
+    for seed in range(4):
+        torch.manual_seed(3)
+        out = model.generate(input_ids=ids, tokenizer=tok, cfg_scale=1.3, is_prefill=False, max_new_tokens=8, show_progress_bar=False,
+                             generation_config={"do_sample": True}, sample_generator=torch.Generator().manual_seed(100 + seed))
+        torch.manual_seed(3)
+        ref = O.generate(sd, cfg, ids, None, tok, cfg_scale=1.3, num_steps=4, max_new_tokens=8, kv_bf16=True, do_sample=True,
+                         sample_generator=torch.Generator().manual_seed(100 + seed))
+        assert set(out.sequences[:, ids.shape[1]:].flatten().tolist()) <= set(model.engine.valid_ids) | {tok.pad_token_id}
+        n = min(out.sequences.shape[1], ref.sequences.shape[1])
+        agree += int(torch.equal(out.sequences[:, :n], ref.sequences[:, :n]))
+        report("generate_do_sample", seed=seed, got=out.sequences[:, ids.shape[1]:].tolist(), want=ref.sequences[:, ids.shape[1]:].tolist())
+    assert agree >= 3, agree
+
+
 @pytest.fixture(scope="module")
 def real15():
     """VibeVoice-1.5B layer shapes (H=1536, I=8960, 12/2 heads, full-size head and codec), 2 LM layers, small vocab."""

@@ -119,3 +119,21 @@ def test_streamer_contract():
     st.end()
     assert [c.sum().item() for c in st.get_stream(0)] == [4.0]
     assert len(list(st.get_stream(1))) == 1
+
+
+def test_sample_valid_tokens_distribution():
+    """do_sample host logic (reference :493-496): draws follow softmax over the valid ids, ids come back in vocabulary space,
+    and the draw does not consume the global CPU RNG that the diffusion noise uses (:701)."""
+    from vibevoice_b200.modeling import sample_valid_tokens
+    valid = [7, 11, 13, 20]
+    logits = np.log(np.array([[0.1, 0.2, 0.3, 0.4]], dtype=np.float32)).repeat(4000, 0)
+    torch.manual_seed(5)
+    before = torch.get_rng_state().clone()
+    toks = sample_valid_tokens(logits, valid, torch.Generator().manual_seed(0))
+    assert torch.equal(before, torch.get_rng_state())
+    assert set(toks.tolist()) <= set(valid)
+    freq = np.array([(toks == v).mean() for v in valid])
+    assert np.abs(freq - np.array([0.1, 0.2, 0.3, 0.4])).max() < 0.03
+    hot = np.full((3, 4), -np.inf, dtype=np.float32)
+    hot[0, 2] = hot[1, 0] = hot[2, 3] = 0.0
+    assert sample_valid_tokens(hot, valid, torch.Generator().manual_seed(1)).tolist() == [13, 7, 20]

@@ -718,8 +718,9 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(GemvP p) {
 // tcgen05 / TMEM GEMM (5th-gen tensor cores) for the M > 8 GEMMs: D^T[128 x 64] += W[128 x K] * A[64 x K]^T ("swap-AB":
 // the 128-row MMA M dimension is filled with weight rows, the MMA N dimension with up to 64 activation rows).
 //   * operands in shared memory, K-major, 128-byte swizzle (canonical UMMA layout ((8,n),2):((8,SBO),1), SBO = 1024 B);
-//     W tiles arrive by cp.async into swizzled positions, activations are split fp32 -> bf16 hi + bf16 lo on the fly and both
-//     halves are multiplied into the SAME accumulator (two MMAs), so the result keeps ~fp32-activation accuracy;
+//     W tiles and the activation planes arrive by cp.async into swizzled positions (three stages, requested two k-blocks ahead);
+//     activations are pre-split fp32 -> bf16 hi + bf16 lo (split_bf16_kernel) and both halves are multiplied into the SAME
+//     accumulator (two MMAs), so the result keeps ~fp32-activation accuracy;
 //   * accumulator in TMEM (64 fp32 columns x 128 lanes), one elected thread issues tcgen05.mma, completion is tracked with
 //     tcgen05.commit on an mbarrier, two shared-memory stages are in flight;
 //   * epilogue: tcgen05.ld 32x32b (warp w owns TMEM lanes 32w..32w+31 = weight rows), fused bias / activation / residual.
@@ -741,7 +742,22 @@ VV_DEVINL void tc5_commit(unsigned long long* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(128) gemm_tc5_kernel(GemvP p) {
+// fp32 activations [M, K] (RowMap) -> dense bf16 planes hi, lo [M, K] with x = hi + lo (|err| <= 2^-17 |x|)
+__global__ void split_bf16_kernel(const float* __restrict__ x, RowMap xmap, bf16* __restrict__ hi, bf16* __restrict__ lo, int M, int K) {
+  pdl_trigger();
+  pdl_wait();
+  const long long n4 = (long long)M * (K >> 2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const int m = (int)(i / (K >> 2)), k = (int)(i % (K >> 2)) << 2;
+    const float4 v = *reinterpret_cast<const float4*>(x + xmap.off(m) + k);
+    const float h0 = __bfloat162float(__float2bfloat16_rn(v.x)), h1 = __bfloat162float(__float2bfloat16_rn(v.y));
+    const float h2 = __bfloat162float(__float2bfloat16_rn(v.z)), h3 = __bfloat162float(__float2bfloat16_rn(v.w));
+    *reinterpret_cast<uint2*>(hi + (size_t)m * K + k) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
+    *reinterpret_cast<uint2*>(lo + (size_t)m * K + k) = make_uint2(pack_bf16(v.x - h0, v.y - h1), pack_bf16(v.z - h2, v.w - h3));
+  }
+}
+
+__global__ void __launch_bounds__(128) gemm_tc5_kernel(GemvP p, const bf16* __restrict__ a_hi, const bf16* __restrict__ a_lo) {
   extern __shared__ unsigned char t5_raw[];
   __shared__ unsigned long long mma_bar[T5_NST];
   __shared__ unsigned tmem_base_s;
@@ -765,8 +781,8 @@ __global__ void __launch_bounds__(128) gemm_tc5_kernel(GemvP p) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const unsigned tmem_d = tmem_base_s;
 
-  // loaders --------------------------------------------------------------------------------------------
-  auto load_w = [&](int stage, int kb) {   // 128 rows x 8 chunks(16 B): 8 cp.async per thread into swizzled positions
+  // one stage = W tile [128 x 64] + A_hi [64 x 64] + A_lo [64 x 64], all bf16, rows of 128 B, 16-byte chunks XOR-swizzled by (row & 7)
+  auto load_w = [&](int stage, int kb) {   // 128 rows x 8 chunks: 8 cp.async per thread
     unsigned char* wt = sm + stage * T5_STAGE;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -776,45 +792,31 @@ __global__ void __launch_bounds__(128) gemm_tc5_kernel(GemvP p) {
       cp_async16(wt + r * 128 + ((c ^ (r & 7)) << 4), p.W + (size_t)(ok ? n : 0) * K + (ok ? k : 0), ok ? 16 : 0);
     }
   };
-  const int ar = tid >> 1, ac = (tid & 1) * 32;          // activation row (0..63) and first of 32 consecutive k
-  const float* arow = (bm + ar < p.M) ? p.x + p.xmap.off(bm + ar) : nullptr;
-  float4 areg[8];
-  auto load_a = [&](int kb) {
+  auto load_a = [&](int stage, int kb) {   // 2 planes x 64 rows x 8 chunks: 8 cp.async per thread
+    unsigned char* ah = sm + stage * T5_STAGE + T5_BM * 128;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int k = kb * T5_BK + ac + i * 4;
-      areg[i] = (arow && k < K) ? *reinterpret_cast<const float4*>(arow + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  auto store_a = [&](int stage) {
-    unsigned char* ah = sm + stage * T5_STAGE + T5_BM * 128;
-    unsigned char* al = ah + T5_BN * 128;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {                         // 4 chunks of 8 k each
-      const float v[8] = {areg[2 * j].x, areg[2 * j].y, areg[2 * j].z, areg[2 * j].w, areg[2 * j + 1].x, areg[2 * j + 1].y, areg[2 * j + 1].z, areg[2 * j + 1].w};
-      float h[8], l[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) { h[q] = __bfloat162float(__float2bfloat16_rn(v[q])); l[q] = v[q] - h[q]; }
-      const int c = (ac >> 3) + j;
-      const unsigned off = ar * 128 + ((c ^ (ar & 7)) << 4);
-      *reinterpret_cast<uint4*>(ah + off) = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
-      *reinterpret_cast<uint4*>(al + off) = make_uint4(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]), pack_bf16(l[4], l[5]), pack_bf16(l[6], l[7]));
+      const int idx = tid + i * 128, pl = idx >> 9, r = (idx >> 3) & 63, c = idx & 7;
+      const int m = bm + r, k = kb * T5_BK + c * 8;
+      const bool ok = (m < p.M) && (k < K);
+      const bf16* src = (pl ? a_lo : a_hi) + (size_t)(ok ? m : 0) * K + (ok ? k : 0);
+      cp_async16(ah + pl * (T5_BN * 128) + r * 128 + ((c ^ (r & 7)) << 4), src, ok ? 16 : 0);
     }
   };
   // instruction descriptor: D=f32, A=B=bf16, both K-major, N=64, M=128
   const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(T5_BN >> 3) << 17) | ((unsigned)(T5_BM >> 4) << 24);
 
   pdl_trigger();
-  load_w(0, 0);
-  cp_async_commit();
+  load_w(0, 0);                                       // weights never depend on the predecessor grid
   if (nk > 1) load_w(1, 1);
-  cp_async_commit();
   pdl_wait();
-  load_a(0);
+  load_a(0, 0);
+  cp_async_commit();                                   // group 0 = W(0), W(1), A(0)
+  if (nk > 1) load_a(1, 1);
+  cp_async_commit();                                   // group 1 = A(1)
   for (int kb = 0; kb < nk; ++kb) {
     const int st = kb % T5_NST;
-    cp_async_wait<1>();                                                 // W(kb) has landed (W(kb+1) may still be in flight)
-    store_a(st);                                                        // stage st was released by MMA(kb-3), waited for at iteration kb-2
+    cp_async_wait<1>();                                                 // everything of k-block kb has landed
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy smem writes -> visible to the tensor core (async proxy)
     __syncthreads();
     if (tid == 0) {
@@ -831,9 +833,9 @@ __global__ void __launch_bounds__(128) gemm_tc5_kernel(GemvP p) {
     if (kb + 2 < nk) {
       if (kb >= 1) mbar_wait(&mma_bar[(kb - 1) % T5_NST], (unsigned)(((kb - 1) / T5_NST) & 1));   // MMA(kb-1) released stage (kb+2)%3
       load_w((kb + 2) % T5_NST, kb + 2);
+      load_a((kb + 2) % T5_NST, kb + 2);
     }
     cp_async_commit();
-    if (kb + 1 < nk) load_a(kb + 1);
   }
   mbar_wait(&mma_bar[(nk - 1) % T5_NST], (unsigned)(((nk - 1) / T5_NST) & 1));
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

@@ -87,6 +87,7 @@ struct vv_ctx {
   bool use_mma_attn = true;
   bool use_splitk = true;
   bool fuse_rope = true;
+  bf16* s_planes = nullptr; size_t planes_elems = 0;
   int mma_min_rows = 9;     // M >= this -> tensor-core GEMM (all prologues/epilogues), below -> weight-streaming GEMV (measured: at M = 8 the GEMV streams weights 1.7x faster)
   int use_tc5 = 1;          // tcgen05/TMEM GEMM: 0 off, 1 auto (wide GEMMs), 2 every M > 8 GEMM (VV_TC5)
   bool fuse_codec = false;  // fused mixer + norm-in-GEMM measured 5% slower than the separate small kernels (VV_FUSE_CODEC=1 to enable)
@@ -219,8 +220,13 @@ static int linear(const L& l, GemvP p) {
   // [N_steps*2B, H] x [(3L+2)H, H]^T = 168 CTAs on 1.5B); mode 2 forces it for every M > 8 GEMM (tests)
   const int tc5_ctas = ((p.N + T5_BM - 1) / T5_BM) * ((p.M + T5_BN - 1) / T5_BN);
   if (l.c->use_tc5 && p.M > 8 && p.pro == PRO_NONE && p.epi != EPI_SWIGLU && (l.c->use_tc5 == 2 || tc5_ctas >= 96)) {
+    if ((size_t)p.M * p.K > l.c->planes_elems) return fail(VV_ERR_INVALID, "tc5: activation planes scratch too small (%d x %d)", p.M, p.K);
+    bf16* hi = l.c->s_planes;
+    bf16* lo = l.c->s_planes + l.c->planes_elems;
+    const long long n4 = (long long)p.M * (p.K >> 2);
+    CK(launch_k(l, split_bf16_kernel, dim3((unsigned)std::min<long long>((n4 + 255) / 256, 1184)), dim3(256), 0, p.x, p.xmap, hi, lo, p.M, p.K));
     CK(cudaFuncSetAttribute(gemm_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T5_SMEM));
-    CK(launch_k(l, gemm_tc5_kernel, dim3((p.N + T5_BM - 1) / T5_BM, (p.M + T5_BN - 1) / T5_BN), dim3(128), (size_t)T5_SMEM, p));
+    CK(launch_k(l, gemm_tc5_kernel, dim3((p.N + T5_BM - 1) / T5_BM, (p.M + T5_BN - 1) / T5_BN), dim3(128), (size_t)T5_SMEM, p, (const bf16*)hi, (const bf16*)lo));
     return 0;
   }
   if (p.M >= l.c->mma_min_rows) {
@@ -857,6 +863,8 @@ extern "C" int vv_finalize_weights(vv_ctx* c) {
   RET(dmalloc(c, &c->s_xn, (size_t)B * max_tc));
   RET(dmalloc(c, &c->s_u, (size_t)B * max_tc * 4));
   RET(dmalloc(c, &c->s_win, (size_t)B * max_win));
+  c->planes_elems = std::max<size_t>((size_t)B * max_tc * 4, (size_t)std::max(d.max_diffusion_steps, 1) * M2 * H);
+  RET(dmalloc(c, &c->s_planes, 2 * c->planes_elems));
   // ---------------- LM scratch ----------------
   RET(dmalloc(c, &c->s_h, (size_t)M2 * H));
   RET(dmalloc(c, &c->s_qkv, (size_t)M2 * c->Nqkv));

@@ -52,6 +52,19 @@ class ForcedTokenScript:
         return s[min(step, len(s) - 1)]
 
 
+def sample_valid_tokens(logits_valid, valid_ids, generator=None) -> np.ndarray:
+    """Multinomial draw of the next token (reference modeling_vibevoice_inference.py:493-496, `do_sample=True`).
+
+    The reference softmaxes the full-vocab scores after `VibeVoiceTokenConstraintProcessor` set every id outside the valid set to
+    -inf (:55-66), so the distribution has support on the valid ids only; softmax over just those logits is the same distribution.
+    `logits_valid` is [rows, n_valid] fp32 in `valid_ids` order.  The draw uses its own generator so that the CPU global RNG, which the
+    reference consumes for the diffusion noise only (:701), sees the same sequence of calls in both modes."""
+    lv = torch.as_tensor(np.asarray(logits_valid), dtype=torch.float32)
+    probs = torch.softmax(lv, dim=-1)
+    idx = torch.multinomial(probs, num_samples=1, generator=generator).squeeze(1)
+    return np.asarray(valid_ids, dtype=np.int64)[idx.numpy()]
+
+
 class VibeVoiceForConditionalGenerationInference:
     def __init__(self, config: VibeVoiceConfig, tokenizer_ids=None, max_batch: int = 1, device: int = 0,
                  max_diffusion_steps: int = 64, torch_prefill: bool = False):
@@ -181,8 +194,10 @@ class VibeVoiceForConditionalGenerationInference:
         kwargs.pop("parsed_scripts", None); kwargs.pop("all_speakers_list", None)
         max_length_times = kwargs.pop("max_length_times", 2)
         verbose = kwargs.get("verbose", False)
-        if generation_config is not None and dict(generation_config).get("do_sample", False):
-            raise NotImplementedError("do_sample=True (multinomial over the valid ids) is a 'next' row (SURVEY 8f-3)")
+        do_sample = bool(generation_config is not None and dict(generation_config).get("do_sample", False))
+        sample_gen = kwargs.get("sample_generator", None)          # torch.Generator for the token draw; never the noise RNG
+        if do_sample and sample_gen is None:
+            sample_gen = torch.Generator().manual_seed(torch.initial_seed())
         if not kwargs.get("refresh_negative", True):
             raise NotImplementedError("refresh_negative=False is a 'next' row (SURVEY 8f-3)")
         use_voice = bool(is_prefill and speech_tensors is not None)
@@ -298,8 +313,10 @@ class VibeVoiceForConditionalGenerationInference:
                 break
             if step > 0:
                 eng.lm_decode()                                                             # :480-482 (+ speculative negative rows)
-            toks_dev, _ = eng.read_tokens()
+            toks_dev, logits_valid = eng.read_tokens()
             next_tokens = toks_dev.astype(np.int64).copy()
+            if do_sample:
+                next_tokens[:b] = sample_valid_tokens(logits_valid[:b], eng.valid_ids, sample_gen)     # :493-496
             if forced is not None:
                 for r in range(b):
                     next_tokens[r] = forced.token(r, step)
