@@ -345,6 +345,66 @@ def test_generate_do_sample_vs_oracle(tiny2):
     assert agree >= 3, agree
 
 
+def test_lora_assets_change_the_model_like_the_oracle_on_merged_weights(tmp_path):
+    """`load_lora_assets` (reference lora_loading.py:148-176).  LoRA pairs on LM q_proj/down_proj and on a head FFN
+    matrix plus a replaced connector are folded into the packed weights; the closed loop must then match the oracle run on a state
+    dict merged independently here (W + (alpha/r) B A in fp32, one rounding to bf16) -- and must differ from the base model."""
+    import json
+    from safetensors.torch import save_file
+    from oracle import vv_oracle as O
+    from vibevoice.modular.lora_loading import load_lora_assets
+    from vibevoice_b200.modeling import ForcedTokenScript
+    model, cfg, tok, sd = make_model("tiny", 1)
+    try:
+        g = torch.Generator().manual_seed(21)
+        rn = lambda *sh: torch.randn(*sh, generator=g)
+        targets = {"model.language_model.layers.0.self_attn.q_proj.weight": "base_model.model.layers.0.self_attn.q_proj",
+                   "model.language_model.layers.1.mlp.down_proj.weight": "base_model.model.layers.1.mlp.down_proj"}
+        head_t = {"model.prediction_head.layers.0.ffn.up_proj.weight": "base_model.model.base.layers.0.ffn.up_proj",
+                  "model.prediction_head.layers.1.adaLN_modulation.1.weight": "base_model.model.base.layers.1.adaLN_modulation.1"}
+        merged = dict(sd)
+        root = tmp_path / "ft" / "lora"
+        for d, tg, r, alpha in ((root, targets, 4, 16.0), (root / "diffusion_head", head_t, 2, 4.0)):
+            d.mkdir(parents=True, exist_ok=True)
+            tens = {}
+            for key, mod in tg.items():
+                out_f, in_f = sd[key].shape
+                A, B = rn(r, in_f) * 0.3, rn(out_f, r) * 0.3
+                tens[mod + ".lora_A.weight"], tens[mod + ".lora_B.weight"] = A, B
+                merged[key] = (sd[key].float() + (alpha / r) * (B @ A)).to(sd[key].dtype)
+            (d / "adapter_config.json").write_text(json.dumps(dict(peft_type="LORA", r=r, lora_alpha=alpha)))
+            save_file(tens, str(d / "adapter_model.safetensors"))
+        (root / "semantic_connector").mkdir()
+        conn = {k.split("semantic_connector.")[1]: (v.float() + 0.05 * rn(*v.shape)).to(v.dtype)
+                for k, v in sd.items() if k.startswith("model.semantic_connector.")}
+        torch.save(conn, root / "semantic_connector" / "pytorch_model.bin")
+        for k, v in conn.items():
+            merged["model.semantic_connector." + k] = v
+
+        dc = cfg.decoder_config
+        ids = torch.randint(0, dc.vocab_size - 20, (1, 8), generator=g)
+        ids[:, -1] = tok.speech_start_id
+        script = [_scripted(tok, "ddddx")]
+        model.set_ddpm_inference_steps(5)
+
+        def run():
+            torch.manual_seed(4)
+            return model.generate(input_ids=ids, tokenizer=tok, cfg_scale=1.3, is_prefill=False, logits_processor=[ForcedTokenScript(script)],
+                                  max_new_tokens=12, show_progress_bar=False).speech_outputs[0].cpu()
+        base_audio = run()
+        rep = load_lora_assets(model, str(tmp_path / "ft"))
+        assert rep.language_model and rep.diffusion_head_lora and rep.semantic_connector and not rep.acoustic_connector
+        tuned = run()
+        torch.manual_seed(4)
+        ref = O.generate(merged, cfg, ids, None, tok, cfg_scale=1.3, num_steps=5, max_new_tokens=12, forced_tokens=script, kv_bf16=True)
+        e, moved = rel_l2(tuned, ref.speech_outputs[0]), rel_l2(tuned, base_audio)
+        report("lora_assets", audio_rel_l2=e, moved_from_base=moved)
+        assert e < 1e-2 and moved > 10 * e, (e, moved)
+    finally:
+        if model.engine is not None:
+            model.engine.close()
+
+
 @pytest.fixture(scope="module")
 def real15():
     """VibeVoice-1.5B layer shapes (H=1536, I=8960, 12/2 heads, full-size head and codec), 2 LM layers, small vocab."""

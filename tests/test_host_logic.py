@@ -137,3 +137,69 @@ def test_sample_valid_tokens_distribution():
     hot = np.full((3, 4), -np.inf, dtype=np.float32)
     hot[0, 2] = hot[1, 0] = hot[2, 3] = 0.0
     assert sample_valid_tokens(hot, valid, torch.Generator().manual_seed(1)).tolist() == [13, 7, 20]
+
+
+def _write_adapter(d, tensors, r, alpha, **extra):
+    import json
+    from safetensors.torch import save_file
+    d.mkdir(parents=True, exist_ok=True)
+    (d / "adapter_config.json").write_text(json.dumps(dict(peft_type="LORA", r=r, lora_alpha=alpha, **extra)))
+    save_file(tensors, str(d / "adapter_model.safetensors"))
+
+
+def test_lora_assets_fold_into_base_weights(tmp_path):
+    """lora.py vs the published PEFT LoRA merge W' = W + (alpha/r) B A, on the directory layout the reference's loader reads
+    (`lora_loading.py:46-55, 72-127, 164-170`): LM adapter at the root, head adapter under diffusion_head/ behind the `base.` shim,
+    connector state dicts replaced wholesale; unknown targets raise instead of being dropped."""
+    from vibevoice_b200 import lora as L
+    g = torch.Generator().manual_seed(0)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    base = {
+        "model.language_model.layers.0.self_attn.q_proj.weight": rn(16, 8).bfloat16(),
+        "model.language_model.layers.0.self_attn.q_proj.bias": rn(16).bfloat16(),
+        "model.language_model.layers.0.mlp.down_proj.weight": rn(8, 24).bfloat16(),
+        "model.prediction_head.layers.0.ffn.gate_proj.weight": rn(24, 8).bfloat16(),
+        "model.acoustic_connector.fc1.weight": rn(8, 4).bfloat16(),
+        "model.acoustic_connector.fc1.bias": rn(8).bfloat16(),
+    }
+    root = tmp_path / "ckpt" / "lora"
+    Aq, Bq, Ad, Bd = rn(4, 8), rn(16, 4), rn(2, 24), rn(8, 2)
+    _write_adapter(root, {"base_model.model.layers.0.self_attn.q_proj.lora_A.weight": Aq,
+                          "base_model.model.layers.0.self_attn.q_proj.lora_B.weight": Bq,
+                          "base_model.model.layers.0.mlp.down_proj.lora_A.default.weight": Ad,
+                          "base_model.model.layers.0.mlp.down_proj.lora_B.default.weight": Bd}, r=4, alpha=8,
+                   rank_pattern={"down_proj": 2}, alpha_pattern={"down_proj": 6})
+    Ah, Bh = rn(4, 8), rn(24, 4)
+    _write_adapter(root / "diffusion_head", {"base_model.model.base.layers.0.ffn.gate_proj.lora_A.weight": Ah,
+                                             "base_model.model.base.layers.0.ffn.gate_proj.lora_B.weight": Bh}, r=4, alpha=4, use_rslora=True)
+    (root / "acoustic_connector").mkdir()
+    new_fc1 = {"fc1.weight": rn(8, 4), "fc1.bias": rn(8)}
+    torch.save(new_fc1, root / "acoustic_connector" / "pytorch_model.bin")
+    deltas, repl, rep = L.collect_overrides(tmp_path / "ckpt")
+    assert rep.language_model and rep.diffusion_head_lora and rep.acoustic_connector and not rep.semantic_connector and not rep.diffusion_head_full
+    assert rep.adapter_root == root
+    out = dict(L.merged_state_dict(base.items(), deltas, repl))
+    want = {
+        "model.language_model.layers.0.self_attn.q_proj.weight": (base["model.language_model.layers.0.self_attn.q_proj.weight"].float() + (8 / 4) * Bq @ Aq).bfloat16(),
+        "model.language_model.layers.0.mlp.down_proj.weight": (base["model.language_model.layers.0.mlp.down_proj.weight"].float() + (6 / 2) * Bd @ Ad).bfloat16(),
+        "model.prediction_head.layers.0.ffn.gate_proj.weight": (base["model.prediction_head.layers.0.ffn.gate_proj.weight"].float() + (4 / 2.0) * Bh @ Ah).bfloat16(),
+        "model.acoustic_connector.fc1.weight": new_fc1["fc1.weight"].bfloat16(),
+        "model.acoustic_connector.fc1.bias": new_fc1["fc1.bias"].bfloat16(),
+        "model.language_model.layers.0.self_attn.q_proj.bias": base["model.language_model.layers.0.self_attn.q_proj.bias"],
+    }
+    assert set(out) == set(base)
+    for k, v in want.items():
+        assert out[k].dtype == torch.bfloat16 and torch.equal(out[k], v), k
+    # an adapter that targets a tensor the checkpoint lacks must not be dropped silently
+    small = {k: v for k, v in base.items() if "down_proj" not in k}
+    with pytest.raises(KeyError):
+        list(L.merged_state_dict(small.items(), deltas, repl))
+    # full-head fallback is only read when no head adapter is present (:97-112)
+    import shutil
+    shutil.rmtree(root / "diffusion_head")
+    torch.save({"layers.0.ffn.gate_proj.weight": rn(24, 8)}, root / "diffusion_head_full.bin")
+    _, repl2, rep2 = L.collect_overrides(tmp_path / "ckpt")
+    assert rep2.diffusion_head_full and not rep2.diffusion_head_lora and "model.prediction_head.layers.0.ffn.gate_proj.weight" in repl2
+    with pytest.raises(FileNotFoundError):
+        L.collect_overrides(tmp_path / "nope" / "lora")
+    from vibevoice.modular.lora_loading import load_lora_assets  # noqa: F401  (drop-in import path)

@@ -81,6 +81,7 @@ class VibeVoiceForConditionalGenerationInference:
         self._max_steps = max_diffusion_steps
         self.engine: Optional[Engine] = None
         self._pending: List[Tuple[str, torch.Tensor]] = []
+        self._weights_source = None              # callable -> fresh (name, tensor) iterator, for adapter re-packing (lora.py)
         self.ddpm_inference_steps = config.diffusion_head_config.ddpm_num_inference_steps
         self.dtype = torch.bfloat16
         self._kv_tokens = 0
@@ -111,6 +112,8 @@ class VibeVoiceForConditionalGenerationInference:
             raise ValueError("tokenizer ids (speech_start/end/diffusion/eos) are needed before weights are packed")
         self._tok = tok
         eng = self._ensure_engine(self._valid_ids(tok))
+        if isinstance(state_dict, dict):
+            self._weights_source = lambda sd=state_dict: iter(sd.items())
         items = state_dict.items() if isinstance(state_dict, dict) else state_dict
         scale = bias = None
         for name, t in items:
@@ -157,8 +160,31 @@ class VibeVoiceForConditionalGenerationInference:
                 with safe_open(f, framework="pt", device="cpu") as sf:
                     for k in sf.keys():
                         yield k, sf.get_tensor(k)
-        m.load_state_dict(it(), tokenizer)
+        m._weights_source = it
+        lora_dir = kw.pop("lora_dir", None)
+        if lora_dir is not None:
+            from .lora import collect_overrides, merged_state_dict
+            deltas, repl, m.lora_report = collect_overrides(lora_dir)
+            m.load_state_dict(merged_state_dict(it(), deltas, repl), tokenizer)
+        else:
+            m.load_state_dict(it(), tokenizer)
         return m
+
+    def _reload_with(self, transform):
+        """Re-stream the weights through `transform` (an iterator -> iterator function) and pack them again; used by
+        `lora.load_lora_assets`.  Generation state (KV pages, codec state) does not survive."""
+        if self._weights_source is None:
+            raise RuntimeError("weights were loaded from a one-shot iterator; build the model with from_pretrained(..., lora_dir=...) instead")
+        if self.engine is not None:
+            self.engine.close()
+        self.engine = None
+        self._prefill = self._voice = None
+        self._lm_sd, self._voice_sd = {}, {}
+        self._kv_tokens = 0
+        src = self._weights_source
+        self.load_state_dict(transform(src()), self._tok)
+        self._weights_source = src
+        return self
 
     def eval(self):
         return self
