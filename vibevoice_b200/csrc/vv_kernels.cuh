@@ -715,6 +715,119 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(GemvP p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Deep-ring variant of gemm_mma_kernel for prologue-free GEMMs (all codec FFNs and transposed convs with M > 8).
+// Why: these GEMMs are tiny (K = 32..2048, <= 112 CTAs) and each CTA used to pay one L2/DRAM round trip PER k-step
+// (A register-prefetched one step ahead, W two steps ahead: ~3300 cycles per 64-wide k-step in ncu, 13-30 us per launch for a few
+// MFLOP).  Here BOTH operands arrive by cp.async into a 6-stage ring -- fp32 A tile [32 x 64] and bf16 W tile [64 x 64] per stage --
+// so up to five k-steps (usually the whole K of a split) are in flight from the first instruction and a CTA pays ~one round trip in
+// total.  The fp32 A tile is converted to the bf16 hi/lo mma fragments straight from shared memory (LDS.64 per fragment register,
+// row stride 72 floats = conflict-free), which also removes the second __syncthreads and the Ah/Al staging of the old kernel.
+// Same tile (32 x 64 x 64, 4 warps, warp = 16 output columns), same split-K / epilogue semantics, same hi+lo accuracy.
+// ---------------------------------------------------------------------------------------------
+constexpr int MR_ST = 6, MR_ALD = MM_BK + 8;   // 72-float rows: a half-warp LDS.64 (4 rows x 8 words) hits 32 distinct banks
+constexpr int MR_A_BYTES = MM_BM * MR_ALD * 4, MR_W_BYTES = MM_BN * MM_LD * 2, MR_STAGE = MR_A_BYTES + MR_W_BYTES;
+constexpr int MR_SMEM = MR_ST * MR_STAGE;
+__global__ void __launch_bounds__(128) gemm_mma_ring_kernel(GemvP p) {
+  extern __shared__ __align__(16) unsigned char mr_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bm = blockIdx.y * MM_BM, bn = blockIdx.x * MM_BN;
+  const int K = p.K, nk_all = (K + MM_BK - 1) / MM_BK;
+  const int kz = blockIdx.z, nz = gridDim.z;
+  const int kt0 = (int)(((long long)nk_all * kz) / nz), kt1 = (int)(((long long)nk_all * (kz + 1)) / nz);
+  const int nk = kt1 - kt0;
+  auto a_tile = [&](int stage) { return reinterpret_cast<float*>(mr_smem + stage * MR_STAGE); };
+  auto w_tile = [&](int stage) { return reinterpret_cast<bf16*>(mr_smem + stage * MR_STAGE + MR_A_BYTES); };
+  auto load_w = [&](int stage, int kt) {          // 64 rows x 8 chunks of 16 B
+    bf16* wt = w_tile(stage);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 128, r = idx >> 3, c = (idx & 7) * 8;
+      const int n = bn + r, k = (kt0 + kt) * MM_BK + c;
+      const bool ok = (n < p.N) && (k < K);
+      cp_async16(wt + r * MM_LD + c, p.W + (size_t)(ok ? n : 0) * K + (ok ? k : 0), ok ? 16 : 0);
+    }
+  };
+  // A loader: 32 rows x 16 chunks of 16 B (4 floats); thread -> row tid/4, chunks (tid%4) + 4 i  (a row's 4 threads cover 64 B runs)
+  const int ar = tid >> 2;
+  const float* arow = (bm + ar < p.M) ? p.x + p.xmap.off(bm + ar) : nullptr;
+  auto load_a = [&](int stage, int kt) {
+    float* at = a_tile(stage) + ar * MR_ALD;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = ((tid & 3) + 4 * i) * 4, k = (kt0 + kt) * MM_BK + c;
+      const bool ok = arow && (k < K);
+      cp_async16(at + c, ok ? arow + k : p.x, ok ? 16 : 0);
+    }
+  };
+  float acc[2][2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+
+  pdl_trigger();
+#pragma unroll
+  for (int s_ = 0; s_ < MR_ST - 1; ++s_) if (s_ < nk) load_w(s_, s_);      // weights do not depend on the predecessor grid
+  pdl_wait();
+#pragma unroll
+  for (int s_ = 0; s_ < MR_ST - 1; ++s_) { if (s_ < nk) load_a(s_, s_); cp_async_commit(); }   // group s_ completes => W(all issued) and A(s_) landed
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<MR_ST - 2>();            // stage kt has landed (this thread's copies) ...
+    __syncthreads();                       // ... and everyone's; all warps are also done reading stage kt-1
+    if (kt + MR_ST - 1 < nk) { load_w((kt + MR_ST - 1) % MR_ST, kt + MR_ST - 1); load_a((kt + MR_ST - 1) % MR_ST, kt + MR_ST - 1); }
+    cp_async_commit();
+    const int st = kt % MR_ST;
+    const float* at = a_tile(st);
+    const bf16* wt = w_tile(st);
+#pragma unroll
+    for (int kk = 0; kk < MM_BK; kk += 16) {
+      unsigned ah[2][4], al[2][4], bw[4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        // m16n8k16 A fragment: reg0 = (row g, k 2t..2t+1), reg1 = (row g+8, same k), reg2 = (row g, k+8..), reg3 = (row g+8, k+8..)
+        const float* a0 = at + (mt * 16 + (lane >> 2)) * MR_ALD + kk + (lane & 3) * 2;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 v = *reinterpret_cast<const float2*>(a0 + (q & 1) * 8 * MR_ALD + (q >> 1) * 8);
+          const float hx = __bfloat162float(__float2bfloat16_rn(v.x)), hy = __bfloat162float(__float2bfloat16_rn(v.y));
+          ah[mt][q] = pack_bf16(hx, hy);
+          al[mt][q] = pack_bf16(v.x - hx, v.y - hy);
+        }
+      }
+      ldmatrix_x4(bw, wt + (warp * 16 + (lane & 7) + ((lane >> 4) << 3)) * MM_LD + kk + ((lane >> 3) & 1) * 8);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        mma_bf16_16816(acc[mt][0], ah[mt], bw[0], bw[1]);
+        mma_bf16_16816(acc[mt][0], al[mt], bw[0], bw[1]);
+        mma_bf16_16816(acc[mt][1], ah[mt], bw[2], bw[3]);
+        mma_bf16_16816(acc[mt][1], al[mt], bw[2], bw[3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int m = bm + mt * 16 + (lane >> 2) + (q >> 1) * 8;
+        const int n = bn + warp * 16 + nt * 8 + (lane & 3) * 2 + (q & 1);
+        if (m < p.M && n < p.N) {
+          if (nz == 1) {
+            epi_store(p, m, n, acc[mt][nt][q] + (p.bias ? p.bias[n] : 0.f));
+          } else {
+            float v = acc[mt][nt][q] + ((kz == 0 && p.bias) ? p.bias[n] : 0.f);
+            if (p.epi == EPI_GAMMA_RESID) v *= p.epi_a[n];
+            else if (p.epi == EPI_GATED_RESID) v *= p.epi_a[(long long)m * p.epi_lda + n];
+            atomicAdd(p.y + (long long)m * p.ldy + n, v);
+          }
+        }
+      }
+}
+
+// ---------------------------------------------------------------------------------------------
 // tcgen05 / TMEM GEMM (5th-gen tensor cores) for the M > 8 GEMMs: D^T[128 x 64] += W[128 x K] * A[64 x K]^T ("swap-AB":
 // the 128-row MMA M dimension is filled with weight rows, the MMA N dimension with up to 64 activation rows).
 //   * operands in shared memory, K-major, 128-byte swizzle (canonical UMMA layout ((8,n),2):((8,SBO),1), SBO = 1024 B);
@@ -1020,19 +1133,28 @@ __global__ void __launch_bounds__(256) mixer_fused_kernel(const float* __restric
   const int c0 = blockIdx.z * MIX_CC, c1 = min(C, c0 + MIX_CC), nc = c1 - c0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ float s_inv[MIX_TT + 6];
+  __shared__ float s_part[MIX_TT + 6][8];
   const float* xb = x + (size_t)b * T * C;
   const float* hb = hist + (size_t)b * 6 * C;
-  for (int r = warp; r < (t1 - t0) + 6; r += 8) {               // row tau = t0 - 6 + r
+  // sum of squares of every row of this tile that lies inside the frame: the 8 warps split the channels of each row, so a
+  // single wide row (T = 1, C = 2048) is reduced by the whole CTA rather than by one warp
+  const int nrow = (t1 - t0) + 6, cw = (C + 7) >> 3;
+  for (int r = 0; r < nrow; ++r) {                              // row tau = t0 - 6 + r
     const int tau = t0 - 6 + r;
-    float inv = 0.f;
+    float ss = 0.f;
     if (tau >= 0) {
       const float* xr = xb + (size_t)tau * C;
-      float ss = 0.f;
-      for (int c = lane; c < C; c += 32) { const float v = xr[c]; ss += v * v; }
-      ss = warp_sum(ss);
-      inv = rsqrtf(ss / (float)C + eps);
+      for (int c = warp * cw + lane; c < min(C, (warp + 1) * cw); c += 32) { const float v = xr[c]; ss += v * v; }
     }
-    if (lane == 0) s_inv[r] = inv;
+    ss = warp_sum(ss);
+    if (lane == 0) s_part[r][warp] = ss;
+  }
+  __syncthreads();
+  if (tid < nrow) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += s_part[tid][i];
+    s_inv[tid] = (t0 - 6 + tid >= 0) ? rsqrtf(t / (float)C + eps) : 0.f;
   }
   __syncthreads();
   auto val = [&](int tau, int c) -> float {                      // normalised input at absolute time tau (tau >= -6)

@@ -90,6 +90,8 @@ struct vv_ctx {
   bf16* s_planes = nullptr; size_t planes_elems = 0;
   int mma_min_rows = 9;     // M >= this -> tensor-core GEMM (all prologues/epilogues), below -> weight-streaming GEMV (measured: at M = 8 the GEMV streams weights 1.7x faster)
   int use_tc5 = 1;          // tcgen05/TMEM GEMM: 0 off, 1 auto (wide GEMMs), 2 every M > 8 GEMM (VV_TC5)
+  bool mma_ring = true;     // 6-stage cp.async ring for both GEMM operands (gemm_mma_ring_kernel); VV_NO_MMA_RING=1 -> old 1-ahead kernel
+  bool fuse_mixer = false, norm_in_gemm = false;   // the two halves of fuse_codec, separately selectable (VV_FUSE_MIXER / VV_NORM_IN_GEMM)
   bool fuse_codec = false;  // fused mixer + norm-in-GEMM measured 5% slower than the separate small kernels (VV_FUSE_CODEC=1 to enable)
   bf16* head_slab = nullptr; size_t head_slab_bytes = 0; size_t l2_persist_bytes = 0; size_t l2_window_max = 0;
   int wr_tasks_min = 296;
@@ -236,6 +238,11 @@ static int linear(const L& l, GemvP p) {
     if (l.c->use_splitk && inplace_res && nk >= 8 && (int)(grid.x * grid.y) < l.c->sm_count) {
       int z = std::min(std::min(nk / 2, 16), (2 * l.c->sm_count) / (int)(grid.x * grid.y));
       grid.z = std::max(z, 1);
+    }
+    if (l.c->mma_ring && p.pro == PRO_NONE && p.epi != EPI_SWIGLU) {
+      CK(cudaFuncSetAttribute(gemm_mma_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MR_SMEM));
+      CK(launch_k(l, gemm_mma_ring_kernel, dim3(grid), dim3(128), (size_t)MR_SMEM, p));
+      return 0;
     }
     CK(launch_k(l, gemm_mma_kernel, dim3(grid), dim3(128), 0, p));
     return 0;
@@ -431,7 +438,10 @@ extern "C" int vv_create(const vv_model_desc* desc, int device, vv_ctx** out) {
   if (getenv("VV_NO_FUSE_ROPE")) c->fuse_rope = false;
   if (getenv("VV_TC5")) c->use_tc5 = atoi(getenv("VV_TC5"));
   if (getenv("VV_MMA_MIN_ROWS")) c->mma_min_rows = atoi(getenv("VV_MMA_MIN_ROWS"));
+  if (getenv("VV_NO_MMA_RING")) c->mma_ring = false;
   if (getenv("VV_FUSE_CODEC")) c->fuse_codec = true;
+  c->fuse_mixer = c->fuse_codec || getenv("VV_FUSE_MIXER");
+  c->norm_in_gemm = c->fuse_codec || getenv("VV_NORM_IN_GEMM");
   const char* ns = getenv("VV_NO_SPLITK");
   c->use_splitk = !(ns && ns[0] == '1');
   const char* np = getenv("VV_NO_PDL");
@@ -1331,7 +1341,7 @@ static int assemble(const L& l, const float* src, const float* hist, float* win,
 static int enqueue_block(const L& l, const Block& b, const float* xin, float* xout, int B, int T, float eps) {
   vv_ctx* c = l.c;
   const int C = b.C, M = B * T;
-  if (c->fuse_codec) {
+  if (c->fuse_mixer) {
     CK(launch_k(l, mixer_fused_kernel, dim3((T + MIX_TT - 1) / MIX_TT, B, (C + MIX_CC - 1) / MIX_CC), dim3(256), 0, xin, b.hist, b.next, b.norm_w, b.dw_w, b.dw_b, b.gamma, xout, T, C, eps));
   } else {
     RET(assemble(l, xin, b.hist, c->s_win, b.next, B, T, 6, C, b.norm_w, eps, 1.f, 0.f));
@@ -1339,7 +1349,7 @@ static int enqueue_block(const L& l, const Block& b, const float* xin, float* xo
     CK(launch_k(l, dwconv_res_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, xin, c->s_win, b.dw_w, b.dw_b, b.gamma, xout, B, T, C));
   }
   GemvP p;
-  if (M <= 8 || c->fuse_codec) {
+  if (M <= 8 || c->norm_in_gemm) {
     p = mk(b.w1, b.b1, xout, C, c->s_u, 4 * C, M, 4 * C, C);
     p.pro = PRO_RMSNORM; p.pro_w = b.ffn_norm_w; p.pro_eps = eps; p.epi = EPI_GELU;
     RET(linear(l, p));
