@@ -715,7 +715,7 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(GemvP p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Deep-ring variant of gemm_mma_kernel for prologue-free GEMMs (all codec FFNs and transposed convs with M > 8).
+// Deep-ring variant of gemm_mma_kernel for the codec GEMMs with M > 8 (FFNs, transposed convs); prologue none or RMSNorm.
 // Why: these GEMMs are tiny (K = 32..2048, <= 112 CTAs) and each CTA used to pay one L2/DRAM round trip PER k-step
 // (A register-prefetched one step ahead, W two steps ahead: ~3300 cycles per 64-wide k-step in ncu, 13-30 us per launch for a few
 // MFLOP).  Here BOTH operands arrive by cp.async into a 6-stage ring -- fp32 A tile [32 x 64] and bf16 W tile [64 x 64] per stage --
@@ -727,6 +727,8 @@ __global__ void __launch_bounds__(128) gemm_mma_kernel(GemvP p) {
 constexpr int MR_ST = 6, MR_ALD = MM_BK + 8;   // 72-float rows: a half-warp LDS.64 (4 rows x 8 words) hits 32 distinct banks
 constexpr int MR_A_BYTES = MM_BM * MR_ALD * 4, MR_W_BYTES = MM_BN * MM_LD * 2, MR_STAGE = MR_A_BYTES + MR_W_BYTES;
 constexpr int MR_SMEM = MR_ST * MR_STAGE;
+constexpr int MR_MAXK_NORM = 512;                  // PRO_RMSNORM: the norm weight row is staged in shared memory behind the ring (2 CTAs/SM must still fit)
+constexpr int MR_SMEM_NORM = MR_SMEM + MR_MAXK_NORM * 4;
 __global__ void __launch_bounds__(128) gemm_mma_ring_kernel(GemvP p) {
   extern __shared__ __align__(16) unsigned char mr_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -766,8 +768,16 @@ __global__ void __launch_bounds__(128) gemm_mma_ring_kernel(GemvP p) {
     for (int j = 0; j < 2; ++j)
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+  // PRO_RMSNORM (never combined with split-K): y = W (x * inv_rms(x) * g) = inv_rms(x) * (W (x * g)) -- the per-row scalar commutes
+  // with the GEMM, so the tile multiplies x * g (g = norm weight, applied while building fragments), every thread accumulates the
+  // squares of the raw x values it converts anyway, and the row scale is applied to the accumulator in the epilogue.  No separate
+  // normalisation pass, no extra read of x.
+  const bool rms = (p.pro == PRO_RMSNORM);
+  float* gk = reinterpret_cast<float*>(mr_smem + MR_SMEM);
+  float ss[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
 
   pdl_trigger();
+  if (rms) for (int i = tid * 4; i < K; i += 128 * 4) cp_async16(gk + i, p.pro_w + i, 16);
 #pragma unroll
   for (int s_ = 0; s_ < MR_ST - 1; ++s_) if (s_ < nk) load_w(s_, s_);      // weights do not depend on the predecessor grid
   pdl_wait();
@@ -790,7 +800,13 @@ __global__ void __launch_bounds__(128) gemm_mma_ring_kernel(GemvP p) {
         const float* a0 = at + (mt * 16 + (lane >> 2)) * MR_ALD + kk + (lane & 3) * 2;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float2 v = *reinterpret_cast<const float2*>(a0 + (q & 1) * 8 * MR_ALD + (q >> 1) * 8);
+          float2 v = *reinterpret_cast<const float2*>(a0 + (q & 1) * 8 * MR_ALD + (q >> 1) * 8);
+          if (rms) {
+            ss[mt][q & 1] = fmaf(v.x, v.x, fmaf(v.y, v.y, ss[mt][q & 1]));
+            const int kg = min((kt0 + kt) * MM_BK + kk + (lane & 3) * 2 + (q >> 1) * 8, K - 2);   // columns >= K hold zeros
+            const float2 g = *reinterpret_cast<const float2*>(gk + kg);
+            v.x *= g.x; v.y *= g.y;
+          }
           const float hx = __bfloat162float(__float2bfloat16_rn(v.x)), hy = __bfloat162float(__float2bfloat16_rn(v.y));
           ah[mt][q] = pack_bf16(hx, hy);
           al[mt][q] = pack_bf16(v.x - hx, v.y - hy);
@@ -806,6 +822,17 @@ __global__ void __launch_bounds__(128) gemm_mma_ring_kernel(GemvP p) {
       }
     }
   }
+  if (rms) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {                 // a row's 64 columns per k-step live in the 4 lanes of a quad
+        float t = ss[mt][h];
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        ss[mt][h] = rsqrtf(t / (float)K + p.pro_eps);
+      }
+  }
 #pragma unroll
   for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -816,7 +843,7 @@ __global__ void __launch_bounds__(128) gemm_mma_ring_kernel(GemvP p) {
         const int n = bn + warp * 16 + nt * 8 + (lane & 3) * 2 + (q & 1);
         if (m < p.M && n < p.N) {
           if (nz == 1) {
-            epi_store(p, m, n, acc[mt][nt][q] + (p.bias ? p.bias[n] : 0.f));
+            epi_store(p, m, n, acc[mt][nt][q] * (rms ? ss[mt][q >> 1] : 1.f) + (p.bias ? p.bias[n] : 0.f));
           } else {
             float v = acc[mt][nt][q] + ((kz == 0 && p.bias) ? p.bias[n] : 0.f);
             if (p.epi == EPI_GAMMA_RESID) v *= p.epi_a[n];
@@ -1117,62 +1144,89 @@ __global__ void dwconv_res_kernel(const float* __restrict__ x, const float* __re
 }
 
 // Fused Block1D mixer: out = x + gamma * (bias + depthwise_causal_conv7(RMSNorm(x) * wn)) in ONE launch (replaces
-// assemble_window(norm) + dwconv_res).  CTA = (batch row, tile of MIX_TT time steps), all channels; the 6 halo rows before the
-// tile are re-normalised from x (or taken from the streaming history for t < 0); the CTA(s) covering the last 6 time steps of
-// the frame also stage the next history.
+// assemble_window(norm) + dwconv_res).  grid (time tiles of MIX_TT, batch, channel slabs of MIX_CC); block 256, thread <-> one fixed
+// channel (its 7 taps, norm weight, gamma and bias are fetched BEFORE griddepcontrol.wait -- they do not depend on the producer).
+// ONE dependent global round trip: the tile's rows (6 halo rows + MIX_TT) are read once -- full rows for the sum of squares, the
+// CTA's channel slab kept in shared memory -- then norm, taps, residual and the next streaming history all come from shared memory.
+// (The first fused version read x through global memory in two dependent phases and was 3.6 us per launch slower than the two
+// kernels it replaced.)  Requires C % 256 == 0 or 256 % C == 0 (host checks; other widths use the two-kernel path).
 constexpr int MIX_TT = 8, MIX_CC = 256;
-// grid (time tiles of MIX_TT, batch, channel slabs of MIX_CC): enough CTAs even for T = 1 (C = 2048 -> 8 CTAs); every CTA
-// re-derives the row norms it needs (rows are L2-resident and short), so there is no cross-CTA dependency.
 __global__ void __launch_bounds__(256) mixer_fused_kernel(const float* __restrict__ x, const float* __restrict__ hist, float* __restrict__ hist_next,
                                                           const float* __restrict__ wn, const float* __restrict__ w /*[7][C]*/,
                                                           const float* __restrict__ bias, const float* __restrict__ gamma, float* __restrict__ out,
                                                           int T, int C, float eps) {
-  pdl_trigger();
-  pdl_wait();
+  __shared__ float xs[MIX_TT + 6][MIX_CC];
+  __shared__ float s_ss[MIX_TT + 6];
   const int b = blockIdx.y, t0 = blockIdx.x * MIX_TT, t1 = min(T, t0 + MIX_TT);
-  const int c0 = blockIdx.z * MIX_CC, c1 = min(C, c0 + MIX_CC), nc = c1 - c0;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  __shared__ float s_inv[MIX_TT + 6];
-  __shared__ float s_part[MIX_TT + 6][8];
+  const int nc = min(C, MIX_CC), c0 = blockIdx.z * nc;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int nrow = (t1 - t0) + 6;
+  const int ci = tid % nc, c = c0 + ci, rp = 256 / nc;          // this thread's channel; rp rows are produced per pass
+  pdl_trigger();
+  float wt[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) wt[j] = w[j * C + c];
+  const float wnc = wn[c], gc = gamma[c], bc = bias[c];
+  if (tid < nrow) s_ss[tid] = 0.f;
+  __syncthreads();
+  pdl_wait();
   const float* xb = x + (size_t)b * T * C;
   const float* hb = hist + (size_t)b * 6 * C;
-  // sum of squares of every row of this tile that lies inside the frame: the 8 warps split the channels of each row, so a
-  // single wide row (T = 1, C = 2048) is reduced by the whole CTA rather than by one warp
-  const int nrow = (t1 - t0) + 6, cw = (C + 7) >> 3;
-  for (int r = 0; r < nrow; ++r) {                              // row tau = t0 - 6 + r
-    const int tau = t0 - 6 + r;
-    float ss = 0.f;
-    if (tau >= 0) {
-      const float* xr = xb + (size_t)tau * C;
-      for (int c = warp * cw + lane; c < min(C, (warp + 1) * cw); c += 32) { const float v = xr[c]; ss += v * v; }
+  // rows before the frame (tau < 0): only this CTA's channel slab of the (already normalised) history is needed
+  const int nh = max(0, min(6, -(t0 - 6)));                       // tile rows 0 .. nh-1 come from the history
+  for (int r = tid / nc; r < nh; r += rp) xs[r][ci] = hb[(size_t)(t0 + r) * C + c];      // tau + 6 = t0 - 6 + r + 6
+  // rows inside the frame: all loads of a thread are issued back to back (no reduction in between -- a shuffle/atomic after every
+  // load serialises the L2 round trips, which made the first version of this loop 10+ us), then reduced row by row
+  if (C >= MIX_CC) {
+    const int per = C / MIX_CC;                                    // 1, 2, 4 or 8 elements of a row per thread
+    for (int r = nh; r < nrow; ++r) {
+      const float* xr = xb + (size_t)(t0 - 6 + r) * C;
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = (k < per) ? xr[tid + k * MIX_CC] : 0.f;
+      float sq = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sq = fmaf(v[k], v[k], sq);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) if (k < per && k == (int)blockIdx.z) xs[r][tid] = v[k];
+      sq = warp_sum(sq);
+      if (lane == 0) atomicAdd(&s_ss[r], sq);
     }
-    ss = warp_sum(ss);
-    if (lane == 0) s_part[r][warp] = ss;
+  } else {
+    // C < 256: a thread owns (row tid / C + k * rp, channel tid % C); at most ceil(14 / rp) <= 8 rows per thread when C >= 128 ...
+    const int r0 = nh + tid / nc;
+    for (int rb = r0; rb < nrow; rb += 8 * rp) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const int r = rb + k * rp; v[k] = (r < nrow) ? xb[(size_t)(t0 - 6 + r) * C + c] : 0.f; }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int r = rb + k * rp;
+        if (r < nrow) xs[r][ci] = v[k];
+        if ((C % 32) == 0) {                                       // the 32 lanes of a warp sit in one row
+          const float sq = warp_sum(v[k] * v[k]);
+          if (lane == 0 && r < nrow) atomicAdd(&s_ss[r], sq);
+        } else if (r < nrow) {
+          atomicAdd(&s_ss[r], v[k] * v[k]);
+        }
+      }
+    }
   }
   __syncthreads();
-  if (tid < nrow) {
-    float t = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t += s_part[tid][i];
-    s_inv[tid] = (t0 - 6 + tid >= 0) ? rsqrtf(t / (float)C + eps) : 0.f;
-  }
+  if (tid < nrow) s_ss[tid] = (t0 - 6 + tid >= 0) ? rsqrtf(s_ss[tid] / (float)C + eps) : 0.f;
   __syncthreads();
-  auto val = [&](int tau, int c) -> float {                      // normalised input at absolute time tau (tau >= -6)
-    return tau < 0 ? hb[(size_t)(tau + 6) * C + c] : xb[(size_t)tau * C + c] * s_inv[tau - t0 + 6] * wn[c];
-  };
-  const int n = (t1 - t0) * nc;
-  for (int i = tid; i < n; i += 256) {
-    const int c = c0 + i % nc, t = t0 + i / nc;
-    float acc = bias[c];
+  auto nval = [&](int r) -> float { return (t0 - 6 + r < 0) ? xs[r][ci] : xs[r][ci] * s_ss[r] * wnc; };
+  for (int tl = tid / nc; tl < t1 - t0; tl += rp) {
+    float acc = bc;
 #pragma unroll
-    for (int j = 0; j < 7; ++j) acc = fmaf(w[j * C + c], val(t - 6 + j, c), acc);
-    out[((size_t)b * T + t) * C + c] = xb[(size_t)t * C + c] + gamma[c] * acc;
+    for (int j = 0; j < 7; ++j) acc = fmaf(wt[j], nval(tl + j), acc);
+    out[((size_t)b * T + t0 + tl) * C + c] = xs[tl + 6][ci] + gc * acc;
   }
-  // next history = normalised rows T-6 .. T-1 (rows before the frame come from the old history)
-  for (int i = tid; i < 6 * nc; i += 256) {
-    const int c = c0 + i % nc, r = i / nc, tau = T - 6 + r;
+  // next history = normalised rows T-6 .. T-1 (rows before the frame come from the old history, held by the first tile)
+  for (int r6 = tid / nc; r6 < 6; r6 += rp) {
+    const int tau = T - 6 + r6;
     const bool mine = (tau >= t0 && tau < t1) || (tau < 0 && blockIdx.x == 0);
-    if (mine) hist_next[((size_t)b * 6 + r) * C + c] = val(tau, c);
+    if (mine) hist_next[((size_t)b * 6 + r6) * C + c] = nval(tau - t0 + 6);
   }
 }
 

@@ -90,6 +90,8 @@ struct vv_ctx {
   bf16* s_planes = nullptr; size_t planes_elems = 0;
   int mma_min_rows = 9;     // M >= this -> tensor-core GEMM (all prologues/epilogues), below -> weight-streaming GEMV (measured: at M = 8 the GEMV streams weights 1.7x faster)
   int use_tc5 = 1;          // tcgen05/TMEM GEMM: 0 off, 1 auto (wide GEMMs), 2 every M > 8 GEMM (VV_TC5)
+  bool ring_rms = true;     // RMSNorm folded into gemm_mma_ring_kernel (row scale in the epilogue) instead of rows_norm_kernel (VV_NO_RING_RMS=1 -> off)
+  int codec_mma_min_rows = 9;   // codec GEMMs with at least this many rows use the tensor-core ring kernel (VV_CODEC_MMA_MIN_ROWS)
   bool mma_ring = true;     // 6-stage cp.async ring for both GEMM operands (gemm_mma_ring_kernel); VV_NO_MMA_RING=1 -> old 1-ahead kernel
   bool fuse_mixer = false, norm_in_gemm = false;   // the two halves of fuse_codec, separately selectable (VV_FUSE_MIXER / VV_NORM_IN_GEMM)
   bool fuse_codec = false;  // fused mixer + norm-in-GEMM measured 5% slower than the separate small kernels (VV_FUSE_CODEC=1 to enable)
@@ -239,9 +241,10 @@ static int linear(const L& l, GemvP p) {
       int z = std::min(std::min(nk / 2, 16), (2 * l.c->sm_count) / (int)(grid.x * grid.y));
       grid.z = std::max(z, 1);
     }
-    if (l.c->mma_ring && p.pro == PRO_NONE && p.epi != EPI_SWIGLU) {
-      CK(cudaFuncSetAttribute(gemm_mma_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MR_SMEM));
-      CK(launch_k(l, gemm_mma_ring_kernel, dim3(grid), dim3(128), (size_t)MR_SMEM, p));
+    const bool ring_rms = p.pro == PRO_RMSNORM && grid.z == 1 && p.K <= MR_MAXK_NORM && p.K % 4 == 0;
+    if (l.c->mma_ring && (p.pro == PRO_NONE || ring_rms) && p.epi != EPI_SWIGLU) {
+      CK(cudaFuncSetAttribute(gemm_mma_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MR_SMEM_NORM));
+      CK(launch_k(l, gemm_mma_ring_kernel, dim3(grid), dim3(128), (size_t)(ring_rms ? MR_SMEM_NORM : MR_SMEM), p));
       return 0;
     }
     CK(launch_k(l, gemm_mma_kernel, dim3(grid), dim3(128), 0, p));
@@ -439,6 +442,9 @@ extern "C" int vv_create(const vv_model_desc* desc, int device, vv_ctx** out) {
   if (getenv("VV_TC5")) c->use_tc5 = atoi(getenv("VV_TC5"));
   if (getenv("VV_MMA_MIN_ROWS")) c->mma_min_rows = atoi(getenv("VV_MMA_MIN_ROWS"));
   if (getenv("VV_NO_MMA_RING")) c->mma_ring = false;
+  if (getenv("VV_NO_RING_RMS")) c->ring_rms = false;
+  if (getenv("VV_CODEC_MMA_MIN_ROWS")) c->codec_mma_min_rows = atoi(getenv("VV_CODEC_MMA_MIN_ROWS"));
+  else if (getenv("VV_MMA_MIN_ROWS")) c->codec_mma_min_rows = c->mma_min_rows;
   if (getenv("VV_FUSE_CODEC")) c->fuse_codec = true;
   c->fuse_mixer = c->fuse_codec || getenv("VV_FUSE_MIXER");
   c->norm_in_gemm = c->fuse_codec || getenv("VV_NORM_IN_GEMM");
@@ -1341,7 +1347,7 @@ static int assemble(const L& l, const float* src, const float* hist, float* win,
 static int enqueue_block(const L& l, const Block& b, const float* xin, float* xout, int B, int T, float eps) {
   vv_ctx* c = l.c;
   const int C = b.C, M = B * T;
-  if (c->fuse_mixer) {
+  if (c->fuse_mixer && (C >= MIX_CC ? C % MIX_CC == 0 : MIX_CC % C == 0)) {
     CK(launch_k(l, mixer_fused_kernel, dim3((T + MIX_TT - 1) / MIX_TT, B, (C + MIX_CC - 1) / MIX_CC), dim3(256), 0, xin, b.hist, b.next, b.norm_w, b.dw_w, b.dw_b, b.gamma, xout, T, C, eps));
   } else {
     RET(assemble(l, xin, b.hist, c->s_win, b.next, B, T, 6, C, b.norm_w, eps, 1.f, 0.f));
@@ -1349,7 +1355,7 @@ static int enqueue_block(const L& l, const Block& b, const float* xin, float* xo
     CK(launch_k(l, dwconv_res_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, xin, c->s_win, b.dw_w, b.dw_b, b.gamma, xout, B, T, C));
   }
   GemvP p;
-  if (M <= 8 || c->norm_in_gemm) {
+  if (M < c->mma_min_rows || c->norm_in_gemm || (c->ring_rms && c->mma_ring && C <= MR_MAXK_NORM && c->use_tc5 != 2)) {
     p = mk(b.w1, b.b1, xout, C, c->s_u, 4 * C, M, 4 * C, C);
     p.pro = PRO_RMSNORM; p.pro_w = b.ffn_norm_w; p.pro_eps = eps; p.epi = EPI_GELU;
     RET(linear(l, p));
@@ -1379,8 +1385,15 @@ static int conv_apply(const L& l, const ConvL& cv, const float* win, float* y, i
   return linear(l, p);
 }
 
+struct ScopedMinRows {     // the codec stages may use a different GEMV/GEMM row threshold than the LM and the sampler
+  vv_ctx* c; int saved;
+  ScopedMinRows(vv_ctx* c_, int v) : c(c_), saved(c_->mma_min_rows) { c->mma_min_rows = v; }
+  ~ScopedMinRows() { c->mma_min_rows = saved; }
+};
+
 static int enqueue_decode(const L& l, const float* latent, const int32_t* active, float* audio) {
   vv_ctx* c = l.c;
+  ScopedMinRows scoped(c, c->codec_mma_min_rows);
   const auto& d = c->d;
   Codec& k = c->dec;
   const int B = d.max_batch, ns = d.n_stages;
@@ -1411,6 +1424,7 @@ static int enqueue_decode(const L& l, const float* latent, const int32_t* active
 
 static int enqueue_encode(const L& l, const float* audio, const int32_t* active, float* feat) {
   vv_ctx* c = l.c;
+  ScopedMinRows scoped(c, c->codec_mma_min_rows);
   const auto& d = c->d;
   Codec& k = c->enc;
   const int B = d.max_batch, ns = d.n_stages;
