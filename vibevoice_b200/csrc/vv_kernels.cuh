@@ -1015,6 +1015,24 @@ __global__ void conv_naive_kernel(const float* __restrict__ W, const float* __re
   y[idx] = acc;
 }
 
+// same product, one WARP per output: for long windows (decoder head conv: K = 7 x 32 = 224, N = 1) the thread-per-output loop is a
+// 224-deep dependent FMA chain on 13 CTAs; here the lanes split K (coalesced 128 B reads of the window) and shuffle-reduce.
+__global__ void __launch_bounds__(256) conv_warp_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ x,
+                                                        RowMap xmap, float* __restrict__ y, int M, int N, int K) {
+  pdl_trigger();
+  pdl_wait();
+  const long long idx = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (idx >= (long long)M * N) return;
+  const int m = (int)(idx / N), n = (int)(idx % N);
+  const float* xr = x + xmap.off(m);
+  const float* wr = W + (size_t)n * K;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc = fmaf(wr[k], xr[k], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) y[idx] = acc + (bias ? bias[n] : 0.f);
+}
+
 // y[m,:] = rmsnorm(x[m,:]) * w   (one warp per row)
 __global__ void rows_norm_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
                                  int M, int C, float eps) {
@@ -1232,6 +1250,7 @@ __global__ void __launch_bounds__(256) mixer_fused_kernel(const float* __restric
 
 struct StateSeg { float* hist; float* next; int n; };   // n floats per batch row
 
+constexpr int ADV_SLICES = 8;     // CTAs per (segment, batch row): the widest histories (6 x 2048 floats) are a latency chain for one CTA
 __global__ void advance_kernel(const StateSeg* __restrict__ segs, const int* __restrict__ active) {
   pdl_trigger();
   pdl_wait();
@@ -1240,7 +1259,7 @@ __global__ void advance_kernel(const StateSeg* __restrict__ segs, const int* __r
   const StateSeg s = segs[blockIdx.x];
   float* d = s.hist + (size_t)b * s.n;
   const float* a = s.next + (size_t)b * s.n;
-  for (int i = threadIdx.x; i < s.n; i += blockDim.x) d[i] = a[i];
+  for (int i = blockIdx.z * blockDim.x + threadIdx.x; i < s.n; i += gridDim.z * blockDim.x) d[i] = a[i];
 }
 __global__ void state_zero_kernel(const StateSeg* __restrict__ segs, const int* __restrict__ rows) {
   const int b = rows[blockIdx.y];

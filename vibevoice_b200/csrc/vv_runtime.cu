@@ -1377,7 +1377,8 @@ static int conv_apply(const L& l, const ConvL& cv, const float* win, float* y, i
   const int M = B * T_out;
   if (cv.wf) {
     const long long n = (long long)M * cv.N;
-    CK(launch_k(l, conv_naive_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, cv.wf, cv.bias, win, xm, y, M, cv.N, cv.K));
+    if (cv.K >= 64) CK(launch_k(l, conv_warp_kernel, dim3((unsigned)((n + 7) / 8)), dim3(256), 0, cv.wf, cv.bias, win, xm, y, M, cv.N, cv.K));
+    else CK(launch_k(l, conv_naive_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, cv.wf, cv.bias, win, xm, y, M, cv.N, cv.K));
     return 0;
   }
   GemvP p = mk(cv.w, cv.bias, win, 0, y, cv.N, M, cv.N, cv.K);
@@ -1418,7 +1419,7 @@ static int enqueue_decode(const L& l, const float* latent, const int32_t* active
   const int T = k.T[ns - 1];
   RET(assemble(l, xa, hd.hist, c->s_win, hd.next, B, T, 6, hd.Cin, nullptr, 0.f, 1.f, 0.f));
   RET(conv_apply(l, hd, c->s_win, audio, B, T, T));
-  CK(launch_k(l, advance_kernel, dim3(k.n_segs, B), dim3(256), 0, k.segs_dev, active));
+  CK(launch_k(l, advance_kernel, dim3(k.n_segs, B, ADV_SLICES), dim3(256), 0, k.segs_dev, active));
   return 0;
 }
 
@@ -1445,7 +1446,7 @@ static int enqueue_encode(const L& l, const float* audio, const int32_t* active,
   const ConvL& hd = k.convs[ns];
   RET(assemble(l, xa, hd.hist, c->s_win, hd.next, B, 1, 6, hd.Cin, nullptr, 0.f, 1.f, 0.f));
   RET(conv_apply(l, hd, c->s_win, feat, B, 1, 1));
-  CK(launch_k(l, advance_kernel, dim3(k.n_segs, B), dim3(256), 0, k.segs_dev, active));
+  CK(launch_k(l, advance_kernel, dim3(k.n_segs, B, ADV_SLICES), dim3(256), 0, k.segs_dev, active));
   return 0;
 }
 
