@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE -- generates `tests/golden/*.pt` by running the UNMODIFIED reference modules
 (imported from /root/reference through `oracle/ref_shim.py`) on seeded synthetic checkpoints.
 
-    python -m oracle.make_golden            # rewrites tests/golden/
+    python -m oracle.make_golden [name ...]   # rewrites tests/golden/ (all fixtures, or the named ones)
 
 The reference has no golden vectors of its own; these fixtures are what pins the oracle
 (`oracle/vv_oracle.py`) and, through it, the CUDA path.  Only runs in the build container (the GPU box
@@ -212,13 +212,73 @@ def gen_voice_prompt(ns, preset="tiny"):
     return dict(preset=preset, wavs=wavs, masks=masks, seed=77, features=feats.clone(), connected=connected.clone())
 
 
-GENERATORS = dict(voice_prompt=gen_voice_prompt, scheduler=gen_scheduler, head=gen_head, codec=gen_codec, connector=gen_connector, lm=gen_lm)
+def _scripted(tok, s):
+    m = {"d": tok.speech_diffusion_id, "e": tok.speech_end_id, "s": tok.speech_start_id, "x": tok.eos_token_id}
+    return [m[c] for c in s]
+
+
+def gen_loop(ns, preset="tiny"):
+    """The reference's own `generate()` (modeling_vibevoice_inference.py:326-695), loop body unmodified, on the synthetic tiny
+    checkpoint; transformers-4.51.3 GenerationMixin glue restated by `ref_shim.install_generate_compat()`.  Three cases:
+      scripted  B=2, ragged left-padded prompts, scripts with a speaker turn (<end>,<start>) and per-row EOS
+                -> negative-stream restart, cache corrections for non-diffusing rows, codec-state zeroing, finished rows
+      free      B=1, the constrained argmax itself drives the state machine
+      maxlen    B=2 ragged, all-diffusion scripts, max_length_times=0.5 -> per-sample step limit / reach_max_step_sample"""
+    ref_shim.install_generate_compat()
+    cfg = preset_config(preset)
+    model = build_ref_model(ns, cfg)
+    tok = SynthTokenizer(cfg.decoder_config.vocab_size)
+    V = cfg.decoder_config.vocab_size
+    steps, cfg_scale = 5, 1.3
+    model.set_ddpm_inference_steps(steps)
+
+    def run(ids, mask, scripts, max_new_tokens, seed, max_length_times=2):
+        ref_shim.script_tokens(ids.shape[1], scripts)
+        torch.manual_seed(seed)
+        out = model.generate(input_ids=ids.clone(), attention_mask=mask.clone(), tokenizer=tok, cfg_scale=cfg_scale,
+                             max_new_tokens=max_new_tokens, speech_tensors=None, speech_masks=None,
+                             speech_input_mask=torch.zeros_like(ids, dtype=torch.bool), show_progress_bar=False, verbose=False,
+                             is_prefill=False, max_length_times=max_length_times)
+        ref_shim.script_tokens()
+        return dict(ids=ids, mask=mask, scripts=scripts, max_new_tokens=max_new_tokens, seed=seed, max_length_times=max_length_times,
+                    sequences=out.sequences.clone(), reach_max=out.reach_max_step_sample.clone(),
+                    audio=[None if a is None else a.clone() for a in out.speech_outputs])
+
+    g = torch.Generator().manual_seed(3)
+    L0 = 12
+    ids = torch.randint(0, V - 20, (2, L0), generator=g)
+    ids[:, -1] = tok.speech_start_id
+    mask = torch.ones(2, L0, dtype=torch.long)
+    mask[1, :4] = 0
+    ids[1, :4] = tok.pad_token_id
+    scripted = run(ids, mask, [_scripted(tok, "dddesddx"), _scripted(tok, "ddddddddx")], 40, 0)
+    # free-running: the first prompt seed whose constrained argmax emits at least two diffusion tokens (random-init weights pick
+    # <eos> or <speech_end> straight away for most prompts, which would leave the audio branch untested)
+    free = None
+    for pseed in range(64):
+        gp = torch.Generator().manual_seed(100 + pseed)
+        ids1 = torch.randint(0, V - 20, (1, 9), generator=gp)
+        ids1[:, -1] = tok.speech_start_id
+        cand = run(ids1, torch.ones_like(ids1), None, 8, 1)
+        if int((cand["sequences"][0, 9:] == tok.speech_diffusion_id).sum()) >= 2:
+            free = dict(cand, prompt_seed=100 + pseed)
+            break
+    assert free is not None, "no free-running prompt with diffusion tokens among 64 seeds"
+    # per-sample step limit (:531-539): ragged rows have different max_step_per_sample under a small max_length_times
+    maxlen = run(ids, mask, [_scripted(tok, "d"), _scripted(tok, "d")], 40, 2, max_length_times=0.5)
+    return dict(preset=preset, num_steps=steps, cfg_scale=cfg_scale, scripted=scripted, free=free, maxlen=maxlen)
+
+
+GENERATORS = dict(loop=gen_loop, voice_prompt=gen_voice_prompt, scheduler=gen_scheduler, head=gen_head, codec=gen_codec, connector=gen_connector, lm=gen_lm)
 
 
 def main():
     ns = ref_shim.load_reference()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    only = set(sys.argv[1:])                  # `python -m oracle.make_golden loop` rewrites just that fixture
     for name, fn in GENERATORS.items():
+        if only and name not in only:
+            continue
         torch.manual_seed(0)
         data = fn(ns)
         path = os.path.join(GOLDEN_DIR, f"{name}.pt")

@@ -166,3 +166,121 @@ def load_reference():
         ns.modeling_error = repr(e)
     _LOADED["ns"] = ns
     return ns
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Running the reference's OWN generate() loop (modeling_vibevoice_inference.py:326-695) in this container.
+#
+# The loop body is the reference's, unmodified.  What does not survive the installed transformers 5.5.0 is the glue it borrows
+# from `transformers.generation.GenerationMixin` -- private API of transformers 4.51.3, the version the reference pins
+# (`pyproject.toml:20`).  That third-party glue is absent here, so its published 4.51.3 behaviour is restated below, and the few
+# private-signature changes are adapted.  Nothing of the reference is copied or edited; the patches are applied to the imported
+# class object at run time, and only `oracle/make_golden.py` uses them.
+#
+#   * `_prepare_generation_config(gc, use_model_defaults, **kw)`      -> 5.5.0 dropped the positional flag (inference.py:269-276)
+#   * `_prepare_cache_for_generation(gc, kw, assistant, B, maxlen, device)` -> a DynamicCache that still exposes the
+#     `.key_cache` / `.value_cache` lists the loop edits in place (inference.py:556-561, 609-616)
+#   * `_update_model_kwargs_for_generation` (4.51.3): past <- outputs.past_key_values; attention_mask gets one column of
+#     ones; cache_position <- cache_position[-1:] + 1                                                    (inference.py:483, 513, 586)
+#   * `prepare_inputs_for_generation` (4.51.3): with a cache, keep only the unprocessed tail of input_ids
+#     (`input_ids[:, -len(cache_position):]` once cache_position has run past the ids, else `input_ids[:, cache_position]`);
+#     `inputs_embeds` are used only when they cover exactly the positions in cache_position; position_ids =
+#     cumsum(attention_mask) - 1 (1 where masked), cut to the current input length               (inference.py:466, 504, 577)
+#   * `tie_weights(**kw)`: 5.5.0 passes `recompute_mapping=`; the reference's override takes no arguments (inference.py:113-131)
+#
+# `script_tokens(...)`: BASELINE.md section 3 scripts "diffusion x F, then EOS"; generate() discards a caller-supplied
+# `logits_processor` (inference.py:375-377 overwrite it), so the script is injected where the reference itself constrains the
+# scores -- after `VibeVoiceTokenConstraintProcessor.__call__` (inference.py:53-66) the scripted id is raised to +inf.
+# ---------------------------------------------------------------------------------------------------------------------
+_SCRIPT = {}
+
+
+def script_tokens(initial_length=None, tokens=None):
+    """Install (or clear, with no arguments) a per-row token script for the next reference generate() call."""
+    _SCRIPT.clear()
+    if tokens is not None:
+        _SCRIPT.update(L0=int(initial_length), tokens=[list(t) for t in tokens])
+
+
+def install_generate_compat():
+    """Patch the imported reference inference class so that its generate() runs under transformers 5.5.0 (see above)."""
+    import torch
+    from transformers.cache_utils import DynamicCache
+
+    load_reference()
+    import importlib
+    infer_mod = importlib.import_module("vibevoice.modular.modeling_vibevoice_inference")
+    cls = infer_mod.VibeVoiceForConditionalGenerationInference
+    if getattr(cls, "_vv_compat", False):
+        return infer_mod
+
+    class LegacyListCache(DynamicCache):
+        @property
+        def key_cache(self):
+            return [layer.keys for layer in self.layers]
+
+        @property
+        def value_cache(self):
+            return [layer.values for layer in self.layers]
+
+    orig_tie = cls.tie_weights
+    cls.tie_weights = lambda self, *a, **k: orig_tie(self)
+    orig_pgc = cls._prepare_generation_config
+    cls._prepare_generation_config = lambda self, gc, *flags, **kw: orig_pgc(self, gc, **kw)
+
+    def prepare_cache(self, generation_config, model_kwargs, assistant_model, batch_size, max_cache_length, device=None):
+        model_kwargs["past_key_values"] = LegacyListCache(config=self.config.decoder_config)
+
+    def update_kwargs(self, outputs, model_kwargs, is_encoder_decoder=False, num_new_tokens=1):
+        model_kwargs["past_key_values"] = outputs.past_key_values
+        am = model_kwargs["attention_mask"]
+        model_kwargs["attention_mask"] = torch.cat([am, am.new_ones((am.shape[0], 1))], dim=-1)
+        model_kwargs["cache_position"] = model_kwargs["cache_position"][-1:] + num_new_tokens
+        return model_kwargs
+
+    def prepare_inputs(self, input_ids, past_key_values=None, attention_mask=None, inputs_embeds=None, cache_position=None, **kwargs):
+        mi = {"cache_position": cache_position}
+        if past_key_values is not None:
+            mi["past_key_values"] = past_key_values
+            if inputs_embeds is not None and input_ids.shape[1] == 0:
+                inputs_embeds = inputs_embeds[:, -cache_position.shape[0]:]
+            elif inputs_embeds is not None or cache_position[-1] >= input_ids.shape[1]:
+                input_ids = input_ids[:, -cache_position.shape[0]:]
+            elif input_ids.shape[1] != cache_position.shape[0]:
+                input_ids = input_ids[:, cache_position]
+        if inputs_embeds is not None and len(cache_position) == inputs_embeds.shape[1]:
+            mi["input_ids"], mi["inputs_embeds"] = None, inputs_embeds
+        else:
+            mi["input_ids"], mi["inputs_embeds"] = input_ids.clone(memory_format=torch.contiguous_format), None
+        position_ids = kwargs.pop("position_ids", None)
+        if attention_mask is not None and position_ids is None:
+            position_ids = attention_mask.long().cumsum(-1) - 1
+            position_ids.masked_fill_(attention_mask == 0, 1)
+        if position_ids is not None:
+            cur = mi["inputs_embeds"].shape[1] if mi["inputs_embeds"] is not None else mi["input_ids"].shape[1]
+            mi["position_ids"] = position_ids[:, -cur:].clone(memory_format=torch.contiguous_format)
+        if attention_mask is not None:
+            mi["attention_mask"] = attention_mask
+        for k, v in kwargs.items():
+            mi.setdefault(k, v)
+        mi.pop("labels", None)
+        return mi
+
+    cls._prepare_cache_for_generation = prepare_cache
+    cls._update_model_kwargs_for_generation = update_kwargs
+    cls.prepare_inputs_for_generation = prepare_inputs
+
+    proc = infer_mod.VibeVoiceTokenConstraintProcessor
+    orig_call = proc.__call__
+
+    def constrained_then_scripted(self, input_ids, scores):
+        scores = orig_call(self, input_ids, scores)
+        if _SCRIPT:
+            step = input_ids.shape[1] - _SCRIPT["L0"]
+            for b, s in enumerate(_SCRIPT["tokens"]):
+                scores[b, s[min(step, len(s) - 1)]] = float("inf")
+        return scores
+
+    proc.__call__ = constrained_then_scripted
+    cls._vv_compat = True
+    return infer_mod

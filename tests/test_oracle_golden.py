@@ -99,3 +99,29 @@ def test_voice_prompt_embeds(golden):
     got = O.voice_prompt_embeds(w, cfg, g["wavs"], g["masks"])
     assert got.shape == g["connected"].shape == (7, cfg.decoder_config.hidden_size)
     close(got, g["connected"], rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("case", ["scripted", "free", "maxlen"])
+def test_generate_loop_matches_the_reference_generate(golden, case):
+    """The whole loop (a-1 token state machine, a-2 negative CFG stream, a-8 state zeroing) against the reference's OWN
+    `generate()` (modeling_vibevoice_inference.py:326-695) run on the same synthetic checkpoint by `oracle/make_golden.py::gen_loop`
+    (loop body unmodified; transformers-4.51.3 glue restated in `oracle/ref_shim.py::install_generate_compat`).
+    Token sequences and reach_max flags: exact.  Waveforms: fp32 on both sides, 1e-5."""
+    from vibevoice_b200.synth import SynthTokenizer
+    g = golden("loop")
+    c = g[case]
+    cfg = preset_config(g["preset"])
+    tok = SynthTokenizer(cfg.decoder_config.vocab_size)
+    sd = synth_state_dict(cfg, SEED, torch.float32)
+    torch.manual_seed(c["seed"])
+    out = O.generate(sd, cfg, c["ids"], c["mask"], tok, cfg_scale=g["cfg_scale"], num_steps=g["num_steps"],
+                     max_new_tokens=c["max_new_tokens"], max_length_times=c["max_length_times"], forced_tokens=c["scripts"])
+    assert torch.equal(out.sequences, c["sequences"])
+    assert torch.equal(out.reach_max_step_sample, c["reach_max"])
+    assert len(out.speech_outputs) == len(c["audio"])
+    for a, b in zip(out.speech_outputs, c["audio"]):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert a.shape == b.shape
+            rel = float((a.double() - b.double()).norm() / b.double().norm())
+            assert rel < 1e-5, rel
