@@ -223,7 +223,9 @@ def gen_loop(ns, preset="tiny"):
       scripted  B=2, ragged left-padded prompts, scripts with a speaker turn (<end>,<start>) and per-row EOS
                 -> negative-stream restart, cache corrections for non-diffusing rows, codec-state zeroing, finished rows
       free      B=1, the constrained argmax itself drives the state machine
-      maxlen    B=2 ragged, all-diffusion scripts, max_length_times=0.5 -> per-sample step limit / reach_max_step_sample"""
+      maxlen    B=2 ragged, all-diffusion scripts, max_length_times=0.5 -> per-sample step limit / reach_max_step_sample
+      norefresh B=2 ragged, two different speaker-turn scripts, refresh_negative=False
+      quirk     B=2 ragged, ill-formed d,e,d row: pins the reference's guard off-by-one in the cache correction"""
     ref_shim.install_generate_compat()
     cfg = preset_config(preset)
     model = build_ref_model(ns, cfg)
@@ -232,15 +234,15 @@ def gen_loop(ns, preset="tiny"):
     steps, cfg_scale = 5, 1.3
     model.set_ddpm_inference_steps(steps)
 
-    def run(ids, mask, scripts, max_new_tokens, seed, max_length_times=2):
+    def run(ids, mask, scripts, max_new_tokens, seed, max_length_times=2, refresh_negative=True):
         ref_shim.script_tokens(ids.shape[1], scripts)
         torch.manual_seed(seed)
         out = model.generate(input_ids=ids.clone(), attention_mask=mask.clone(), tokenizer=tok, cfg_scale=cfg_scale,
                              max_new_tokens=max_new_tokens, speech_tensors=None, speech_masks=None,
                              speech_input_mask=torch.zeros_like(ids, dtype=torch.bool), show_progress_bar=False, verbose=False,
-                             is_prefill=False, max_length_times=max_length_times)
+                             is_prefill=False, max_length_times=max_length_times, refresh_negative=refresh_negative)
         ref_shim.script_tokens()
-        return dict(ids=ids, mask=mask, scripts=scripts, max_new_tokens=max_new_tokens, seed=seed, max_length_times=max_length_times,
+        return dict(ids=ids, mask=mask, scripts=scripts, max_new_tokens=max_new_tokens, seed=seed, max_length_times=max_length_times, refresh_negative=refresh_negative,
                     sequences=out.sequences.clone(), reach_max=out.reach_max_step_sample.clone(),
                     audio=[None if a is None else a.clone() for a in out.speech_outputs])
 
@@ -266,7 +268,13 @@ def gen_loop(ns, preset="tiny"):
     assert free is not None, "no free-running prompt with diffusion tokens among 64 seeds"
     # per-sample step limit (:531-539): ragged rows have different max_step_per_sample under a small max_length_times
     maxlen = run(ids, mask, [_scripted(tok, "d"), _scripted(tok, "d")], 40, 2, max_length_times=0.5)
-    return dict(preset=preset, num_steps=steps, cfg_scale=cfg_scale, scripted=scripted, free=free, maxlen=maxlen)
+    # refresh_negative=False (:503-517): negative stream forwarded every step, never restarted, batch-coupled corrections
+    norefresh = run(ids, mask, [_scripted(tok, "dddesddx"), _scripted(tok, "desdddddx")], 40, 3, refresh_negative=False)
+    # ill-formed turn (<speech_end> followed directly by diffusion) while the other row diffuses: the off-by-one guard of the
+    # correction block (:603 vs :613) hides slot correct_cnt instead of the newest entry (see vv_oracle.NegativeStream)
+    quirk = run(ids, mask, [_scripted(tok, "dedddx"), _scripted(tok, "ddddddx")], 40, 4)
+    return dict(preset=preset, num_steps=steps, cfg_scale=cfg_scale, scripted=scripted, free=free, maxlen=maxlen, norefresh=norefresh,
+                quirk=quirk)
 
 
 GENERATORS = dict(loop=gen_loop, voice_prompt=gen_voice_prompt, scheduler=gen_scheduler, head=gen_head, codec=gen_codec, connector=gen_connector, lm=gen_lm)

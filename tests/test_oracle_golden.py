@@ -101,7 +101,7 @@ def test_voice_prompt_embeds(golden):
     close(got, g["connected"], rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("case", ["scripted", "free", "maxlen"])
+@pytest.mark.parametrize("case", ["scripted", "free", "maxlen", "norefresh", "quirk"])
 def test_generate_loop_matches_the_reference_generate(golden, case):
     """The whole loop (a-1 token state machine, a-2 negative CFG stream, a-8 state zeroing) against the reference's OWN
     `generate()` (modeling_vibevoice_inference.py:326-695) run on the same synthetic checkpoint by `oracle/make_golden.py::gen_loop`
@@ -115,7 +115,8 @@ def test_generate_loop_matches_the_reference_generate(golden, case):
     sd = synth_state_dict(cfg, SEED, torch.float32)
     torch.manual_seed(c["seed"])
     out = O.generate(sd, cfg, c["ids"], c["mask"], tok, cfg_scale=g["cfg_scale"], num_steps=g["num_steps"],
-                     max_new_tokens=c["max_new_tokens"], max_length_times=c["max_length_times"], forced_tokens=c["scripts"])
+                     max_new_tokens=c["max_new_tokens"], max_length_times=c["max_length_times"], forced_tokens=c["scripts"],
+                     refresh_negative=c["refresh_negative"])
     assert torch.equal(out.sequences, c["sequences"])
     assert torch.equal(out.reach_max_step_sample, c["reach_max"])
     assert len(out.speech_outputs) == len(c["audio"])
@@ -125,3 +126,30 @@ def test_generate_loop_matches_the_reference_generate(golden, case):
             assert a.shape == b.shape
             rel = float((a.double() - b.double()).norm() / b.double().norm())
             assert rel < 1e-5, rel
+
+
+def test_logical_negative_bookkeeping_is_the_reference_on_well_formed_sequences(golden):
+    """The CUDA path keeps the negative stream by the rule the reference's mask/cache shifting implements -- "a row that is not in
+    diffusion mode does not keep its new KV entry" (`vv_kv_commit` advance 0).  That rule (oracle `negative_bookkeeping="logical"`)
+    is bit-identical to the reference-faithful bookkeeping on well-formed sequences, and differs on the one ill-formed pattern
+    where the reference's two guards disagree (:603 vs :613) -- a stated deviation of the product path."""
+    from vibevoice_b200.synth import SynthTokenizer
+    g = golden("loop")
+    cfg = preset_config(g["preset"])
+    tok = SynthTokenizer(cfg.decoder_config.vocab_size)
+    sd = synth_state_dict(cfg, SEED, torch.float32)
+
+    def run(c, mode):
+        torch.manual_seed(c["seed"])
+        return O.generate(sd, cfg, c["ids"], c["mask"], tok, cfg_scale=g["cfg_scale"], num_steps=g["num_steps"],
+                          max_new_tokens=c["max_new_tokens"], max_length_times=c["max_length_times"], forced_tokens=c["scripts"],
+                          negative_bookkeeping=mode)
+    for case in ("scripted", "maxlen"):
+        a, b = run(g[case], "reference"), run(g[case], "logical")
+        assert torch.equal(a.sequences, b.sequences)
+        for x, y in zip(a.speech_outputs, b.speech_outputs):
+            assert torch.equal(x, y)
+    a, b = run(g["quirk"], "reference"), run(g["quirk"], "logical")
+    rel = float((a.speech_outputs[0] - b.speech_outputs[0]).norm() / a.speech_outputs[0].norm())
+    assert rel > 1e-3                                    # the d,e,d row hears a different negative context ...
+    assert torch.equal(a.speech_outputs[1], b.speech_outputs[1])      # ... the well-formed row does not
