@@ -225,7 +225,8 @@ def gen_loop(ns, preset="tiny"):
       free      B=1, the constrained argmax itself drives the state machine
       maxlen    B=2 ragged, all-diffusion scripts, max_length_times=0.5 -> per-sample step limit / reach_max_step_sample
       norefresh B=2 ragged, two different speaker-turn scripts, refresh_negative=False
-      quirk     B=2 ragged, ill-formed d,e,d row: pins the reference's guard off-by-one in the cache correction"""
+      quirk     B=2 ragged, ill-formed d,e,d row: pins the reference's guard off-by-one in the cache correction
+      voice     B=2 ragged, `is_prefill=True` with two voice prompts (acoustic encoder + Gaussian sample + connector, :149-163, 216-224)"""
     ref_shim.install_generate_compat()
     cfg = preset_config(preset)
     model = build_ref_model(ns, cfg)
@@ -273,8 +274,29 @@ def gen_loop(ns, preset="tiny"):
     # ill-formed turn (<speech_end> followed directly by diffusion) while the other row diffuses: the off-by-one guard of the
     # correction block (:603 vs :613) hides slot correct_cnt instead of the newest entry (see vv_oracle.NegativeStream)
     quirk = run(ids, mask, [_scripted(tok, "dedddx"), _scripted(tok, "ddddddx")], 40, 4)
+    # voice-prompt prefill (a-9) through generate(): `is_prefill=True`, two voices of different length scattered into the prompts
+    gv = torch.Generator().manual_seed(51)
+    wavs = torch.zeros(2, 3200 * 3 + 100)
+    wavs[0] = torch.randn(wavs.shape[1], generator=gv) * 0.05
+    wavs[1, :3200 * 2 + 7] = torch.randn(3200 * 2 + 7, generator=gv) * 0.05
+    vmasks = torch.zeros(2, 4, dtype=torch.bool)
+    vmasks[0, :4] = True
+    vmasks[1, :3] = True
+    sim = torch.zeros(2, L0, dtype=torch.bool)
+    sim[0, 3:7] = True                                             # 4 frames of voice 0 inside row 0
+    sim[1, 6:9] = True                                             # 3 frames of voice 1 inside row 1 (after its 4 pad slots)
+    ref_shim.script_tokens(L0, [_scripted(tok, "dddx"), _scripted(tok, "ddx")])
+    torch.manual_seed(5)
+    out = model.generate(input_ids=ids.clone(), attention_mask=mask.clone(), tokenizer=tok, cfg_scale=cfg_scale, max_new_tokens=40,
+                         speech_tensors=wavs.clone(), speech_masks=vmasks.clone(), speech_input_mask=sim.clone(),
+                         show_progress_bar=False, verbose=False, is_prefill=True)
+    ref_shim.script_tokens()
+    voice = dict(ids=ids, mask=mask, scripts=[_scripted(tok, "dddx"), _scripted(tok, "ddx")], max_new_tokens=40, seed=5,
+                 max_length_times=2, refresh_negative=True, wavs=wavs, voice_masks=vmasks, speech_input_mask=sim,
+                 sequences=out.sequences.clone(), reach_max=out.reach_max_step_sample.clone(),
+                 audio=[None if a is None else a.clone() for a in out.speech_outputs])
     return dict(preset=preset, num_steps=steps, cfg_scale=cfg_scale, scripted=scripted, free=free, maxlen=maxlen, norefresh=norefresh,
-                quirk=quirk)
+                quirk=quirk, voice=voice)
 
 
 GENERATORS = dict(loop=gen_loop, voice_prompt=gen_voice_prompt, scheduler=gen_scheduler, head=gen_head, codec=gen_codec, connector=gen_connector, lm=gen_lm)

@@ -101,7 +101,7 @@ def test_voice_prompt_embeds(golden):
     close(got, g["connected"], rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("case", ["scripted", "free", "maxlen", "norefresh", "quirk"])
+@pytest.mark.parametrize("case", ["scripted", "free", "maxlen", "norefresh", "quirk", "voice"])
 def test_generate_loop_matches_the_reference_generate(golden, case):
     """The whole loop (a-1 token state machine, a-2 negative CFG stream, a-8 state zeroing) against the reference's OWN
     `generate()` (modeling_vibevoice_inference.py:326-695) run on the same synthetic checkpoint by `oracle/make_golden.py::gen_loop`
@@ -114,9 +114,17 @@ def test_generate_loop_matches_the_reference_generate(golden, case):
     tok = SynthTokenizer(cfg.decoder_config.vocab_size)
     sd = synth_state_dict(cfg, SEED, torch.float32)
     torch.manual_seed(c["seed"])
+    speech_embeds = None
+    if "wavs" in c:                     # a-9: the prefill draws its Gaussian sample first, from the same CPU stream as the frame noise
+        connected = O.voice_prompt_embeds(sd, cfg, c["wavs"], c["voice_masks"])
+        speech_embeds, o = [], 0
+        for b in range(c["ids"].shape[0]):
+            m = c["speech_input_mask"][b][c["mask"][b].bool()]
+            speech_embeds.append((m, connected[o:o + int(m.sum())]))
+            o += int(m.sum())
     out = O.generate(sd, cfg, c["ids"], c["mask"], tok, cfg_scale=g["cfg_scale"], num_steps=g["num_steps"],
                      max_new_tokens=c["max_new_tokens"], max_length_times=c["max_length_times"], forced_tokens=c["scripts"],
-                     refresh_negative=c["refresh_negative"])
+                     refresh_negative=c["refresh_negative"], speech_embeds=speech_embeds)
     assert torch.equal(out.sequences, c["sequences"])
     assert torch.equal(out.reach_max_step_sample, c["reach_max"])
     assert len(out.speech_outputs) == len(c["audio"])
