@@ -226,6 +226,7 @@ def gen_loop(ns, preset="tiny"):
       maxlen    B=2 ragged, all-diffusion scripts, max_length_times=0.5 -> per-sample step limit / reach_max_step_sample
       norefresh B=2 ragged, two different speaker-turn scripts, refresh_negative=False
       quirk     B=2 ragged, ill-formed d,e,d row: pins the reference's guard off-by-one in the cache correction
+      sampled   B=2 ragged, do_sample=True
       voice     B=2 ragged, `is_prefill=True` with two voice prompts (acoustic encoder + Gaussian sample + connector, :149-163, 216-224)"""
     ref_shim.install_generate_compat()
     cfg = preset_config(preset)
@@ -235,15 +236,16 @@ def gen_loop(ns, preset="tiny"):
     steps, cfg_scale = 5, 1.3
     model.set_ddpm_inference_steps(steps)
 
-    def run(ids, mask, scripts, max_new_tokens, seed, max_length_times=2, refresh_negative=True):
+    def run(ids, mask, scripts, max_new_tokens, seed, max_length_times=2, refresh_negative=True, do_sample=False):
         ref_shim.script_tokens(ids.shape[1], scripts)
         torch.manual_seed(seed)
         out = model.generate(input_ids=ids.clone(), attention_mask=mask.clone(), tokenizer=tok, cfg_scale=cfg_scale,
                              max_new_tokens=max_new_tokens, speech_tensors=None, speech_masks=None,
                              speech_input_mask=torch.zeros_like(ids, dtype=torch.bool), show_progress_bar=False, verbose=False,
-                             is_prefill=False, max_length_times=max_length_times, refresh_negative=refresh_negative)
+                             is_prefill=False, max_length_times=max_length_times, refresh_negative=refresh_negative,
+                             generation_config={"do_sample": True, "top_k": 0} if do_sample else None)
         ref_shim.script_tokens()
-        return dict(ids=ids, mask=mask, scripts=scripts, max_new_tokens=max_new_tokens, seed=seed, max_length_times=max_length_times, refresh_negative=refresh_negative,
+        return dict(ids=ids, mask=mask, scripts=scripts, max_new_tokens=max_new_tokens, seed=seed, max_length_times=max_length_times, refresh_negative=refresh_negative, do_sample=do_sample,
                     sequences=out.sequences.clone(), reach_max=out.reach_max_step_sample.clone(),
                     audio=[None if a is None else a.clone() for a in out.speech_outputs])
 
@@ -274,6 +276,10 @@ def gen_loop(ns, preset="tiny"):
     # ill-formed turn (<speech_end> followed directly by diffusion) while the other row diffuses: the off-by-one guard of the
     # correction block (:603 vs :613) hides slot correct_cnt instead of the newest entry (see vv_oracle.NegativeStream)
     quirk = run(ids, mask, [_scripted(tok, "dedddx"), _scripted(tok, "ddddddx")], 40, 4)
+    # do_sample=True (:493-496): multinomial over the constrained scores on the global CPU generator, interleaved with the noise draws.
+    # top_k=0: HF's default top_k=50 warper runs BEFORE the constraint processor and, with random-init weights, leaves none of the
+    # valid ids finite (softmax of all -inf -> NaN inside the reference); temperature / top_p stay at their neutral defaults.
+    sampled = run(ids, mask, None, 10, 6, do_sample=True)
     # voice-prompt prefill (a-9) through generate(): `is_prefill=True`, two voices of different length scattered into the prompts
     gv = torch.Generator().manual_seed(51)
     wavs = torch.zeros(2, 3200 * 3 + 100)
@@ -292,11 +298,11 @@ def gen_loop(ns, preset="tiny"):
                          show_progress_bar=False, verbose=False, is_prefill=True)
     ref_shim.script_tokens()
     voice = dict(ids=ids, mask=mask, scripts=[_scripted(tok, "dddx"), _scripted(tok, "ddx")], max_new_tokens=40, seed=5,
-                 max_length_times=2, refresh_negative=True, wavs=wavs, voice_masks=vmasks, speech_input_mask=sim,
+                 max_length_times=2, refresh_negative=True, do_sample=False, wavs=wavs, voice_masks=vmasks, speech_input_mask=sim,
                  sequences=out.sequences.clone(), reach_max=out.reach_max_step_sample.clone(),
                  audio=[None if a is None else a.clone() for a in out.speech_outputs])
     return dict(preset=preset, num_steps=steps, cfg_scale=cfg_scale, scripted=scripted, free=free, maxlen=maxlen, norefresh=norefresh,
-                quirk=quirk, voice=voice)
+                quirk=quirk, voice=voice, sampled=sampled)
 
 
 GENERATORS = dict(loop=gen_loop, voice_prompt=gen_voice_prompt, scheduler=gen_scheduler, head=gen_head, codec=gen_codec, connector=gen_connector, lm=gen_lm)

@@ -224,6 +224,15 @@ class VibeVoiceForConditionalGenerationInference:
         sample_gen = kwargs.get("sample_generator", None)          # torch.Generator for the token draw; never the noise RNG
         if do_sample and sample_gen is None:
             sample_gen = torch.Generator().manual_seed(torch.initial_seed())
+        temperature = 1.0
+        if do_sample:
+            gc = dict(generation_config)
+            temperature = float(gc.get("temperature", 1.0) or 1.0)      # scaling commutes with the -inf constraint: exact
+            if gc.get("top_k") not in (None, 0) or float(gc.get("top_p", 1.0) or 1.0) < 1.0:
+                import warnings
+                warnings.warn("top_k / top_p act on the full-vocabulary ranking before the token constraint in the reference "
+                              "(HF warpers, modeling_vibevoice_inference.py:310-319); this path never materialises full-vocab logits "
+                              "and samples from the softmax over the constrained ids only (= top_k 0, top_p 1)")
         if not kwargs.get("refresh_negative", True):
             raise NotImplementedError("refresh_negative=False is a 'next' row (SURVEY 8f-3)")
         use_voice = bool(is_prefill and speech_tensors is not None)
@@ -342,7 +351,7 @@ class VibeVoiceForConditionalGenerationInference:
             toks_dev, logits_valid = eng.read_tokens()
             next_tokens = toks_dev.astype(np.int64).copy()
             if do_sample:
-                next_tokens[:b] = sample_valid_tokens(logits_valid[:b], eng.valid_ids, sample_gen)     # :493-496
+                next_tokens[:b] = sample_valid_tokens(logits_valid[:b] / temperature, eng.valid_ids, sample_gen)     # :493-496
             if forced is not None:
                 for r in range(b):
                     next_tokens[r] = forced.token(r, step)
