@@ -1,0 +1,145 @@
+"""TEST INFRASTRUCTURE: a CPU stand-in for `vibevoice_b200.engine.Engine` whose arithmetic is the oracle's.
+
+Purpose: run the PRODUCT's host-side state machine (`vibevoice_b200/modeling.py::generate` -- token bookkeeping, which KV entries
+each stream keeps, when codec state is zeroed, how noise rows are packed, what is streamed out) on a machine without a GPU and hold
+it to the fixtures produced by the reference's own `generate()` (`tests/golden/loop.pt`).  The CUDA library is not involved and
+nothing here is importable from the product; the GPU tests hold the real engine to the same oracle.
+
+The engine contract mirrored here (include/vibevoice_b200.h):
+  * 2B rows: 0..B-1 positive streams, B..2B-1 negative (CFG) streams; `lm_decode` consumes `embeds[2B,H]`, appends one K/V entry per
+    row SPECULATIVELY at kv_len, writes `hidden[2B,H]`, and the constrained logits / argmax for rows 0..B-1;
+  * `kv_commit(advance[2B])` keeps (1) or discards (0) the speculative entry; `kv_set_len(seq, n)` truncates;
+  * `frame_tail(cfg)`: for active rows  hidden(pos,neg) + noise -> latent -> audio frame -> semantic feature -> connectors ->
+    embeds[b] and embeds[B+b]; inactive rows keep their token embeddings (select_embeds_kernel).
+"""
+from __future__ import annotations
+
+from typing import List
+
+import numpy as np
+import torch
+
+from oracle import vv_oracle as O
+
+
+class FakeEngine:
+    def __init__(self, config, valid_ids, max_batch: int, weights):
+        self.config, self.w = config, weights
+        self.B = max_batch
+        self.device = torch.device("cpu")
+        self.stream = None                                   # torch.cuda.stream(None) is a no-op context
+        self.valid_ids = sorted(set(int(v) for v in valid_ids))
+        self.finalized = True
+        self.kv_pages = 0
+        self.n_steps = 0
+        dc = config.decoder_config
+        H, B = dc.hidden_size, max_batch
+        self.embeds = torch.zeros(2 * B, H)
+        self.hidden = torch.zeros(2 * B, H)
+        self.logits = torch.zeros(B, len(self.valid_ids))
+        self.tokens = torch.zeros(B, dtype=torch.int32)
+        self.noise = torch.zeros(B, 64)
+        self.active = torch.zeros(B, dtype=torch.int32)
+        self.latent = torch.zeros(B, 64)
+        self.audio = torch.zeros(B, 3200)
+        self.kv: List[O.KVCache] = [O.KVCache(dc.num_hidden_layers) for _ in range(2 * B)]
+        self.spec = [False] * (2 * B)                        # a speculative (uncommitted) entry sits at the end of the stream
+        self.a_state, self.s_state = O.StreamState(B), O.StreamState(B)
+        self.embed_w = weights["model.language_model.embed_tokens.weight"].float()
+        self.head_rows = O.lm_head_weight(weights, dc)[self.valid_ids].float()
+        self.calls = {"lm_decode": 0, "frame_tail": 0, "kv_commit": 0}
+
+    # ---- KV ----
+    def kv_init(self, total_tokens: int):
+        self.kv_pages = (total_tokens + 63) // 64 + 4 * self.B
+
+    def kv_len(self, seq: int) -> int:
+        return len(self.kv[seq]) - (1 if self.spec[seq] else 0)
+
+    def kv_set_len(self, seq: int, n: int):
+        self.kv[seq].truncate(n)
+        self.spec[seq] = False
+
+    def kv_commit(self, advance):
+        assert len(advance) == 2 * self.B
+        self.calls["kv_commit"] += 1
+        for s, a in enumerate(advance):
+            if self.spec[s] and not a:
+                self.kv[s].truncate(len(self.kv[s]) - 1)
+            self.spec[s] = False
+
+    # ---- programs ----
+    def set_diffusion_steps(self, n_steps: int):
+        self.n_steps = int(n_steps)
+
+    def embed_tokens(self, tokens, out: torch.Tensor):
+        out[:len(tokens)] = self.embed_w[torch.as_tensor(list(tokens), dtype=torch.long)]
+
+    def lm_decode(self):
+        self.calls["lm_decode"] += 1
+        dc = self.config.decoder_config
+        for s in range(2 * self.B):
+            if self.spec[s]:                                 # a second decode without a commit overwrites the speculative slot
+                self.kv[s].truncate(len(self.kv[s]) - 1)
+            self.hidden[s] = O.qwen2_forward(self.w, dc, self.embeds[s][None].clone(), self.kv[s], len(self.kv[s]))[-1]
+            self.spec[s] = True
+        self.lm_head(self.hidden)
+
+    def lm_head(self, hidden: torch.Tensor):
+        lg = hidden[:self.B] @ self.head_rows.T
+        self.logits.copy_(lg)
+        self.tokens.copy_(torch.tensor(self.valid_ids)[torch.argmax(lg, dim=-1)].to(torch.int32))   # lowest id among ties
+
+    def read_tokens(self):
+        return self.tokens.numpy().copy(), self.logits.numpy().copy()
+
+    def upload_frame_inputs(self, noise_rows: torch.Tensor, active_rows):
+        self.noise.zero_()
+        self.active.zero_()
+        for i, b in enumerate(active_rows):
+            self.noise[b] = noise_rows[i]
+            self.active[b] = 1
+
+    def frame_tail(self, cfg_scale: float):
+        self.calls["frame_tail"] += 1
+        cfg, w, B = self.config, self.w, self.B
+        hc = cfg.diffusion_head_config
+        rows = self.active.nonzero().flatten()
+        scale, bias = float(w["model.speech_scaling_factor"]), float(w["model.speech_bias_factor"])
+        n = rows.numel()
+        noise = torch.cat([self.noise[rows], torch.zeros(n, 64)])            # the sampler uses rows [:n] of the 2n draw (:701-704)
+        lat = O.sample_speech_tokens(w, self.hidden[rows], self.hidden[B + rows], cfg_scale, self.n_steps, noise, hc.head_layers, hc.rms_norm_eps)
+        audio = O.decoder_frame(w, cfg.acoustic_tokenizer_config, (lat / scale - bias)[:, None, :], self.a_state, rows)
+        sem = O.encoder_frame(w, cfg.semantic_tokenizer_config, audio, self.s_state, rows)
+        emb = O.connector(w, "model.acoustic_connector", lat) + O.connector(w, "model.semantic_connector", sem[:, 0])
+        self.latent[rows] = lat
+        self.audio[rows] = audio[:, 0]
+        self.embeds[rows] = emb
+        self.embeds[B:] = self.embeds[:B]                                     # select_embeds_kernel: negative rows see the same input
+
+    def codec_state_zero(self, rows):
+        if len(rows):
+            r = torch.as_tensor(list(rows), dtype=torch.long)
+            self.a_state.set_to_zero(r)
+            self.s_state.set_to_zero(r)
+
+    def codec_state_reset(self):
+        self.a_state, self.s_state = O.StreamState(self.B), O.StreamState(self.B)
+
+    def launch_count(self) -> int:
+        return 0
+
+    def sync(self):
+        pass
+
+    def close(self):
+        pass
+
+
+def make_model(cfg, tok, weights, max_batch: int):
+    """The product's `VibeVoiceForConditionalGenerationInference` with a FakeEngine plugged in (no CUDA library is touched)."""
+    from vibevoice_b200.modeling import VibeVoiceForConditionalGenerationInference
+    m = VibeVoiceForConditionalGenerationInference(cfg, tok, max_batch=max_batch)
+    m.engine = FakeEngine(cfg, m._valid_ids(tok), max_batch, weights)
+    m._scale, m._bias = float(weights["model.speech_scaling_factor"]), float(weights["model.speech_bias_factor"])
+    return m

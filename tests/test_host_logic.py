@@ -203,3 +203,40 @@ def test_lora_assets_fold_into_base_weights(tmp_path):
     with pytest.raises(FileNotFoundError):
         L.collect_overrides(tmp_path / "nope" / "lora")
     from vibevoice.modular.lora_loading import load_lora_assets  # noqa: F401  (drop-in import path)
+
+
+@pytest.mark.parametrize("case", ["scripted", "free", "maxlen", "quirk"])
+def test_product_generate_host_logic_against_reference_generate_fixture(golden, case):
+    """`modeling.generate` (the product's host state machine, a-1/a-2/a-8: token bookkeeping, which KV entries the negative stream
+    keeps, restart on <speech_start>, codec-state zeroing, per-row finishing, noise-row packing) driven through a CPU stand-in of the
+    engine (`tests/fake_engine.py`, oracle arithmetic) and held to what the REFERENCE's own generate() produced on the same
+    checkpoint (`tests/golden/loop.pt`).  Sequences and flags exact; audio 1e-5."""
+    from fake_engine import make_model
+    from vibevoice_b200.configuration import preset_config
+    from vibevoice_b200.modeling import ForcedTokenScript
+    from vibevoice_b200.synth import SynthTokenizer, synth_state_dict
+    g = golden("loop")
+    c = g[case]
+    cfg = preset_config(g["preset"])
+    tok = SynthTokenizer(cfg.decoder_config.vocab_size)
+    sd = synth_state_dict(cfg, 1234, torch.float32)
+    model = make_model(cfg, tok, sd, max_batch=c["ids"].shape[0])
+    model.set_ddpm_inference_steps(g["num_steps"])
+    torch.manual_seed(c["seed"])
+    out = model.generate(input_ids=c["ids"], attention_mask=c["mask"], tokenizer=tok, cfg_scale=g["cfg_scale"], is_prefill=False,
+                         max_new_tokens=c["max_new_tokens"], max_length_times=c["max_length_times"], show_progress_bar=False,
+                         logits_processor=[ForcedTokenScript(c["scripts"])] if c["scripts"] else None)
+    assert torch.equal(out.sequences, c["sequences"])
+    assert torch.equal(out.reach_max_step_sample, c["reach_max"])
+    for r, (a, b) in enumerate(zip(out.speech_outputs, c["audio"])):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert a.shape == b.shape
+            rel = float((a.double() - b.double()).norm() / b.double().norm())
+            if case == "quirk" and r == 0:
+                # stated deviation (DESIGN section 4): the ill-formed d,e,d row keeps a different negative context in the reference
+                # (guard off-by-one at :603/:613); the product drops the newest entry.  Same tokens, same length, different audio.
+                assert 1e-3 < rel < 0.2, rel
+            else:
+                assert rel < 1e-5, rel
+    assert model.engine.calls["frame_tail"] > 0 or case == "free" and all(a is None for a in c["audio"])
