@@ -225,6 +225,7 @@ def gen_loop(ns, preset="tiny"):
       free      B=1, the constrained argmax itself drives the state machine
       maxlen    B=2 ragged, all-diffusion scripts, max_length_times=0.5 -> per-sample step limit / reach_max_step_sample
       norefresh B=2 ragged, two different speaker-turn scripts, refresh_negative=False
+      norefresh1 B=1, two speaker turns, refresh_negative=False (no cache correction can occur: the product path supports this case)
       quirk     B=2 ragged, ill-formed d,e,d row: pins the reference's guard off-by-one in the cache correction
       sampled   B=2 ragged, do_sample=True
       voice     B=2 ragged, `is_prefill=True` with two voice prompts (acoustic encoder + Gaussian sample + connector, :149-163, 216-224)"""
@@ -273,6 +274,10 @@ def gen_loop(ns, preset="tiny"):
     maxlen = run(ids, mask, [_scripted(tok, "d"), _scripted(tok, "d")], 40, 2, max_length_times=0.5)
     # refresh_negative=False (:503-517): negative stream forwarded every step, never restarted, batch-coupled corrections
     norefresh = run(ids, mask, [_scripted(tok, "dddesddx"), _scripted(tok, "desdddddx")], 40, 3, refresh_negative=False)
+    g1 = torch.Generator().manual_seed(31)
+    ids_one = torch.randint(0, V - 20, (1, 10), generator=g1)
+    ids_one[:, -1] = tok.speech_start_id
+    norefresh1 = run(ids_one, torch.ones_like(ids_one), [_scripted(tok, "ddesdddesdx")], 40, 7, refresh_negative=False)
     # ill-formed turn (<speech_end> followed directly by diffusion) while the other row diffuses: the off-by-one guard of the
     # correction block (:603 vs :613) hides slot correct_cnt instead of the newest entry (see vv_oracle.NegativeStream)
     quirk = run(ids, mask, [_scripted(tok, "dedddx"), _scripted(tok, "ddddddx")], 40, 4)
@@ -302,7 +307,7 @@ def gen_loop(ns, preset="tiny"):
                  sequences=out.sequences.clone(), reach_max=out.reach_max_step_sample.clone(),
                  audio=[None if a is None else a.clone() for a in out.speech_outputs])
     return dict(preset=preset, num_steps=steps, cfg_scale=cfg_scale, scripted=scripted, free=free, maxlen=maxlen, norefresh=norefresh,
-                quirk=quirk, voice=voice, sampled=sampled)
+                quirk=quirk, voice=voice, sampled=sampled, norefresh1=norefresh1)
 
 
 GENERATORS = dict(loop=gen_loop, voice_prompt=gen_voice_prompt, scheduler=gen_scheduler, head=gen_head, codec=gen_codec, connector=gen_connector, lm=gen_lm)

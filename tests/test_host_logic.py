@@ -205,7 +205,7 @@ def test_lora_assets_fold_into_base_weights(tmp_path):
     from vibevoice.modular.lora_loading import load_lora_assets  # noqa: F401  (drop-in import path)
 
 
-@pytest.mark.parametrize("case", ["scripted", "free", "maxlen", "quirk"])
+@pytest.mark.parametrize("case", ["scripted", "free", "maxlen", "quirk", "norefresh1"])
 def test_product_generate_host_logic_against_reference_generate_fixture(golden, case):
     """`modeling.generate` (the product's host state machine, a-1/a-2/a-8: token bookkeeping, which KV entries the negative stream
     keeps, restart on <speech_start>, codec-state zeroing, per-row finishing, noise-row packing) driven through a CPU stand-in of the
@@ -225,7 +225,8 @@ def test_product_generate_host_logic_against_reference_generate_fixture(golden, 
     torch.manual_seed(c["seed"])
     out = model.generate(input_ids=c["ids"], attention_mask=c["mask"], tokenizer=tok, cfg_scale=g["cfg_scale"], is_prefill=False,
                          max_new_tokens=c["max_new_tokens"], max_length_times=c["max_length_times"], show_progress_bar=False,
-                         logits_processor=[ForcedTokenScript(c["scripts"])] if c["scripts"] else None)
+                         logits_processor=[ForcedTokenScript(c["scripts"])] if c["scripts"] else None,
+                         refresh_negative=c["refresh_negative"])
     assert torch.equal(out.sequences, c["sequences"])
     assert torch.equal(out.reach_max_step_sample, c["reach_max"])
     for r, (a, b) in enumerate(zip(out.speech_outputs, c["audio"])):

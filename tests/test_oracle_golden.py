@@ -101,7 +101,7 @@ def test_voice_prompt_embeds(golden):
     close(got, g["connected"], rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("case", ["scripted", "free", "maxlen", "norefresh", "quirk", "voice", "sampled"])
+@pytest.mark.parametrize("case", ["scripted", "free", "maxlen", "norefresh", "quirk", "voice", "sampled", "norefresh1"])
 def test_generate_loop_matches_the_reference_generate(golden, case):
     """The whole loop (a-1 token state machine, a-2 negative CFG stream, a-8 state zeroing) against the reference's OWN
     `generate()` (modeling_vibevoice_inference.py:326-695) run on the same synthetic checkpoint by `oracle/make_golden.py::gen_loop`

@@ -215,7 +215,7 @@ class VibeVoiceForConditionalGenerationInference:
                  negative_prompt_ids=None, negative_prompt_attention_mask=None, speech_tensors=None, speech_masks=None,
                  speech_input_mask=None, is_prefill: bool = True, return_speech: bool = True, cfg_scale: float = 1.0,
                  stop_check_fn: Optional[Callable[[], bool]] = None, tqdm_class=None, **kwargs) -> VibeVoiceGenerationOutput:
-        """`modeling_vibevoice_inference.py:326-695` (greedy; `refresh_negative=True`)."""
+        """`modeling_vibevoice_inference.py:326-695`."""
         tokenizer = kwargs.pop("tokenizer", None) or self._tok
         kwargs.pop("parsed_scripts", None); kwargs.pop("all_speakers_list", None)
         max_length_times = kwargs.pop("max_length_times", 2)
@@ -233,8 +233,7 @@ class VibeVoiceForConditionalGenerationInference:
                 warnings.warn("top_k / top_p act on the full-vocabulary ranking before the token constraint in the reference "
                               "(HF warpers, modeling_vibevoice_inference.py:310-319); this path never materialises full-vocab logits "
                               "and samples from the softmax over the constrained ids only (= top_k 0, top_p 1)")
-        if not kwargs.get("refresh_negative", True):
-            raise NotImplementedError("refresh_negative=False is a 'next' row (SURVEY 8f-3)")
+        refresh_negative = bool(kwargs.get("refresh_negative", True))
         use_voice = bool(is_prefill and speech_tensors is not None)
         if use_voice and (self._voice is None or self._prefill is None):
             raise N.VVError("voice-prompt prefill needs torch_prefill=True and the acoustic-encoder weights (a-9 runs on PyTorch library kernels)")
@@ -259,6 +258,13 @@ class VibeVoiceForConditionalGenerationInference:
         B = eng.B
         if b > B:
             raise ValueError("batch %d exceeds the engine's max_batch %d" % (b, B))
+        if not refresh_negative and b > 1:
+            # :503-517 + :590-624: with refresh_negative=False the reference forwards the negative stream on every step and undoes the
+            # step of non-diffusing rows only when ANOTHER row diffuses, through a cache shift whose guard keeps the newest entry and
+            # hides an older one in the common kv_len == correct_cnt + 2 case (oracle: NegativeStream).  A paged KV stream can drop its
+            # newest entry but not hide an older one, so only the single-prompt case -- where no correction ever happens -- is exact.
+            raise NotImplementedError("refresh_negative=False is supported for one prompt per call (the reference's batched behaviour "
+                                      "depends on its cache-shift guard; see DESIGN section 4)")
         tok = tokenizer
         start_id, end_id, diff_id, eos_id = tok.speech_start_id, tok.speech_end_id, tok.speech_diffusion_id, tok.eos_token_id
 
@@ -380,9 +386,12 @@ class VibeVoiceForConditionalGenerationInference:
             diff_rows = np.nonzero(diff_mask)[0]
             # KV bookkeeping: positive rows always keep their entry; negative rows only when the token is a diffusion token
             adv_pos = pending_adv_pos if step == 0 else [1] * b + [0] * (B - b)
-            eng.kv_commit(list(adv_pos) + [1 if diff_mask[r] else 0 for r in range(B)])
-            for r in start_rows.tolist():
-                eng.kv_set_len(B + r, 0)                                                      # negative stream restarts at [<speech_start>]
+            if refresh_negative:
+                eng.kv_commit(list(adv_pos) + [1 if diff_mask[r] else 0 for r in range(B)])
+                for r in start_rows.tolist():
+                    eng.kv_set_len(B + r, 0)                                                  # negative stream restarts at [<speech_start>]
+            else:
+                eng.kv_commit(list(adv_pos) + [1] * B)       # :503-517: every step's input stays in the negative stream, no restart
             tl = [int(t) for t in next_tokens]
             eng.embed_tokens(tl + tl, eng.embeds)                                             # :569 (negative rows see the same input, :579-581)
             if diff_rows.size:
