@@ -56,6 +56,21 @@ def gen_scheduler(ns):
             zz = s.step(vs[i], t, zz).prev_sample
             traj.append(zz.clone())
         out[n] = dict(timesteps=s.timesteps.clone(), sigmas=s.sigmas.clone(), z0=z, vs=vs, traj=torch.stack(traj))
+    # SDE variant as the Gradio demo configures it (demo/gradio_demo.py:141-146), variance noise passed explicitly
+    for n in (5, 10, 30):
+        base = ns.dpm.DPMSolverMultistepScheduler(num_train_timesteps=1000, beta_schedule="cosine", prediction_type="v_prediction")
+        s = base.from_config(base.config, algorithm_type="sde-dpmsolver++", beta_schedule="squaredcos_cap_v2")
+        s.set_timesteps(n)
+        g = torch.Generator().manual_seed(200 + n)
+        z = torch.randn(3, 64, generator=g)
+        vs = torch.randn(n, 3, 64, generator=g)
+        ns_ = torch.randn(n, 3, 64, generator=g)
+        traj = []
+        zz = z.clone()
+        for i, t in enumerate(s.timesteps):
+            zz = s.step(vs[i], t, zz, variance_noise=ns_[i]).prev_sample
+            traj.append(zz.clone())
+        out["sde%d" % n] = dict(timesteps=s.timesteps.clone(), sigmas=s.sigmas.clone(), z0=z, vs=vs, noise=ns_, traj=torch.stack(traj))
     return out
 
 

@@ -28,6 +28,20 @@ def test_dpm_tables_match_reference_scheduler(golden, n):
         close(z, g["traj"][i], rtol=0, atol=0)                             # scalar-table form is bit-exact in fp32
 
 
+@pytest.mark.parametrize("n", [5, 10, 30])
+def test_sde_dpm_tables_match_reference_scheduler(golden, n):
+    """`sde-dpmsolver++` (the Gradio demo's scheduler, demo/gradio_demo.py:141-146; dpm_solver.py:680-686, 785-793): scalar tables +
+    explicit variance noise reproduce the reference scheduler's trajectory bit for bit."""
+    g = golden("scheduler")["sde%d" % n]
+    tab = O.dpm_tables(n, algorithm_type="sde-dpmsolver++")
+    assert np.array_equal(tab.timesteps, g["timesteps"].numpy())
+    assert np.array_equal(tab.sigmas, g["sigmas"].numpy())
+    z, x0p = g["z0"].clone(), None
+    for i in range(n):
+        z, x0p = O.dpm_step(tab, i, g["vs"][i], z, x0p, noise=g["noise"][i])
+        close(z, g["traj"][i], rtol=0, atol=0)
+
+
 def test_known_timesteps():
     # SURVEY 8a-4: N=10 -> 999,899,...,100 ; N=30 -> 999,966,932,...,33
     assert O.dpm_tables(10).timesteps.tolist() == [999, 899, 799, 699, 599, 500, 400, 300, 200, 100]
