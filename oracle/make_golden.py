@@ -240,6 +240,7 @@ def gen_loop(ns, preset="tiny"):
       free      B=1, the constrained argmax itself drives the state machine
       maxlen    B=2 ragged, all-diffusion scripts, max_length_times=0.5 -> per-sample step limit / reach_max_step_sample
       norefresh B=2 ragged, two different speaker-turn scripts, refresh_negative=False
+      streamed / stopped  B=2 with the reference AudioStreamer; with `stop_check_fn` firing after three steps
       norefresh1 B=1, two speaker turns, refresh_negative=False (no cache correction can occur: the product path supports this case)
       quirk     B=2 ragged, ill-formed d,e,d row: pins the reference's guard off-by-one in the cache correction
       sampled   B=2 ragged, do_sample=True
@@ -252,16 +253,40 @@ def gen_loop(ns, preset="tiny"):
     steps, cfg_scale = 5, 1.3
     model.set_ddpm_inference_steps(steps)
 
-    def run(ids, mask, scripts, max_new_tokens, seed, max_length_times=2, refresh_negative=True, do_sample=False):
+    def run(ids, mask, scripts, max_new_tokens, seed, max_length_times=2, refresh_negative=True, do_sample=False, streamer=False,
+            stop_after_calls=None):
         ref_shim.script_tokens(ids.shape[1], scripts)
         torch.manual_seed(seed)
-        out = model.generate(input_ids=ids.clone(), attention_mask=mask.clone(), tokenizer=tok, cfg_scale=cfg_scale,
+        extra = {}
+        st = None
+        if streamer:                                 # the reference's own AudioStreamer (vibevoice/modular/streamer.py:13-92)
+            import importlib
+            st = importlib.import_module("vibevoice.modular.streamer").AudioStreamer(batch_size=ids.shape[0])
+            extra["audio_streamer"] = st
+        if stop_after_calls is not None:
+            calls = {"n": 0}
+
+            def stop_fn():
+                calls["n"] += 1
+                return calls["n"] > stop_after_calls
+            extra["stop_check_fn"] = stop_fn
+        out = model.generate(**extra, input_ids=ids.clone(), attention_mask=mask.clone(), tokenizer=tok, cfg_scale=cfg_scale,
                              max_new_tokens=max_new_tokens, speech_tensors=None, speech_masks=None,
                              speech_input_mask=torch.zeros_like(ids, dtype=torch.bool), show_progress_bar=False, verbose=False,
                              is_prefill=False, max_length_times=max_length_times, refresh_negative=refresh_negative,
                              generation_config={"do_sample": True, "top_k": 0} if do_sample else None)
         ref_shim.script_tokens()
-        return dict(ids=ids, mask=mask, scripts=scripts, max_new_tokens=max_new_tokens, seed=seed, max_length_times=max_length_times, refresh_negative=refresh_negative, do_sample=do_sample,
+        streamed = None
+        if st is not None:                           # queue contents per row, stop signal (None) included
+            streamed = []
+            for q in st.audio_queues:
+                items = []
+                while not q.empty():
+                    it = q.get()
+                    items.append(None if it is None else it.clone())
+                streamed.append(items)
+        return dict(streamed=streamed, stop_after_calls=stop_after_calls,
+                    ids=ids, mask=mask, scripts=scripts, max_new_tokens=max_new_tokens, seed=seed, max_length_times=max_length_times, refresh_negative=refresh_negative, do_sample=do_sample,
                     sequences=out.sequences.clone(), reach_max=out.reach_max_step_sample.clone(),
                     audio=[None if a is None else a.clone() for a in out.speech_outputs])
 
@@ -289,6 +314,10 @@ def gen_loop(ns, preset="tiny"):
     maxlen = run(ids, mask, [_scripted(tok, "d"), _scripted(tok, "d")], 40, 2, max_length_times=0.5)
     # refresh_negative=False (:503-517): negative stream forwarded every step, never restarted, batch-coupled corrections
     norefresh = run(ids, mask, [_scripted(tok, "dddesddx"), _scripted(tok, "desdddddx")], 40, 3, refresh_negative=False)
+    # audio_streamer hand-off (:443-447, :525-539, :653-655, :677-678: the loop ends as soon as ANY row's stream is finished) and the
+    # cooperative stop hook (:434-440)
+    streamed = run(ids, mask, [_scripted(tok, "dddesddx"), _scripted(tok, "ddddddddx")], 40, 8, streamer=True)
+    stopped = run(ids, mask, [_scripted(tok, "d"), _scripted(tok, "d")], 40, 9, streamer=True, stop_after_calls=3)
     g1 = torch.Generator().manual_seed(31)
     ids_one = torch.randint(0, V - 20, (1, 10), generator=g1)
     ids_one[:, -1] = tok.speech_start_id
@@ -322,7 +351,7 @@ def gen_loop(ns, preset="tiny"):
                  sequences=out.sequences.clone(), reach_max=out.reach_max_step_sample.clone(),
                  audio=[None if a is None else a.clone() for a in out.speech_outputs])
     return dict(preset=preset, num_steps=steps, cfg_scale=cfg_scale, scripted=scripted, free=free, maxlen=maxlen, norefresh=norefresh,
-                quirk=quirk, voice=voice, sampled=sampled, norefresh1=norefresh1)
+                quirk=quirk, voice=voice, sampled=sampled, norefresh1=norefresh1, streamed=streamed, stopped=stopped)
 
 
 GENERATORS = dict(loop=gen_loop, voice_prompt=gen_voice_prompt, scheduler=gen_scheduler, head=gen_head, codec=gen_codec, connector=gen_connector, lm=gen_lm)

@@ -241,3 +241,49 @@ def test_product_generate_host_logic_against_reference_generate_fixture(golden, 
             else:
                 assert rel < 1e-5, rel
     assert model.engine.calls["frame_tail"] > 0 or case == "free" and all(a is None for a in c["audio"])
+
+
+@pytest.mark.parametrize("case", ["streamed", "stopped"])
+def test_product_streaming_and_stop_hooks_against_reference_generate_fixture(golden, case):
+    """Boundary behaviour (b): `audio_streamer` hand-off and `stop_check_fn` through the product's generate() + AudioStreamer vs what the
+    reference's generate() + its own AudioStreamer did (fixture): same chunks in the same order in every per-row queue, the stop
+    signal where the reference put it, the loop ending as soon as any row's stream is finished (:443-447), same sequences / audio."""
+    from fake_engine import make_model
+    from vibevoice_b200.configuration import preset_config
+    from vibevoice_b200.modeling import ForcedTokenScript
+    from vibevoice_b200.streamer import AudioStreamer
+    from vibevoice_b200.synth import SynthTokenizer, synth_state_dict
+    g = golden("loop")
+    c = g[case]
+    cfg = preset_config(g["preset"])
+    tok = SynthTokenizer(cfg.decoder_config.vocab_size)
+    model = make_model(cfg, tok, synth_state_dict(cfg, 1234, torch.float32), max_batch=2)
+    model.set_ddpm_inference_steps(g["num_steps"])
+    st = AudioStreamer(batch_size=2)
+    extra = {}
+    if c["stop_after_calls"] is not None:
+        calls = {"n": 0}
+
+        def stop_fn():
+            calls["n"] += 1
+            return calls["n"] > c["stop_after_calls"]
+        extra["stop_check_fn"] = stop_fn
+    torch.manual_seed(c["seed"])
+    out = model.generate(input_ids=c["ids"], attention_mask=c["mask"], tokenizer=tok, cfg_scale=g["cfg_scale"], is_prefill=False,
+                         max_new_tokens=c["max_new_tokens"], show_progress_bar=False, audio_streamer=st,
+                         logits_processor=[ForcedTokenScript(c["scripts"])], **extra)
+    assert torch.equal(out.sequences, c["sequences"])
+    assert torch.equal(out.reach_max_step_sample, c["reach_max"])
+    for a, b in zip(out.speech_outputs, c["audio"]):
+        assert a.shape == b.shape and float((a.double() - b.double()).norm() / b.double().norm()) < 1e-5
+    for r in range(2):
+        got = []
+        while not st.audio_queues[r].empty():
+            got.append(st.audio_queues[r].get())
+        want = c["streamed"][r]
+        assert len(got) == len(want), (r, len(got), len(want))
+        for x, y in zip(got, want):
+            assert (x is None) == (y is None)                      # the stop signal sits where the reference put it
+            if x is not None:
+                assert tuple(x.shape) == tuple(y.shape)
+                assert float((x.double() - y.double()).norm() / y.double().norm()) < 1e-5
