@@ -23,7 +23,30 @@ from oracle import vv_oracle as O
 
 
 class FakeEngine:
-    def __init__(self, config, valid_ids, max_batch: int, weights):
+    def __init__(self, config, valid_ids, max_batch: int = 1, device=0, max_diffusion_steps=64, weights=None):   # Engine's signature + weights
+        if weights is None:                                  # constructed by the product code (Engine signature): weights arrive
+            self._pending, self.finalized_args = {}, None    # through load_tensor()/finalize() like the C ABI's vv_load_tensor
+            self._init_args = (config, valid_ids, max_batch)
+            self.config, self.B, self.finalized, self.kv_pages = config, max_batch, False, 0
+            self.device, self.stream = torch.device("cpu"), None
+            self.valid_ids = sorted(set(int(v) for v in valid_ids))
+            self.scheduler = None
+            return
+        self._setup(config, valid_ids, max_batch, weights)
+
+    def load_tensor(self, name: str, t: torch.Tensor) -> int:
+        self._pending[name] = t.detach().clone()
+        return 0
+
+    def finalize(self, speech_scaling_factor=None, speech_bias_factor=None):
+        w = dict(self._pending)
+        w["model.speech_scaling_factor"] = torch.tensor(float(speech_scaling_factor))
+        w["model.speech_bias_factor"] = torch.tensor(float(speech_bias_factor))
+        config, valid_ids, max_batch = self._init_args
+        self._setup(config, valid_ids, max_batch, w)
+
+    def _setup(self, config, valid_ids, max_batch: int, weights):
+        self.scheduler = None
         self.config, self.w = config, weights
         self.B = max_batch
         self.device = torch.device("cpu")
@@ -140,6 +163,6 @@ def make_model(cfg, tok, weights, max_batch: int):
     """The product's `VibeVoiceForConditionalGenerationInference` with a FakeEngine plugged in (no CUDA library is touched)."""
     from vibevoice_b200.modeling import VibeVoiceForConditionalGenerationInference
     m = VibeVoiceForConditionalGenerationInference(cfg, tok, max_batch=max_batch)
-    m.engine = FakeEngine(cfg, m._valid_ids(tok), max_batch, weights)
+    m.engine = FakeEngine(cfg, m._valid_ids(tok), max_batch, weights=weights)
     m._scale, m._bias = float(weights["model.speech_scaling_factor"]), float(weights["model.speech_bias_factor"])
     return m
