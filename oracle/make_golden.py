@@ -241,6 +241,7 @@ def gen_loop(ns, preset="tiny"):
       maxlen    B=2 ragged, all-diffusion scripts, max_length_times=0.5 -> per-sample step limit / reach_max_step_sample
       norefresh B=2 ragged, two different speaker-turn scripts, refresh_negative=False
       streamed / stopped  B=2 with the reference AudioStreamer; with `stop_check_fn` firing after three steps
+      sde       B=2 ragged scripted, scheduler replaced by sde-dpmsolver++
       norefresh1 B=1, two speaker turns, refresh_negative=False (no cache correction can occur: the product path supports this case)
       quirk     B=2 ragged, ill-formed d,e,d row: pins the reference's guard off-by-one in the cache correction
       sampled   B=2 ragged, do_sample=True
@@ -318,6 +319,15 @@ def gen_loop(ns, preset="tiny"):
     # cooperative stop hook (:434-440)
     streamed = run(ids, mask, [_scripted(tok, "dddesddx"), _scripted(tok, "ddddddddx")], 40, 8, streamer=True)
     stopped = run(ids, mask, [_scripted(tok, "d"), _scripted(tok, "d")], 40, 9, streamer=True, stop_after_calls=3)
+    # sde-dpmsolver++ as the Gradio demo installs it (demo/gradio_demo.py:141-146); on the CPU every step's variance noise comes from the
+    # global generator, interleaved with the per-frame draw
+    ode_sched = model.model.noise_scheduler
+    model.model.noise_scheduler = ode_sched.from_config(ode_sched.config, algorithm_type="sde-dpmsolver++", beta_schedule="squaredcos_cap_v2")
+    model.set_ddpm_inference_steps(steps)
+    sde = run(ids, mask, [_scripted(tok, "dddesddx"), _scripted(tok, "ddddddddx")], 40, 10)
+    sde["algorithm_type"] = "sde-dpmsolver++"
+    model.model.noise_scheduler = ode_sched
+    model.set_ddpm_inference_steps(steps)
     g1 = torch.Generator().manual_seed(31)
     ids_one = torch.randint(0, V - 20, (1, 10), generator=g1)
     ids_one[:, -1] = tok.speech_start_id
@@ -351,7 +361,7 @@ def gen_loop(ns, preset="tiny"):
                  sequences=out.sequences.clone(), reach_max=out.reach_max_step_sample.clone(),
                  audio=[None if a is None else a.clone() for a in out.speech_outputs])
     return dict(preset=preset, num_steps=steps, cfg_scale=cfg_scale, scripted=scripted, free=free, maxlen=maxlen, norefresh=norefresh,
-                quirk=quirk, voice=voice, sampled=sampled, norefresh1=norefresh1, streamed=streamed, stopped=stopped)
+                quirk=quirk, voice=voice, sampled=sampled, norefresh1=norefresh1, streamed=streamed, stopped=stopped, sde=sde)
 
 
 GENERATORS = dict(loop=gen_loop, voice_prompt=gen_voice_prompt, scheduler=gen_scheduler, head=gen_head, codec=gen_codec, connector=gen_connector, lm=gen_lm)

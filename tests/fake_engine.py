@@ -92,8 +92,23 @@ class FakeEngine:
             self.spec[s] = False
 
     # ---- programs ----
+    @property
+    def sde(self) -> bool:
+        return self.scheduler is not None and getattr(self.scheduler.config, "algorithm_type", "dpmsolver++") == "sde-dpmsolver++"
+
+    def set_scheduler(self, scheduler):
+        self.scheduler = scheduler
+        self.n_steps = 0
+
     def set_diffusion_steps(self, n_steps: int):
         self.n_steps = int(n_steps)
+        self.step_noise = torch.zeros(self.n_steps, self.B, 64)
+
+    def upload_step_noise(self, draw, active_rows):
+        n = len(active_rows)
+        rows = torch.as_tensor(list(active_rows), dtype=torch.long)
+        for i in range(self.n_steps):
+            self.step_noise[i].index_copy_(0, rows, draw(i)[:n].float())
 
     def embed_tokens(self, tokens, out: torch.Tensor):
         out[:len(tokens)] = self.embed_w[torch.as_tensor(list(tokens), dtype=torch.long)]
@@ -131,7 +146,8 @@ class FakeEngine:
         scale, bias = float(w["model.speech_scaling_factor"]), float(w["model.speech_bias_factor"])
         n = rows.numel()
         noise = torch.cat([self.noise[rows], torch.zeros(n, 64)])            # the sampler uses rows [:n] of the 2n draw (:701-704)
-        lat = O.sample_speech_tokens(w, self.hidden[rows], self.hidden[B + rows], cfg_scale, self.n_steps, noise, hc.head_layers, hc.rms_norm_eps)
+        kw = dict(algorithm_type="sde-dpmsolver++", step_noise=[self.step_noise[i][rows] for i in range(self.n_steps)]) if self.sde else {}
+        lat = O.sample_speech_tokens(w, self.hidden[rows], self.hidden[B + rows], cfg_scale, self.n_steps, noise, hc.head_layers, hc.rms_norm_eps, **kw)
         audio = O.decoder_frame(w, cfg.acoustic_tokenizer_config, (lat / scale - bias)[:, None, :], self.a_state, rows)
         sem = O.encoder_frame(w, cfg.semantic_tokenizer_config, audio, self.s_state, rows)
         emb = O.connector(w, "model.acoustic_connector", lat) + O.connector(w, "model.semantic_connector", sem[:, 0])

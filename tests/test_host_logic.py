@@ -44,12 +44,21 @@ def test_product_schedule_equals_oracle_tables(n):
     for j, a in enumerate([t.a0, t.s0, t.ks, t.kx, t.rinv]):
         assert np.array_equal(s.coef[:, j], a)
     assert np.array_equal(s.coef[:, 5].astype(np.int32), t.order)
+    # sde-dpmsolver++ (seven columns): the oracle's tables are bit-exact against the reference scheduler (test_oracle_golden.py)
+    s = DPMSolverMultistepScheduler(algorithm_type="sde-dpmsolver++", beta_schedule="squaredcos_cap_v2").set_timesteps(n)
+    t = O.dpm_tables(n, algorithm_type="sde-dpmsolver++")
+    for j, a in enumerate([t.a0, t.s0, t.ks, t.kx, t.rinv, t.order.astype(np.float32), t.kn]):
+        assert np.array_equal(s.coef[:, j], a), j
 
 
 def test_scheduler_rejects_variants_off_the_path():
     from vibevoice_b200.schedule import DPMSolverMultistepScheduler
     with pytest.raises(NotImplementedError):
-        DPMSolverMultistepScheduler(algorithm_type="sde-dpmsolver++")
+        DPMSolverMultistepScheduler(algorithm_type="dpmsolver")
+    with pytest.raises(NotImplementedError):
+        DPMSolverMultistepScheduler(solver_order=3)
+    sde = DPMSolverMultistepScheduler(algorithm_type="sde-dpmsolver++").set_timesteps(10)
+    assert sde.coef.shape == (10, 7) and sde.coef[-1, 6] == 0.0 and (sde.coef[:-1, 6] > 0).all()
     s = DPMSolverMultistepScheduler()
     s2 = DPMSolverMultistepScheduler.from_config(s.config)
     assert s2.config.solver_order == 2
@@ -205,7 +214,7 @@ def test_lora_assets_fold_into_base_weights(tmp_path):
     from vibevoice.modular.lora_loading import load_lora_assets  # noqa: F401  (drop-in import path)
 
 
-@pytest.mark.parametrize("case", ["scripted", "free", "maxlen", "quirk", "norefresh1"])
+@pytest.mark.parametrize("case", ["scripted", "free", "maxlen", "quirk", "norefresh1", "sde"])
 def test_product_generate_host_logic_against_reference_generate_fixture(golden, case):
     """`modeling.generate` (the product's host state machine, a-1/a-2/a-8: token bookkeeping, which KV entries the negative stream
     keeps, restart on <speech_start>, codec-state zeroing, per-row finishing, noise-row packing) driven through a CPU stand-in of the
@@ -222,6 +231,10 @@ def test_product_generate_host_logic_against_reference_generate_fixture(golden, 
     sd = synth_state_dict(cfg, 1234, torch.float32)
     model = make_model(cfg, tok, sd, max_batch=c["ids"].shape[0])
     model.set_ddpm_inference_steps(g["num_steps"])
+    if c.get("algorithm_type") == "sde-dpmsolver++":            # the way demo/gradio_demo.py:141-146 switches solvers
+        from vibevoice_b200.schedule import DPMSolverMultistepScheduler
+        base = DPMSolverMultistepScheduler()
+        model.model.noise_scheduler = base.from_config(base.config, algorithm_type="sde-dpmsolver++", beta_schedule="squaredcos_cap_v2")
     torch.manual_seed(c["seed"])
     out = model.generate(input_ids=c["ids"], attention_mask=c["mask"], tokenizer=tok, cfg_scale=g["cfg_scale"], is_prefill=False,
                          max_new_tokens=c["max_new_tokens"], max_length_times=c["max_length_times"], show_progress_bar=False,

@@ -115,7 +115,7 @@ def test_voice_prompt_embeds(golden):
     close(got, g["connected"], rtol=1e-4, atol=1e-5)
 
 
-@pytest.mark.parametrize("case", ["scripted", "free", "maxlen", "norefresh", "quirk", "voice", "sampled", "norefresh1"])
+@pytest.mark.parametrize("case", ["scripted", "free", "maxlen", "norefresh", "quirk", "voice", "sampled", "norefresh1", "sde"])
 def test_generate_loop_matches_the_reference_generate(golden, case):
     """The whole loop (a-1 token state machine, a-2 negative CFG stream, a-8 state zeroing) against the reference's OWN
     `generate()` (modeling_vibevoice_inference.py:326-695) run on the same synthetic checkpoint by `oracle/make_golden.py::gen_loop`
@@ -138,7 +138,8 @@ def test_generate_loop_matches_the_reference_generate(golden, case):
             o += int(m.sum())
     out = O.generate(sd, cfg, c["ids"], c["mask"], tok, cfg_scale=g["cfg_scale"], num_steps=g["num_steps"],
                      max_new_tokens=c["max_new_tokens"], max_length_times=c["max_length_times"], forced_tokens=c["scripts"],
-                     refresh_negative=c["refresh_negative"], speech_embeds=speech_embeds, do_sample=c["do_sample"])
+                     refresh_negative=c["refresh_negative"], speech_embeds=speech_embeds, do_sample=c["do_sample"],
+                     algorithm_type=c.get("algorithm_type", "dpmsolver++"))
     assert torch.equal(out.sequences, c["sequences"])
     assert torch.equal(out.reach_max_step_sample, c["reach_max"])
     assert len(out.speech_outputs) == len(c["audio"])

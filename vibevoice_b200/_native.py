@@ -61,6 +61,8 @@ SYMBOLS = {
     "vv_kv_len": (_L, [_P, _I]),
     "vv_embed_tokens": (_I, [_P, _P, _I, _P, _P]),
     "vv_set_diffusion_steps": (_I, [_P, _I, _P, _P, _P]),
+    "vv_set_diffusion_steps_sde": (_I, [_P, _I, _P, _P, _P]),
+    "vv_set_step_noise": (_I, [_P, _P]),
     "vv_diffusion_sample": (_I, [_P, _P, _P, _P, _F, _P, _P]),
     "vv_codec_decode_frame": (_I, [_P, _P, _P, _P, _P]),
     "vv_semantic_encode_frame": (_I, [_P, _P, _P, _P, _P]),

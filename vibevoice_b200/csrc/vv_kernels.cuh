@@ -1720,11 +1720,13 @@ __global__ void head_cond_prep_kernel(const float* __restrict__ condp, const flo
   c_all[idx] = silu_f(condp[(size_t)r * H + k] + temb[(size_t)i * H + k]);
 }
 
-struct DpmCoef { float a0, s0, ks, kx, rinv; int order; };
+struct DpmCoef { float a0, s0, ks, kx, rinv; int order; float kn; };   // kn: per-step noise gain (sde-dpmsolver++), 0 for the ODE solver
 
 // Step `i` CFG + DPM-Solver++(2M) update of z from the head output v of step i, then (optionally)
 // the projection x = noisy_images_proj(z') for the next head evaluation, rows b and B+b.
-//   v = v_u + s (v_c - v_u); x0 = a0 z - s0 v; z' = ks z - kx x0 [- 0.5 kx rinv (x0 - x0_prev)]
+//   v = v_u + s (v_c - v_u); x0 = a0 z - s0 v; z' = ks z - kx x0 [- 0.5 kx rinv (x0 - x0_prev)] [+ kn * step_noise[step]]
+// (sde-dpmsolver++, dpm_solver.py:680-686 / 785-793: same two forms with other ks/kx plus the variance-noise term; step_noise is
+//  [n_steps][B][64] or nullptr for the ODE solver)
 // grid (B, H/256): every CTA recomputes the 64-element update from the read-only (z_in, x0_in) pair,
 // CTA y==0 publishes (z_out, x0_out); the ping-pong removes the cross-CTA read/write hazard.
 __global__ void __launch_bounds__(256) dpm_update_proj_kernel(const float* __restrict__ z_in, float* __restrict__ z_out,
@@ -1732,7 +1734,8 @@ __global__ void __launch_bounds__(256) dpm_update_proj_kernel(const float* __res
                                                               const float* __restrict__ v, const float* __restrict__ noise,
                                                               const DpmCoef* __restrict__ coef, int step, float cfg,
                                                               const bf16* __restrict__ w_noisy /*[H][64]*/, float* __restrict__ xout,
-                                                              float* __restrict__ latent_out, int B, int H, int do_proj) {
+                                                              float* __restrict__ latent_out, int B, int H, int do_proj,
+                                                              const float* __restrict__ step_noise) {
   pdl_trigger();
   pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x;
@@ -1749,6 +1752,7 @@ __global__ void __launch_bounds__(256) dpm_update_proj_kernel(const float* __res
       x0 = c.a0 * zo - c.s0 * vv;
       zn = c.ks * zo - c.kx * x0;
       if (c.order == 2) zn -= 0.5f * c.kx * (c.rinv * (x0 - x0_in[b * 64 + tid]));
+      if (step_noise) zn += c.kn * step_noise[((size_t)step * B + b) * 64 + tid];
     }
     zs[tid] = zn;
     if (blockIdx.y == 0) {

@@ -112,6 +112,7 @@ struct vv_ctx {
   bf16 *h_noisy = nullptr, *h_cond = nullptr, *h_t0 = nullptr, *h_t2 = nullptr, *h_mod = nullptr, *h_final = nullptr;
   std::vector<HeadLayer> head;
   int n_steps = 0; float* temb = nullptr; DpmCoef* coef_dev = nullptr; float* tfreqs = nullptr;
+  bool sde = false; const float* step_noise = nullptr;   // sde-dpmsolver++: per-step variance noise [n_steps][B][64] (vv_set_step_noise)
   // connectors
   bf16 *ca_fc1 = nullptr, *ca_fc2 = nullptr, *cs_fc1 = nullptr, *cs_fc2 = nullptr;
   float *ca_b1 = nullptr, *ca_b2 = nullptr, *ca_n = nullptr, *cs_b1 = nullptr, *cs_b2 = nullptr, *cs_n = nullptr;
@@ -1179,17 +1180,37 @@ extern "C" int vv_embed_tokens(vv_ctx* c, const int32_t* tokens_host, int n, flo
 // ------------------------------------------------------------------------------------------------
 // a-4: diffusion sampler
 // ------------------------------------------------------------------------------------------------
+static int set_diffusion_steps(vv_ctx* c, int n_steps, const float* timesteps, const float* coef, int ncol, void* stream);
 extern "C" int vv_set_diffusion_steps(vv_ctx* c, int n_steps, const float* timesteps, const float* coef, void* stream) {
+  return set_diffusion_steps(c, n_steps, timesteps, coef, 6, stream);
+}
+extern "C" int vv_set_diffusion_steps_sde(vv_ctx* c, int n_steps, const float* timesteps, const float* coef7, void* stream) {
+  return set_diffusion_steps(c, n_steps, timesteps, coef7, 7, stream);
+}
+extern "C" int vv_set_step_noise(vv_ctx* c, const float* step_noise) {
+  if (!c) return fail(VV_ERR_INVALID, "null ctx");
+  if (c->step_noise != step_noise) {            // captured graphs hold the old pointer
+    for (auto it = c->graphs.begin(); it != c->graphs.end();) {
+      if (it->first.rfind("tail:", 0) == 0 || it->first.rfind("diff:", 0) == 0) { cudaGraphExecDestroy(it->second.exec); it = c->graphs.erase(it); }
+      else ++it;
+    }
+  }
+  c->step_noise = step_noise;
+  return 0;
+}
+static int set_diffusion_steps(vv_ctx* c, int n_steps, const float* timesteps, const float* coef, int ncol, void* stream) {
   if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
   if (n_steps < 1 || n_steps > c->d.max_diffusion_steps) return fail(VV_ERR_INVALID, "n_steps %d outside [1,%d]", n_steps, c->d.max_diffusion_steps);
+  if (ncol == 7 && c->use_mega) return fail(VV_ERR_INVALID, "sde-dpmsolver++ is not available in the persistent program kernel (VV_MEGA)");
   CK(cudaSetDevice(c->device));
   cudaStream_t s = (cudaStream_t)stream;
   const int H = c->d.hidden_size;
   std::vector<DpmCoef> cf(n_steps);
   for (int i = 0; i < n_steps; ++i) {
-    cf[i].a0 = coef[i * 6 + 0]; cf[i].s0 = coef[i * 6 + 1]; cf[i].ks = coef[i * 6 + 2]; cf[i].kx = coef[i * 6 + 3];
-    cf[i].rinv = coef[i * 6 + 4]; cf[i].order = (int)coef[i * 6 + 5];
+    cf[i].a0 = coef[i * ncol + 0]; cf[i].s0 = coef[i * ncol + 1]; cf[i].ks = coef[i * ncol + 2]; cf[i].kx = coef[i * ncol + 3];
+    cf[i].rinv = coef[i * ncol + 4]; cf[i].order = (int)coef[i * ncol + 5]; cf[i].kn = ncol == 7 ? coef[i * ncol + 6] : 0.f;
   }
+  c->sde = (ncol == 7);
   CK(cudaStreamSynchronize(s));
   CK(cudaMemcpy(c->coef_dev, cf.data(), sizeof(DpmCoef) * n_steps, cudaMemcpyHostToDevice));
   float* tdev = c->s_t1;   // reuse as staging for the timesteps (n floats) before it is overwritten below
@@ -1272,6 +1293,7 @@ static int enqueue_diffusion(const L& l, const float* cond, const float* noise, 
   const int H = d.hidden_size, B = d.max_batch, M = 2 * B, LH = d.head_layers, N = c->n_steps;
   if (N < 1) return fail(VV_ERR_STATE, "vv_set_diffusion_steps not called");
   const int modld = (3 * LH + 2) * H;
+  if (c->sde && !c->step_noise) return fail(VV_ERR_STATE, "sde-dpmsolver++ needs vv_set_step_noise before sampling");
   GemvP p = mk(c->h_cond, nullptr, cond, H, c->s_condp, H, M, H, H);
   RET(linear(l, p));
   {
@@ -1284,7 +1306,7 @@ static int enqueue_diffusion(const L& l, const float* cond, const float* noise, 
   RET(linear(l, p));
   if (prog && prog->n_ops > 0) return launch_program(l, *prog);
   CK(launch_k(l, dpm_update_proj_kernel, dim3(B, (H + 255) / 256), dim3(256), 0, c->s_z + B * 64, c->s_z, c->s_x0 + B * 64, c->s_x0, c->s_v, noise,
-              c->coef_dev, -1, cfg, c->h_noisy, c->s_hx, nullptr, B, H, 1));
+              c->coef_dev, -1, cfg, c->h_noisy, c->s_hx, nullptr, B, H, 1, (const float*)nullptr));
   L lh = l;
   if (c->l2_persist_bytes && c->head_slab_bytes) {
     lh.win_base = c->head_slab;
@@ -1298,7 +1320,7 @@ static int enqueue_diffusion(const L& l, const float* cond, const float* noise, 
     const bool last = (i == N - 1);
     const DpmOp o = dpm_op(c, i, noise, cfg, latent_out);
     CK(launch_k(l, dpm_update_proj_kernel, dim3(B, last ? 1 : (H + 255) / 256), dim3(256), 0, o.z_in, o.z_out, o.x0_in, o.x0_out, o.v, noise, o.coef, i,
-                cfg, o.w_noisy, o.xout, o.latent_out, B, H, o.do_proj));
+                cfg, o.w_noisy, o.xout, o.latent_out, B, H, o.do_proj, c->sde ? c->step_noise : (const float*)nullptr));
   }
   return 0;
 }

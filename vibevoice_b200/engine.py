@@ -88,6 +88,7 @@ class Engine:
         self.noise_h = torch.zeros(B, 64, dtype=torch.float32).pin_memory()
         self.active_h = torch.zeros(B, dtype=torch.int32).pin_memory()
         self.n_steps = 0
+        self.step_noise = None
         self.scheduler = DPMSolverMultistepScheduler(
             num_train_timesteps=config.diffusion_head_config.ddpm_num_steps,
             beta_schedule=config.diffusion_head_config.ddpm_beta_schedule,
@@ -163,14 +164,39 @@ class Engine:
                                      self.s), "vv_kv_write")
 
     # ---- programs -------------------------------------------------------------------------------------
+    @property
+    def sde(self) -> bool:
+        return getattr(self.scheduler.config, "algorithm_type", "dpmsolver++") == "sde-dpmsolver++"
+
+    def set_scheduler(self, scheduler):
+        """`model.model.noise_scheduler = scheduler.from_config(...)` (demo/gradio_demo.py:141-146) lands here."""
+        self.scheduler = scheduler
+        self.n_steps = 0                          # tables are rebuilt on the next set_diffusion_steps
+
     def set_diffusion_steps(self, n_steps: int):
         if n_steps == self.n_steps:
             return
         self.scheduler.set_timesteps(n_steps)
         ts = np.ascontiguousarray(self.scheduler.timesteps.numpy().astype(np.float32))
         coef = np.ascontiguousarray(self.scheduler.coef)
-        N.check(self.lib.vv_set_diffusion_steps(self.h, n_steps, N.iptr(ts), N.iptr(coef), self.s), "vv_set_diffusion_steps")
+        if self.sde:
+            if self.step_noise is None or self.step_noise.shape[0] < n_steps:
+                with torch.cuda.device(self.device):
+                    self.step_noise = torch.zeros(max(n_steps, 8), self.B, 64, dtype=torch.float32, device=self.device)
+            N.check(self.lib.vv_set_diffusion_steps_sde(self.h, n_steps, N.iptr(ts), N.iptr(coef), self.s), "vv_set_diffusion_steps_sde")
+            N.check(self.lib.vv_set_step_noise(self.h, C.c_void_p(self.step_noise.data_ptr())), "vv_set_step_noise")
+        else:
+            N.check(self.lib.vv_set_diffusion_steps(self.h, n_steps, N.iptr(ts), N.iptr(coef), self.s), "vv_set_diffusion_steps")
         self.n_steps = n_steps
+
+    def upload_step_noise(self, draw, active_rows):
+        """sde-dpmsolver++: the reference draws randn_tensor([2n,64]) once per solver step on the model's device (dpm_solver.py:993-997)
+        and only rows [:n] reach the latent (:703-706); `draw(i)` returns that [2n,64] block for step i."""
+        n = len(active_rows)
+        rows = torch.as_tensor(list(active_rows), dtype=torch.long, device=self.step_noise.device)
+        with torch.cuda.stream(self.stream):
+            for i in range(self.n_steps):
+                self.step_noise[i].index_copy_(0, rows, draw(i)[:n].to(self.step_noise.device, torch.float32))
 
     def embed_tokens(self, tokens, out: torch.Tensor):
         a = N.i32(tokens)

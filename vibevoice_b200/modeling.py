@@ -275,7 +275,10 @@ class VibeVoiceForConditionalGenerationInference:
         max_steps = min(max_length - L0, int(max_length_times * L0))                       # :421
         max_step_per_sample = torch.min(max_length - init_len, (max_length_times * init_len).long())   # :422
         self._reserve_kv(int(b * (L0 + max_steps + 2) + b * (max_steps + 2)))
+        if self.model.noise_scheduler is not None and self.model.noise_scheduler is not eng.scheduler:
+            eng.set_scheduler(self.model.noise_scheduler)      # `model.model.noise_scheduler = sched.from_config(...)`, gradio_demo.py:141-146
         eng.set_diffusion_steps(int(self.ddpm_inference_steps))
+        step_noise_fn = kwargs.get("_step_noise_fn", None)      # test hook: i, n -> [2n,64]; default = device RNG like the reference
         eng.codec_state_reset()
         for s in range(2 * B):
             eng.kv_set_len(s, 0)
@@ -398,6 +401,10 @@ class VibeVoiceForConditionalGenerationInference:
                 n = int(diff_rows.size)
                 noise = torch.randn(2 * n, self.config.acoustic_vae_dim)[:n]                  # CPU global RNG, rows [:n] used (:701-704)
                 eng.upload_frame_inputs(noise, diff_rows.tolist())
+                if eng.sde:                                                                   # dpm_solver.py:993-997, one draw per step
+                    draw = (lambda i: step_noise_fn(i, n)) if step_noise_fn is not None else \
+                        (lambda i: torch.randn(2 * n, self.config.acoustic_vae_dim, device=eng.device))
+                    eng.upload_step_noise(draw, diff_rows.tolist())
                 eng.frame_tail(cfg_scale)                                                     # :626-672
                 with torch.cuda.stream(eng.stream):
                     chunk = eng.audio[diff_rows.tolist()].clone()                              # [n, 3200]

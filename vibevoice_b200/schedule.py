@@ -11,6 +11,10 @@ hands per-step coefficients {a0, s0, ks, kx, rinv, order} to the CUDA sampler:
     x0 = a0*z - s0*v                                   (:581-584)
     z' = ks*z - kx*x0                                  order 1, steps 0 and N-1   (:669-677)
     z' = ks*z - kx*x0 - 0.5*kx*rinv*(x0 - x0_prev)      order 2 midpoint           (:738-764)
+
+`algorithm_type="sde-dpmsolver++"` (what `demo/gradio_demo.py:141-146` switches to; :680-686, :785-793) keeps both forms with
+ks = sigma_t/sigma_s0 * e^-h, kx = -(alpha_t (1 - e^-2h)) and adds `+ kn * noise_i`, kn = sigma_t sqrt(1 - e^-2h): a seventh
+coefficient column and one [2n,64] normal draw per step (`randn_tensor`, :993-997).
 """
 from __future__ import annotations
 
@@ -34,10 +38,13 @@ class DPMSolverMultistepScheduler:
         cfg = dict(_SUPPORTED, num_train_timesteps=num_train_timesteps, beta_schedule=beta_schedule,
                    prediction_type=prediction_type)
         for k, v in kwargs.items():
+            if k == "algorithm_type" and v == "sde-dpmsolver++":
+                cfg[k] = v
+                continue
             if k in _SUPPORTED and v != _SUPPORTED[k]:
                 raise NotImplementedError(
-                    "DPMSolverMultistepScheduler(%s=%r) is not on the accelerated path (only %r); the sde/3rd-order/"
-                    "heun variants are listed as next rows in SURVEY 8f-3" % (k, v, _SUPPORTED[k]))
+                    "DPMSolverMultistepScheduler(%s=%r) is not on the accelerated path (only %r; algorithm_type may also be "
+                    "'sde-dpmsolver++')" % (k, v, _SUPPORTED[k]))
             cfg[k] = v
         if beta_schedule not in ("cosine", "squaredcos_cap_v2"):
             raise NotImplementedError("beta_schedule %r" % beta_schedule)
@@ -78,7 +85,8 @@ class DPMSolverMultistepScheduler:
             return alpha_t, sigma * alpha_t
 
         n = len(ts)
-        coef = np.zeros((n, 6), np.float32)
+        sde = self.config.algorithm_type == "sde-dpmsolver++"
+        coef = np.zeros((n, 7 if sde else 6), np.float32)
         for i in range(n):
             alpha_s0, sigma_s0 = a_s(sigmas[i])
             alpha_t, sigma_t = a_s(sigmas[i + 1])
@@ -91,7 +99,12 @@ class DPMSolverMultistepScheduler:
                 alpha_s1, sigma_s1 = a_s(sigmas[i - 1])
                 lam_s1 = torch.log(alpha_s1) - torch.log(sigma_s1)
                 rinv = (1.0 / ((lam_s0 - lam_s1) / h)).item()
-            coef[i] = [alpha_s0.item(), sigma_s0.item(), (sigma_t / sigma_s0).item(),
-                       (alpha_t * (torch.exp(-h) - 1.0)).item(), rinv, 1.0 if first else 2.0]
+            if sde:
+                coef[i] = [alpha_s0.item(), sigma_s0.item(), (sigma_t / sigma_s0 * torch.exp(-h)).item(),
+                           -(alpha_t * (1 - torch.exp(-2.0 * h))).item(), rinv, 1.0 if first else 2.0,
+                           (sigma_t * torch.sqrt(1.0 - torch.exp(-2 * h))).item()]
+            else:
+                coef[i] = [alpha_s0.item(), sigma_s0.item(), (sigma_t / sigma_s0).item(),
+                           (alpha_t * (torch.exp(-h) - 1.0)).item(), rinv, 1.0 if first else 2.0]
         self.coef = coef
         return self
