@@ -175,7 +175,10 @@ class VibeVoiceForConditionalGenerationInference:
         `lora.load_lora_assets`.  Generation state (KV pages, codec state) does not survive."""
         if self._weights_source is None:
             raise RuntimeError("weights were loaded from a one-shot iterator; build the model with from_pretrained(..., lora_dir=...) instead")
+        user_sched = None
         if self.engine is not None:
+            if self.model.noise_scheduler is not self.engine.scheduler:
+                user_sched = self.model.noise_scheduler           # a scheduler the caller installed survives the re-pack
             self.engine.close()
         self.engine = None
         self._prefill = self._voice = None
@@ -184,6 +187,8 @@ class VibeVoiceForConditionalGenerationInference:
         src = self._weights_source
         self.load_state_dict(transform(src()), self._tok)
         self._weights_source = src
+        if user_sched is not None:
+            self.model.noise_scheduler = user_sched
         return self
 
     def eval(self):
