@@ -1,0 +1,109 @@
+"""GPU parity tests written after round 1's GPU budget was spent -- NOT collected by pytest (no `test_` prefix in the file name) so
+that the round-end `pytest -m gpu` run only contains tests that have already passed on a B200.  First thing to do with a GPU:
+
+    python -m pytest tests/gpu_pending_round2.py -x -q -m gpu -p no:cacheprovider
+
+and, once green, move the functions into tests/test_gpu_parity.py.
+
+Covered: `sde-dpmsolver++` through the CUDA sampler (the `+ kn * step_noise` term of dpm_update_proj_kernel, vv_set_diffusion_steps_sde,
+vv_set_step_noise) and `refresh_negative=False` for one prompt.  Both are already held to fixtures from the reference's own
+generate() on the CPU (oracle: tests/test_oracle_golden.py; product host logic through the engine stand-in: tests/test_host_logic.py).
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from test_gpu_parity import _scripted, make_model, rel_l2, report  # noqa: E402
+
+
+def test_sde_sampler_vs_oracle():
+    """Closed loop with the Gradio demo's scheduler (demo/gradio_demo.py:141-146).  The per-step variance noise is injected on both
+    sides (the product would otherwise draw it from the CUDA generator, the oracle from the CPU one)."""
+    from oracle import vv_oracle as O
+    from vibevoice_b200.modeling import ForcedTokenScript
+    model, cfg, tok, sd = make_model("tiny", 2)
+    try:
+        base = model.model.noise_scheduler
+        model.model.noise_scheduler = base.from_config(base.config, algorithm_type="sde-dpmsolver++", beta_schedule="squaredcos_cap_v2")
+        model.set_ddpm_inference_steps(5)
+        dc = cfg.decoder_config
+        g = torch.Generator().manual_seed(5)
+        ids = torch.randint(0, dc.vocab_size - 20, (2, 10), generator=g)
+        ids[:, -1] = tok.speech_start_id
+        scripts = [_scripted(tok, "dddesddx"), _scripted(tok, "ddddddx")]
+        pool = torch.randn(64, 5, 4, 64, generator=g)            # [frame][step][2n<=4][64]
+        frame = {"i": -1}
+
+        def step_noise_fn(i, n):
+            if i == 0:
+                frame["i"] += 1
+            return pool[frame["i"], i, :2 * n]
+        torch.manual_seed(0)
+        out = model.generate(input_ids=ids, tokenizer=tok, cfg_scale=1.3, is_prefill=False, logits_processor=[ForcedTokenScript(scripts)],
+                             max_new_tokens=20, show_progress_bar=False, _step_noise_fn=step_noise_fn)
+        # oracle: same frame noise stream (CPU global RNG), same step noise through sample_speech_tokens' hook
+        oframe = {"i": -1}
+        orig = O.sample_speech_tokens
+
+        def patched(w, pc, nc, cs, ns, noise, nl=4, eps=1e-5, trace=None, algorithm_type="dpmsolver++", step_noise=None):
+            oframe["i"] += 1
+            n = pc.shape[0]
+            return orig(w, pc, nc, cs, ns, noise, nl, eps, trace, algorithm_type, [pool[oframe["i"], i, :2 * n] for i in range(ns)])
+        O.sample_speech_tokens = patched
+        try:
+            torch.manual_seed(0)
+            ref = O.generate(sd, cfg, ids, None, tok, cfg_scale=1.3, num_steps=5, max_new_tokens=20, forced_tokens=scripts, kv_bf16=True,
+                             algorithm_type="sde-dpmsolver++")
+        finally:
+            O.sample_speech_tokens = orig
+        assert torch.equal(out.sequences, ref.sequences)
+        for r in range(2):
+            e = rel_l2(out.speech_outputs[r].cpu(), ref.speech_outputs[r])
+            report("sde_generate", row=r, audio_rel_l2=e)
+            assert e < 1e-2, (r, e)
+        # and the noise term is live: the ODE solver on the same inputs gives different audio
+        model.model.noise_scheduler = base
+        torch.manual_seed(0)
+        ode = model.generate(input_ids=ids, tokenizer=tok, cfg_scale=1.3, is_prefill=False, logits_processor=[ForcedTokenScript(scripts)],
+                             max_new_tokens=20, show_progress_bar=False)
+        assert rel_l2(ode.speech_outputs[0].cpu(), out.speech_outputs[0].cpu()) > 1e-2
+    finally:
+        model.engine.close()
+
+
+def test_refresh_negative_false_single_prompt_vs_oracle():
+    """`refresh_negative=False` (reference :503-517), one prompt with two speaker turns: the negative stream keeps every step's input
+    and is never restarted."""
+    from oracle import vv_oracle as O
+    from vibevoice_b200.modeling import ForcedTokenScript
+    model, cfg, tok, sd = make_model("tiny", 1)
+    try:
+        dc = cfg.decoder_config
+        g = torch.Generator().manual_seed(31)
+        ids = torch.randint(0, dc.vocab_size - 20, (1, 10), generator=g)
+        ids[:, -1] = tok.speech_start_id
+        script = [_scripted(tok, "ddesdddesdx")]
+        model.set_ddpm_inference_steps(5)
+        torch.manual_seed(7)
+        out = model.generate(input_ids=ids, tokenizer=tok, cfg_scale=1.3, is_prefill=False, logits_processor=[ForcedTokenScript(script)],
+                             max_new_tokens=40, show_progress_bar=False, refresh_negative=False)
+        torch.manual_seed(7)
+        ref = O.generate(sd, cfg, ids, None, tok, cfg_scale=1.3, num_steps=5, max_new_tokens=40, forced_tokens=script, kv_bf16=True,
+                         refresh_negative=False)
+        torch.manual_seed(7)
+        refreshed = O.generate(sd, cfg, ids, None, tok, cfg_scale=1.3, num_steps=5, max_new_tokens=40, forced_tokens=script, kv_bf16=True)
+        assert torch.equal(out.sequences, ref.sequences)
+        e = rel_l2(out.speech_outputs[0].cpu(), ref.speech_outputs[0])
+        moved = rel_l2(ref.speech_outputs[0], refreshed.speech_outputs[0])
+        report("refresh_negative_false", audio_rel_l2=e, differs_from_refresh_true=moved)
+        assert e < 1e-2 and moved > 10 * e, (e, moved)
+        with pytest.raises(NotImplementedError):
+            m2, _, _, _ = make_model("tiny", 2)
+            try:
+                m2.generate(input_ids=torch.cat([ids, ids]), tokenizer=tok, is_prefill=False, max_new_tokens=2, refresh_negative=False,
+                            show_progress_bar=False)
+            finally:
+                m2.engine.close()
+    finally:
+        model.engine.close()
