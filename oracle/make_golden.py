@@ -364,7 +364,60 @@ def gen_loop(ns, preset="tiny"):
                 quirk=quirk, voice=voice, sampled=sampled, norefresh1=norefresh1, streamed=streamed, stopped=stopped, sde=sde)
 
 
-GENERATORS = dict(loop=gen_loop, voice_prompt=gen_voice_prompt, scheduler=gen_scheduler, head=gen_head, codec=gen_codec, connector=gen_connector, lm=gen_lm)
+def gen_streaming(ns, preset="tiny"):
+    """The streaming-0.5B variant's own `generate()` (modeling_vibevoice_streaming_inference.py:412-725, loop body unmodified; same
+    transformers-4.51.3 glue as `gen_loop`) on a synthetic split checkpoint: 1 lower + 1 upper layer of the tiny preset, random
+    type embeddings and EOS classifier (`vv_streaming.streaming_state_dict`).  The four prefilled outputs the loop starts from are
+    computed with the reference's own `forward_lm` / `forward_tts_lm` on a text-only prompt.  Cases:
+      eos      classifier fires inside the first speech window (frames after it are dropped)
+      windows  classifier biased off: three text windows (5,5,2), then text-less windows until max_new_tokens -> reach_max
+      short    text shorter than one window, max length hit inside a speech window"""
+    import importlib
+    from oracle import vv_streaming as VS
+    mod = ref_shim.install_streaming_generate_compat()
+    scfg_mod = importlib.import_module("vibevoice.modular.configuration_vibevoice_streaming")
+    cfg = preset_config(preset)
+    rc = _ref_cfg(ns, cfg)
+    tts_layers = 1
+    sc = scfg_mod.VibeVoiceStreamingConfig(acoustic_tokenizer_config=rc.acoustic_tokenizer_config, decoder_config=rc.decoder_config,
+                                            diffusion_head_config=rc.diffusion_head_config, tts_backbone_num_hidden_layers=tts_layers)
+    sc.decoder_config._attn_implementation = "sdpa"
+    tok = SynthTokenizer(cfg.decoder_config.vocab_size)
+    tok.convert_tokens_to_ids = lambda t: tok.pad_token_id        # "<|image_pad|>" (:465)
+    base = synth_state_dict(cfg, SEED, torch.float32)
+    steps = 5
+    out = dict(preset=preset, tts_layers=tts_layers, num_steps=steps, neg_id=tok.pad_token_id)
+    g = torch.Generator().manual_seed(7)
+    prompt = torch.randint(0, 2000, (1, 6), generator=g)
+    for name, eos_bias, n_text, max_new, cfg_scale, seed in (("eos", -0.3, 12, 40, 1.5, 0), ("windows", -6.0, 12, 30, 1.5, 1),
+                                                              ("short", -6.0, 3, 7, 1.3, 2)):
+        sd = VS.streaming_state_dict(base, cfg, tts_layers, eos_bias=eos_bias)
+        m = mod.VibeVoiceStreamingForConditionalGenerationInference(sc).eval()
+        res = m.load_state_dict(sd, strict=False)
+        assert not [k for k in res.missing_keys if "fix_std" not in k and "rotary" not in k] and not res.unexpected_keys, res
+        m.set_ddpm_inference_steps(steps)
+        text = torch.randint(0, 2000, (1, n_text), generator=g)
+        neg = torch.full((1, 1), tok.pad_token_id)
+        new = lambda: ref_shim.legacy_cache(sc.decoder_config)
+        with torch.no_grad():
+            lm = m.forward_lm(input_ids=prompt, attention_mask=torch.ones_like(prompt), past_key_values=new(), use_cache=True, return_dict=True)
+            tts = m.forward_tts_lm(input_ids=prompt, attention_mask=torch.ones_like(prompt), past_key_values=new(), use_cache=True,
+                                   return_dict=True, lm_last_hidden_state=lm.last_hidden_state, tts_text_masks=torch.ones_like(prompt))
+            nlm = m.forward_lm(input_ids=neg, attention_mask=torch.ones_like(neg), past_key_values=new(), use_cache=True, return_dict=True)
+            ntts = m.forward_tts_lm(input_ids=neg, attention_mask=torch.ones_like(neg), past_key_values=new(), use_cache=True,
+                                    return_dict=True, lm_last_hidden_state=nlm.last_hidden_state, tts_text_masks=torch.ones_like(neg))
+        torch.manual_seed(seed)
+        r = m.generate(input_ids=prompt.clone(), attention_mask=torch.ones_like(prompt), tts_lm_input_ids=prompt.clone(),
+                       tts_lm_attention_mask=torch.ones_like(prompt), tts_text_ids=text.clone(),
+                       all_prefilled_outputs={"lm": lm, "tts_lm": tts, "neg_lm": nlm, "neg_tts_lm": ntts}, tokenizer=tok,
+                       cfg_scale=cfg_scale, max_new_tokens=max_new, show_progress_bar=False, verbose=False)
+        out[name] = dict(eos_bias=eos_bias, prompt=prompt[0].clone(), text=text[0].clone(), max_new_tokens=max_new, cfg_scale=cfg_scale,
+                         seed=seed, sequences=r.sequences.clone(), reach_max=r.reach_max_step_sample.clone(),
+                         audio=None if r.speech_outputs[0] is None else r.speech_outputs[0].clone())
+    return out
+
+
+GENERATORS = dict(streaming=gen_streaming, loop=gen_loop, voice_prompt=gen_voice_prompt, scheduler=gen_scheduler, head=gen_head, codec=gen_codec, connector=gen_connector, lm=gen_lm)
 
 
 def main():

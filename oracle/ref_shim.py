@@ -202,17 +202,8 @@ def script_tokens(initial_length=None, tokens=None):
         _SCRIPT.update(L0=int(initial_length), tokens=[list(t) for t in tokens])
 
 
-def install_generate_compat():
-    """Patch the imported reference inference class so that its generate() runs under transformers 5.5.0 (see above)."""
-    import torch
+def _legacy_cache_class():
     from transformers.cache_utils import DynamicCache
-
-    load_reference()
-    import importlib
-    infer_mod = importlib.import_module("vibevoice.modular.modeling_vibevoice_inference")
-    cls = infer_mod.VibeVoiceForConditionalGenerationInference
-    if getattr(cls, "_vv_compat", False):
-        return infer_mod
 
     class LegacyListCache(DynamicCache):
         @property
@@ -223,13 +214,23 @@ def install_generate_compat():
         def value_cache(self):
             return [layer.values for layer in self.layers]
 
+    return LegacyListCache
+
+
+def _patch_generation_class(cls, cache_config_of):
+    """transformers-4.51.3 GenerationMixin glue (see the block comment above) installed on one reference inference class."""
+    import torch
+
+    if getattr(cls, "_vv_compat", False):
+        return
+    LegacyListCache = _legacy_cache_class()
     orig_tie = cls.tie_weights
     cls.tie_weights = lambda self, *a, **k: orig_tie(self)
     orig_pgc = cls._prepare_generation_config
     cls._prepare_generation_config = lambda self, gc, *flags, **kw: orig_pgc(self, gc, **kw)
 
     def prepare_cache(self, generation_config, model_kwargs, assistant_model, batch_size, max_cache_length, device=None):
-        model_kwargs["past_key_values"] = LegacyListCache(config=self.config.decoder_config)
+        model_kwargs["past_key_values"] = LegacyListCache(config=cache_config_of(self))
 
     def update_kwargs(self, outputs, model_kwargs, is_encoder_decoder=False, num_new_tokens=1):
         model_kwargs["past_key_values"] = outputs.past_key_values
@@ -269,6 +270,18 @@ def install_generate_compat():
     cls._prepare_cache_for_generation = prepare_cache
     cls._update_model_kwargs_for_generation = update_kwargs
     cls.prepare_inputs_for_generation = prepare_inputs
+    cls._vv_compat = True
+
+
+def install_generate_compat():
+    """Patch the imported reference inference class so that its generate() runs under transformers 5.5.0 (see above)."""
+    load_reference()
+    import importlib
+    infer_mod = importlib.import_module("vibevoice.modular.modeling_vibevoice_inference")
+    cls = infer_mod.VibeVoiceForConditionalGenerationInference
+    if getattr(cls, "_vv_compat", False):
+        return infer_mod
+    _patch_generation_class(cls, lambda self: self.config.decoder_config)
 
     proc = infer_mod.VibeVoiceTokenConstraintProcessor
     orig_call = proc.__call__
@@ -282,5 +295,21 @@ def install_generate_compat():
         return scores
 
     proc.__call__ = constrained_then_scripted
-    cls._vv_compat = True
     return infer_mod
+
+
+def install_streaming_generate_compat():
+    """Same glue for the streaming-0.5B inference class (modeling_vibevoice_streaming_inference.py:95-762).  Its four KV streams
+    (lm / tts_lm and their negatives) are created by `_prepare_cache_for_generation` with no layer count of their own; the caller
+    replaces them with the prefilled caches (`all_prefilled_outputs`, :517-534) before any forward, so an empty legacy-list cache
+    is all that is needed here."""
+    load_reference()
+    import importlib
+    mod = importlib.import_module("vibevoice.modular.modeling_vibevoice_streaming_inference")
+    _patch_generation_class(mod.VibeVoiceStreamingForConditionalGenerationInference, lambda self: self.config.decoder_config)
+    return mod
+
+
+def legacy_cache(config):
+    """An empty transformers-5.5.0 DynamicCache that also exposes the 4.x `.key_cache` / `.value_cache` lists."""
+    return _legacy_cache_class()(config=config)

@@ -176,3 +176,26 @@ def test_logical_negative_bookkeeping_is_the_reference_on_well_formed_sequences(
     rel = float((a.speech_outputs[0] - b.speech_outputs[0]).norm() / a.speech_outputs[0].norm())
     assert rel > 1e-3                                    # the d,e,d row hears a different negative context ...
     assert torch.equal(a.speech_outputs[1], b.speech_outputs[1])      # ... the well-formed row does not
+
+
+@pytest.mark.parametrize("case", ["eos", "windows", "short"])
+def test_streaming_generate_matches_the_reference(golden, case):
+    """SURVEY 8f-1 groundwork: the streaming-0.5B loop (split LM, type embeddings, EOS classifier, 5-token text windows / 6-frame
+    speech windows) restated in `oracle/vv_streaming.py` against the reference's own streaming generate()
+    (modeling_vibevoice_streaming_inference.py:412-725) on a synthetic split checkpoint.  Sequences and the max-length flag exact,
+    waveform 1e-5."""
+    from oracle import vv_streaming as VS
+    g = golden("streaming")
+    c = g[case]
+    cfg = preset_config(g["preset"])
+    sd = VS.streaming_state_dict(synth_state_dict(cfg, SEED, torch.float32), cfg, g["tts_layers"], eos_bias=c["eos_bias"])
+    torch.manual_seed(c["seed"])
+    out = VS.generate_streaming(sd, cfg, g["tts_layers"], c["prompt"], c["text"], g["neg_id"], cfg_scale=c["cfg_scale"],
+                                num_steps=g["num_steps"], max_new_tokens=c["max_new_tokens"])
+    assert torch.equal(out.sequences, c["sequences"])
+    assert torch.equal(out.reach_max_step_sample, c["reach_max"])
+    a, b = out.speech_outputs[0], c["audio"]
+    assert (a is None) == (b is None)
+    if a is not None:
+        assert a.shape == b.shape
+        assert float((a.double() - b.double()).norm() / b.double().norm()) < 1e-5
