@@ -66,10 +66,10 @@ def eos_logit(w, h: Tensor) -> Tensor:
 class Streams:
     """The four KV streams of the loop (`all_prefilled_outputs`, :517-534) and the last hidden state of the two TTS-LM streams."""
 
-    def __init__(self, w, cfg, tts_layers: int):
+    def __init__(self, w, cfg, tts_layers: int, kv_bf16: bool = False):
         self.w, self.dc, self.t = w, cfg.decoder_config, tts_layers
         self.low = self.dc.num_hidden_layers - tts_layers
-        mk = lambda n: O.KVCache(n)
+        mk = lambda n: O.KVCache(n, kv_bf16)
         self.lm, self.tts, self.neg_tts = mk(self.low), mk(tts_layers), mk(tts_layers)
         self.types = w["model.tts_input_types.weight"].float()
         self.h_pos: Optional[Tensor] = None
@@ -88,16 +88,16 @@ def prefill(st: Streams, prompt_ids: Tensor, neg_id: int):
     demo/streaming_inference_from_file.py:291): lower stack over the prompt, upper stack over its outputs (type 1); the negative
     streams see the single token <|image_pad|> (:475, :476-482)."""
     st.h_pos = st.forward_tts(st.forward_lm(prompt_ids, st.lm), 1, st.tts)
-    neg_lm = O.KVCache(st.low)
+    neg_lm = O.KVCache(st.low, st.lm.kv_bf16)
     st.h_neg = st.forward_tts(st.forward_lm(torch.tensor([neg_id]), neg_lm), 1, st.neg_tts)
 
 
 def generate_streaming(w, cfg, tts_layers: int, prompt_ids: Tensor, tts_text_ids: Tensor, neg_id: int, cfg_scale: float = 1.5,
-                       num_steps: int = 5, max_new_tokens: Optional[int] = None) -> O.GenerateResult:
+                       num_steps: int = 5, max_new_tokens: Optional[int] = None, kv_bf16: bool = False) -> O.GenerateResult:
     """prompt_ids [L0], tts_text_ids [T] (one sample).  Returns sequences = `tts_lm_input_ids` (prompt, text windows, a 1 per speech
     frame, :643), the concatenated waveform, and the max-length flag."""
     dc, hc = cfg.decoder_config, cfg.diffusion_head_config
-    st = Streams(w, cfg, tts_layers)
+    st = Streams(w, cfg, tts_layers, kv_bf16)
     prefill(st, prompt_ids, neg_id)
     L0 = int(prompt_ids.numel())
     if max_new_tokens is None:

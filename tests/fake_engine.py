@@ -65,6 +65,7 @@ class FakeEngine:
         self.active = torch.zeros(B, dtype=torch.int32)
         self.latent = torch.zeros(B, 64)
         self.audio = torch.zeros(B, 3200)
+        self.feat = torch.zeros(B, config.semantic_vae_dim)
         self.kv: List[O.KVCache] = [O.KVCache(dc.num_hidden_layers) for _ in range(2 * B)]
         self.spec = [False] * (2 * B)                        # a speculative (uncommitted) entry sits at the end of the stream
         self.a_state, self.s_state = O.StreamState(B), O.StreamState(B)
@@ -88,7 +89,7 @@ class FakeEngine:
         self.calls["kv_commit"] += 1
         for s, a in enumerate(advance):
             if self.spec[s] and not a:
-                self.kv[s].truncate(len(self.kv[s]) - 1)
+                self.kv[s].truncate(max(0 if k is None else k.shape[1] for k in self.kv[s].k) - 1)
             self.spec[s] = False
 
     # ---- programs ----
@@ -123,6 +124,28 @@ class FakeEngine:
             self.spec[s] = True
         self.lm_head(self.hidden)
 
+    # ---- streaming-0.5B split stack (vv_set_row_mode / vv_lm_decode_range) ----
+    def set_row_mode(self, modes):
+        self.row_mode = [int(m) for m in modes]
+
+    def lm_decode_range(self, layer_begin: int, layer_end: int, final_norm: bool, out=None):
+        out = self.hidden if out is None else out
+        dc = self.config.decoder_config
+        for s in range(2 * self.B):
+            if not getattr(self, "row_mode", [1] * (2 * self.B))[s]:
+                out[s] = float("nan")                      # the real kernels leave rows with mode 0 undefined: make misuse visible
+                continue
+            if self.spec[s]:
+                self.kv[s].truncate(self._len(s, layer_begin) - 1)
+            pos = self._len(s, layer_begin)
+            out[s] = O.qwen2_forward(self.w, dc, self.embeds[s][None].clone(), self.kv[s], pos, n_layers=layer_end - layer_begin,
+                                     final_norm=final_norm, layer_begin=layer_begin)[-1]
+            self.spec[s] = True
+
+    def _len(self, s: int, layer: int) -> int:
+        k = self.kv[s].k[layer]
+        return 0 if k is None else k.shape[1]
+
     def lm_head(self, hidden: torch.Tensor):
         lg = hidden[:self.B] @ self.head_rows.T
         self.logits.copy_(lg)
@@ -155,6 +178,27 @@ class FakeEngine:
         self.audio[rows] = audio[:, 0]
         self.embeds[rows] = emb
         self.embeds[B:] = self.embeds[:B]                                     # select_embeds_kernel: negative rows see the same input
+
+    # individual stages (the streaming loop has no semantic encoder, so it calls them one by one)
+    def diffusion_sample(self, cfg_scale: float):
+        hc = self.config.diffusion_head_config
+        rows = self.active.nonzero().flatten()
+        n = rows.numel()
+        noise = torch.cat([self.noise[rows], torch.zeros(n, 64)])
+        self.latent[rows] = O.sample_speech_tokens(self.w, self.hidden[rows], self.hidden[self.B + rows], cfg_scale, self.n_steps, noise,
+                                                   hc.head_layers, hc.rms_norm_eps)
+
+    def codec_decode(self):
+        rows = self.active.nonzero().flatten()
+        scale, bias = float(self.w["model.speech_scaling_factor"]), float(self.w["model.speech_bias_factor"])
+        audio = O.decoder_frame(self.w, self.config.acoustic_tokenizer_config, (self.latent[rows] / scale - bias)[:, None, :], self.a_state, rows)
+        self.audio[rows] = audio[:, 0]
+
+    def connect(self):
+        rows = self.active.nonzero().flatten()
+        emb = O.connector(self.w, "model.acoustic_connector", self.latent[rows]) + O.connector(self.w, "model.semantic_connector", self.feat[rows])
+        self.embeds[rows] = emb
+        self.embeds[self.B:] = self.embeds[:self.B]
 
     def codec_state_zero(self, rows):
         if len(rows):

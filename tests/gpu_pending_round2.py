@@ -107,3 +107,33 @@ def test_refresh_negative_false_single_prompt_vs_oracle():
                 m2.engine.close()
     finally:
         model.engine.close()
+
+
+def test_streaming_variant_vs_oracle():
+    """SURVEY 8f-1 on the GPU: `vibevoice_b200.streaming` (vv_lm_decode_range split stack, row modes, zero-semantic connector) against
+    `oracle/vv_streaming.py`, which is pinned to the reference's own streaming generate() (tests/golden/streaming.pt)."""
+    from oracle import vv_streaming as VS
+    from vibevoice_b200 import streaming as S
+    from vibevoice_b200.configuration import preset_config
+    from vibevoice_b200.synth import synth_state_dict
+    cfg = preset_config("tiny")
+    for eos_bias, n_text, max_new in ((-0.3, 12, 40), (-6.0, 12, 30), (-6.0, 3, 7)):
+        sd = VS.streaming_state_dict(synth_state_dict(cfg, 1234, torch.bfloat16), cfg, 1, eos_bias=eos_bias)
+        m = S.VibeVoiceStreamingForConditionalGenerationInference(cfg, tts_backbone_num_hidden_layers=1)
+        m.load_state_dict(sd)
+        try:
+            m.set_ddpm_inference_steps(5)
+            g = torch.Generator().manual_seed(7)
+            prompt = torch.randint(0, 2000, (6,), generator=g)
+            text = torch.randint(0, 2000, (n_text,), generator=g)
+            torch.manual_seed(0)
+            out = m.generate(input_ids=prompt[None], tts_text_ids=text[None], neg_text_input_id=2047, cfg_scale=1.5, max_new_tokens=max_new)
+            torch.manual_seed(0)
+            ref = VS.generate_streaming(sd, cfg, 1, prompt, text, 2047, cfg_scale=1.5, num_steps=5, max_new_tokens=max_new, kv_bf16=True)
+            assert torch.equal(out.sequences, ref.sequences), (out.sequences, ref.sequences)
+            assert torch.equal(out.reach_max_step_sample, ref.reach_max_step_sample)
+            e = rel_l2(out.speech_outputs[0].cpu(), ref.speech_outputs[0])
+            report("streaming_generate", eos_bias=eos_bias, n_text=n_text, audio_rel_l2=e)
+            assert e < 1e-2, e
+        finally:
+            m.engine.close()

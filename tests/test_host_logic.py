@@ -341,3 +341,31 @@ def test_from_pretrained_reads_an_hf_checkpoint_directory(tmp_path, monkeypatch,
         outs.append(model.generate(input_ids=c["ids"], tokenizer=tok, cfg_scale=1.3, is_prefill=False, max_new_tokens=6, show_progress_bar=False))
     assert torch.equal(outs[0].sequences, outs[1].sequences)
     assert torch.equal(outs[0].speech_outputs[0], outs[1].speech_outputs[0])
+
+
+@pytest.mark.parametrize("case", ["eos", "windows", "short"])
+def test_streaming_product_host_logic_against_reference_fixture(golden, monkeypatch, case):
+    """`vibevoice_b200/streaming.py` (split stack over `lm_decode_range`, type embeddings, EOS classifier, text/speech
+    windows, zero-semantic connector) through the engine stand-in against the fixtures of the reference's own streaming generate()."""
+    import fake_engine
+    from oracle import vv_streaming as VS
+    from vibevoice_b200 import streaming as S
+    from vibevoice_b200.configuration import preset_config
+    from vibevoice_b200.synth import synth_state_dict
+    g = golden("streaming")
+    c = g[case]
+    cfg = preset_config(g["preset"])
+    sd = VS.streaming_state_dict(synth_state_dict(cfg, 1234, torch.float32), cfg, g["tts_layers"], eos_bias=c["eos_bias"])
+    m = S.VibeVoiceStreamingForConditionalGenerationInference(cfg, tts_backbone_num_hidden_layers=g["tts_layers"])
+    monkeypatch.setattr(m, "_new_engine", lambda: fake_engine.FakeEngine(cfg, [0, 1], 2))
+    m.load_state_dict(sd)
+    m.set_ddpm_inference_steps(g["num_steps"])
+    torch.manual_seed(c["seed"])
+    out = m.generate(input_ids=c["prompt"][None], tts_text_ids=c["text"][None], neg_text_input_id=g["neg_id"], cfg_scale=c["cfg_scale"],
+                     max_new_tokens=c["max_new_tokens"])
+    assert torch.equal(out.sequences, c["sequences"])
+    assert torch.equal(out.reach_max_step_sample, c["reach_max"])
+    a, b = out.speech_outputs[0], c["audio"]
+    assert (a is None) == (b is None)
+    if a is not None:
+        assert a.shape == b.shape and float((a.double() - b.double()).norm() / b.double().norm()) < 1e-5

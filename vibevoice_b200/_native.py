@@ -57,6 +57,7 @@ SYMBOLS = {
     "vv_set_row_mode": (_I, [_P, _P, _P]),
     "vv_lm_decode": (_I, [_P, _P, _P, _P, _P, _P]),
     "vv_lm_head": (_I, [_P, _P, _P, _P, _P]),
+    "vv_lm_decode_range": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "vv_kv_commit": (_I, [_P, _P, _P]),
     "vv_kv_len": (_L, [_P, _I]),
     "vv_embed_tokens": (_I, [_P, _P, _I, _P, _P]),

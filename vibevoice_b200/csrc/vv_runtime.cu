@@ -1043,14 +1043,14 @@ static int enqueue_lm_head(const L& l, const float* hidden, float* logits, int32
   return 0;
 }
 
-static int enqueue_lm_decode(const L& l, const float* embeds, float* hidden, float* logits, int32_t* tokens) {
+// decoder layers [li0, li1) over the residual stream s_h (rows = 2B sequences; rows with row_mode 0 neither read nor append KV)
+static int enqueue_lm_layers(const L& l, int li0, int li1) {
   vv_ctx* c = l.c;
   const auto& d = c->d;
   const int H = d.hidden_size, I = d.intermediate_size, M = 2 * d.max_batch, nq = d.num_q_heads * HD;
-  CK(cudaMemcpyAsync(c->s_h, embeds, (size_t)M * H * 4, cudaMemcpyDeviceToDevice, l.s));
   const size_t per_layer = (size_t)c->n_pages * d.num_kv_heads * KV_PAGE * HD;
   const float scale = 1.0f / sqrtf((float)HD);
-  for (int li = 0; li < d.num_layers; ++li) {
+  for (int li = li0; li < li1; ++li) {
     const LmLayer& y = c->lm[li];
     GemvP p = mk(y.wqkv, y.bqkv, c->s_h, H, c->s_qkv, c->Nqkv, M, c->Nqkv, H);
     p.pro = PRO_RMSNORM; p.pro_w = y.ln1; p.pro_eps = d.rms_norm_eps;
@@ -1084,9 +1084,39 @@ static int enqueue_lm_decode(const L& l, const float* embeds, float* hidden, flo
     p.epi = EPI_RESID; p.res = c->s_h; p.ldres = H;
     RET(linear(l, p));
   }
+  return 0;
+}
+
+static int enqueue_final_norm(const L& l, float* hidden) {
+  vv_ctx* c = l.c;
+  const auto& d = c->d;
+  const int H = d.hidden_size, M = 2 * d.max_batch;
   if (H >= 512) CK(launch_k(l, rows_norm_block_kernel, dim3(M), dim3(256), 0, c->s_h, c->lm_norm, hidden, H, d.rms_norm_eps));
   else CK(launch_k(l, rows_norm_kernel, dim3((M + 7) / 8), dim3(256), 0, c->s_h, c->lm_norm, hidden, M, H, d.rms_norm_eps));
+  return 0;
+}
+
+static int enqueue_lm_decode(const L& l, const float* embeds, float* hidden, float* logits, int32_t* tokens) {
+  vv_ctx* c = l.c;
+  const int H = c->d.hidden_size, M = 2 * c->d.max_batch;
+  CK(cudaMemcpyAsync(c->s_h, embeds, (size_t)M * H * 4, cudaMemcpyDeviceToDevice, l.s));
+  RET(enqueue_lm_layers(l, 0, c->d.num_layers));
+  RET(enqueue_final_norm(l, hidden));
   return enqueue_lm_head(l, hidden, logits, tokens);
+}
+
+// streaming-0.5B: the Qwen2 stack is split into a lower text-only stack without final norm and an upper "TTS LM" stack
+// (modeling_vibevoice_streaming.py:134-146); each stack keeps its own KV sequences (lengths differ: the upper stack also sees the speech
+// positions).  One call runs layers [begin, end) for the rows enabled by vv_set_row_mode, appends their K/V speculatively at kv_len (commit
+// with vv_kv_commit as for vv_lm_decode) and returns the residual stream -- normalised with the model's final norm iff final_norm != 0.
+static int enqueue_lm_range(const L& l, const float* embeds, int li0, int li1, int final_norm, float* hidden) {
+  vv_ctx* c = l.c;
+  const int H = c->d.hidden_size, M = 2 * c->d.max_batch;
+  CK(cudaMemcpyAsync(c->s_h, embeds, (size_t)M * H * 4, cudaMemcpyDeviceToDevice, l.s));
+  RET(enqueue_lm_layers(l, li0, li1));
+  if (final_norm) return enqueue_final_norm(l, hidden);
+  CK(cudaMemcpyAsync(hidden, c->s_h, (size_t)M * H * 4, cudaMemcpyDeviceToDevice, l.s));
+  return 0;
 }
 
 static int build_lm_program(vv_ctx* c, const float* embeds, float* hidden, float* logits, int32_t* tokens, vv_ctx::Program* pr) {
@@ -1163,6 +1193,16 @@ __global__ void embed_gather_val_kernel(const bf16* __restrict__ table, Toks t, 
   const bf16* row = table + (size_t)t.v[blockIdx.x] * H;
   for (int k = threadIdx.x; k < H; k += blockDim.x) out[(size_t)blockIdx.x * H + k] = __bfloat162float(row[k]);
 }
+extern "C" int vv_lm_decode_range(vv_ctx* c, const float* embeds, int layer_begin, int layer_end, int final_norm, float* hidden, void* stream) {
+  if (!c || !c->kpool) return fail(VV_ERR_STATE, "vv_lm_decode_range: KV pool not initialised");
+  if (layer_begin < 0 || layer_end > c->d.num_layers || layer_begin >= layer_end) return fail(VV_ERR_INVALID, "bad layer range [%d,%d)", layer_begin, layer_end);
+  CK(cudaSetDevice(c->device));
+  for (int s = 0; s < 2 * c->d.max_batch; ++s) RET(vv_kv_reserve(c, s, c->kv_len_host[s] + 1, stream));
+  char key[256];
+  snprintf(key, sizeof key, "lmr:%p:%p:%d:%d:%d", (const void*)embeds, (void*)hidden, layer_begin, layer_end, final_norm);
+  return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_lm_range(l, embeds, layer_begin, layer_end, final_norm, hidden); });
+}
+
 extern "C" int vv_embed_tokens(vv_ctx* c, const int32_t* tokens_host, int n, float* out, void* stream) {
   if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
   if (n < 1 || n > 16) return fail(VV_ERR_INVALID, "vv_embed_tokens: n must be in [1,16]");
