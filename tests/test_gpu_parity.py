@@ -405,6 +405,129 @@ def test_lora_assets_change_the_model_like_the_oracle_on_merged_weights(tmp_path
             model.engine.close()
 
 
+# ---- next-row features: SDE scheduler, refresh_negative=False, streaming-0.5B variant -------------------------------
+def test_sde_sampler_vs_oracle():
+    """Closed loop with the Gradio demo's scheduler (demo/gradio_demo.py:141-146).  The per-step variance noise is injected on both
+    sides (the product would otherwise draw it from the CUDA generator, the oracle from the CPU one)."""
+    from oracle import vv_oracle as O
+    from vibevoice_b200.modeling import ForcedTokenScript
+    model, cfg, tok, sd = make_model("tiny", 2)
+    try:
+        base = model.model.noise_scheduler
+        model.model.noise_scheduler = base.from_config(base.config, algorithm_type="sde-dpmsolver++", beta_schedule="squaredcos_cap_v2")
+        model.set_ddpm_inference_steps(5)
+        dc = cfg.decoder_config
+        g = torch.Generator().manual_seed(5)
+        ids = torch.randint(0, dc.vocab_size - 20, (2, 10), generator=g)
+        ids[:, -1] = tok.speech_start_id
+        scripts = [_scripted(tok, "dddesddx"), _scripted(tok, "ddddddx")]
+        pool = torch.randn(64, 5, 4, 64, generator=g)            # [frame][step][2n<=4][64]
+        frame = {"i": -1}
+
+        def step_noise_fn(i, n):
+            if i == 0:
+                frame["i"] += 1
+            return pool[frame["i"], i, :2 * n]
+        torch.manual_seed(0)
+        out = model.generate(input_ids=ids, tokenizer=tok, cfg_scale=1.3, is_prefill=False, logits_processor=[ForcedTokenScript(scripts)],
+                             max_new_tokens=20, show_progress_bar=False, _step_noise_fn=step_noise_fn)
+        # oracle: same frame noise stream (CPU global RNG), same step noise through sample_speech_tokens' hook
+        oframe = {"i": -1}
+        orig = O.sample_speech_tokens
+
+        def patched(w, pc, nc, cs, ns, noise, nl=4, eps=1e-5, trace=None, algorithm_type="dpmsolver++", step_noise=None):
+            oframe["i"] += 1
+            n = pc.shape[0]
+            return orig(w, pc, nc, cs, ns, noise, nl, eps, trace, algorithm_type, [pool[oframe["i"], i, :2 * n] for i in range(ns)])
+        O.sample_speech_tokens = patched
+        try:
+            torch.manual_seed(0)
+            ref = O.generate(sd, cfg, ids, None, tok, cfg_scale=1.3, num_steps=5, max_new_tokens=20, forced_tokens=scripts, kv_bf16=True,
+                             algorithm_type="sde-dpmsolver++")
+        finally:
+            O.sample_speech_tokens = orig
+        assert torch.equal(out.sequences, ref.sequences)
+        for r in range(2):
+            e = rel_l2(out.speech_outputs[r].cpu(), ref.speech_outputs[r])
+            report("sde_generate", row=r, audio_rel_l2=e)
+            assert e < 1e-2, (r, e)
+        # and the noise term is live: the ODE solver on the same inputs gives different audio
+        model.model.noise_scheduler = base
+        torch.manual_seed(0)
+        ode = model.generate(input_ids=ids, tokenizer=tok, cfg_scale=1.3, is_prefill=False, logits_processor=[ForcedTokenScript(scripts)],
+                             max_new_tokens=20, show_progress_bar=False)
+        assert rel_l2(ode.speech_outputs[0].cpu(), out.speech_outputs[0].cpu()) > 1e-2
+    finally:
+        model.engine.close()
+
+
+def test_refresh_negative_false_single_prompt_vs_oracle():
+    """`refresh_negative=False` (reference :503-517), one prompt with two speaker turns: the negative stream keeps every step's input
+    and is never restarted."""
+    from oracle import vv_oracle as O
+    from vibevoice_b200.modeling import ForcedTokenScript
+    model, cfg, tok, sd = make_model("tiny", 1)
+    try:
+        dc = cfg.decoder_config
+        g = torch.Generator().manual_seed(31)
+        ids = torch.randint(0, dc.vocab_size - 20, (1, 10), generator=g)
+        ids[:, -1] = tok.speech_start_id
+        script = [_scripted(tok, "ddesdddesdx")]
+        model.set_ddpm_inference_steps(5)
+        torch.manual_seed(7)
+        out = model.generate(input_ids=ids, tokenizer=tok, cfg_scale=1.3, is_prefill=False, logits_processor=[ForcedTokenScript(script)],
+                             max_new_tokens=40, show_progress_bar=False, refresh_negative=False)
+        torch.manual_seed(7)
+        ref = O.generate(sd, cfg, ids, None, tok, cfg_scale=1.3, num_steps=5, max_new_tokens=40, forced_tokens=script, kv_bf16=True,
+                         refresh_negative=False)
+        torch.manual_seed(7)
+        refreshed = O.generate(sd, cfg, ids, None, tok, cfg_scale=1.3, num_steps=5, max_new_tokens=40, forced_tokens=script, kv_bf16=True)
+        assert torch.equal(out.sequences, ref.sequences)
+        e = rel_l2(out.speech_outputs[0].cpu(), ref.speech_outputs[0])
+        moved = rel_l2(ref.speech_outputs[0], refreshed.speech_outputs[0])
+        report("refresh_negative_false", audio_rel_l2=e, differs_from_refresh_true=moved)
+        assert e < 1e-2 and moved > 10 * e, (e, moved)
+        with pytest.raises(NotImplementedError):
+            m2, _, _, _ = make_model("tiny", 2)
+            try:
+                m2.generate(input_ids=torch.cat([ids, ids]), tokenizer=tok, is_prefill=False, max_new_tokens=2, refresh_negative=False,
+                            show_progress_bar=False)
+            finally:
+                m2.engine.close()
+    finally:
+        model.engine.close()
+
+
+def test_streaming_variant_vs_oracle():
+    """SURVEY 8f-1 on the GPU: `vibevoice_b200.streaming` (vv_lm_decode_range split stack, row modes, zero-semantic connector) against
+    `oracle/vv_streaming.py`, which is pinned to the reference's own streaming generate() (tests/golden/streaming.pt)."""
+    from oracle import vv_streaming as VS
+    from vibevoice_b200 import streaming as S
+    from vibevoice_b200.configuration import preset_config
+    from vibevoice_b200.synth import synth_state_dict
+    cfg = preset_config("tiny")
+    for eos_bias, n_text, max_new in ((-0.3, 12, 40), (-6.0, 12, 30), (-6.0, 3, 7)):
+        sd = VS.streaming_state_dict(synth_state_dict(cfg, 1234, torch.bfloat16), cfg, 1, eos_bias=eos_bias)
+        m = S.VibeVoiceStreamingForConditionalGenerationInference(cfg, tts_backbone_num_hidden_layers=1)
+        m.load_state_dict(sd)
+        try:
+            m.set_ddpm_inference_steps(5)
+            g = torch.Generator().manual_seed(7)
+            prompt = torch.randint(0, 2000, (6,), generator=g)
+            text = torch.randint(0, 2000, (n_text,), generator=g)
+            torch.manual_seed(0)
+            out = m.generate(input_ids=prompt[None], tts_text_ids=text[None], neg_text_input_id=2047, cfg_scale=1.5, max_new_tokens=max_new)
+            torch.manual_seed(0)
+            ref = VS.generate_streaming(sd, cfg, 1, prompt, text, 2047, cfg_scale=1.5, num_steps=5, max_new_tokens=max_new, kv_bf16=True)
+            assert torch.equal(out.sequences, ref.sequences), (out.sequences, ref.sequences)
+            assert torch.equal(out.reach_max_step_sample, ref.reach_max_step_sample)
+            e = rel_l2(out.speech_outputs[0].cpu(), ref.speech_outputs[0])
+            report("streaming_generate", eos_bias=eos_bias, n_text=n_text, audio_rel_l2=e)
+            assert e < 1e-2, e
+        finally:
+            m.engine.close()
+
+
 @pytest.fixture(scope="module")
 def real15():
     """VibeVoice-1.5B layer shapes (H=1536, I=8960, 12/2 heads, full-size head and codec), 2 LM layers, small vocab."""

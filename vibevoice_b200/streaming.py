@@ -14,9 +14,10 @@ What differs from the multi-speaker loop (`modeling.py`), and how it maps onto t
     encoder stage is simply never launched.
 Batch size 1, like the reference (`:511`).
 
-STATUS: the host logic below is held to fixtures from the reference's own streaming generate() on the CPU through the engine stand-in
-(`tests/test_host_logic.py::test_streaming_product_host_logic_against_reference_fixture`); `vv_lm_decode_range` and this class have not
-run on a GPU yet (written after round 1's GPU budget was spent) -- `tests/gpu_pending_round2.py` holds the parity test.
+STATUS: host logic held to fixtures from the reference's own streaming generate() on the CPU through the engine stand-in
+(`tests/test_host_logic.py::test_streaming_product_host_logic_against_reference_fixture`); CUDA path vs the pinned oracle on B200
+(`tests/test_gpu_parity.py::test_streaming_variant_vs_oracle`, sequences exact, audio 4e-6).  The shipped 0.5B checkpoint has head_dim 64
+(H = 896, 14 heads), which the attention kernels (specialised for 128) do not cover yet -- `vv_create` rejects it.
 """
 from __future__ import annotations
 
