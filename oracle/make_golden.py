@@ -406,12 +406,16 @@ def gen_streaming(ns, preset="tiny"):
             nlm = m.forward_lm(input_ids=neg, attention_mask=torch.ones_like(neg), past_key_values=new(), use_cache=True, return_dict=True)
             ntts = m.forward_tts_lm(input_ids=neg, attention_mask=torch.ones_like(neg), past_key_values=new(), use_cache=True,
                                     return_dict=True, lm_last_hidden_state=nlm.last_hidden_state, tts_text_masks=torch.ones_like(neg))
+        # the caches grow inside generate(): keep what `all_prefilled_outputs` held at the call
+        dump = lambda o: dict(kv=[(l.keys.clone(), l.values.clone()) for l in o.past_key_values.layers if l.keys is not None],
+                              hidden=o.last_hidden_state.clone())
+        pref = {k: dump(v) for k, v in (("lm", lm), ("tts_lm", tts), ("neg_lm", nlm), ("neg_tts_lm", ntts))}
         torch.manual_seed(seed)
         r = m.generate(input_ids=prompt.clone(), attention_mask=torch.ones_like(prompt), tts_lm_input_ids=prompt.clone(),
                        tts_lm_attention_mask=torch.ones_like(prompt), tts_text_ids=text.clone(),
                        all_prefilled_outputs={"lm": lm, "tts_lm": tts, "neg_lm": nlm, "neg_tts_lm": ntts}, tokenizer=tok,
                        cfg_scale=cfg_scale, max_new_tokens=max_new, show_progress_bar=False, verbose=False)
-        out[name] = dict(eos_bias=eos_bias, prompt=prompt[0].clone(), text=text[0].clone(), max_new_tokens=max_new, cfg_scale=cfg_scale,
+        out[name] = dict(prefilled=pref, eos_bias=eos_bias, prompt=prompt[0].clone(), text=text[0].clone(), max_new_tokens=max_new, cfg_scale=cfg_scale,
                          seed=seed, sequences=r.sequences.clone(), reach_max=r.reach_max_step_sample.clone(),
                          audio=None if r.speech_outputs[0] is None else r.speech_outputs[0].clone())
     return out

@@ -84,6 +84,12 @@ class FakeEngine:
         self.kv[seq].truncate(n)
         self.spec[seq] = False
 
+    def kv_write(self, seq: int, layer: int, pos0: int, k: torch.Tensor, v: torch.Tensor):
+        """prefill hand-off: k, v [n_tokens, kv_heads, head_dim] for positions pos0.. of (seq, layer)"""
+        assert pos0 == 0 and k.dim() == 3
+        self.kv[seq].k[layer] = k.float().transpose(0, 1).contiguous()
+        self.kv[seq].v[layer] = v.float().transpose(0, 1).contiguous()
+
     def kv_commit(self, advance):
         assert len(advance) == 2 * self.B
         self.calls["kv_commit"] += 1

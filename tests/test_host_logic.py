@@ -360,12 +360,16 @@ def test_streaming_product_host_logic_against_reference_fixture(golden, monkeypa
     monkeypatch.setattr(m, "_new_engine", lambda: fake_engine.FakeEngine(cfg, [0, 1], 2))
     m.load_state_dict(sd)
     m.set_ddpm_inference_steps(g["num_steps"])
-    torch.manual_seed(c["seed"])
-    out = m.generate(input_ids=c["prompt"][None], tts_text_ids=c["text"][None], neg_text_input_id=g["neg_id"], cfg_scale=c["cfg_scale"],
-                     max_new_tokens=c["max_new_tokens"])
-    assert torch.equal(out.sequences, c["sequences"])
-    assert torch.equal(out.reach_max_step_sample, c["reach_max"])
-    a, b = out.speech_outputs[0], c["audio"]
-    assert (a is None) == (b is None)
-    if a is not None:
-        assert a.shape == b.shape and float((a.double() - b.double()).norm() / b.double().norm()) < 1e-5
+    from types import SimpleNamespace
+    prefilled = {k: SimpleNamespace(past_key_values=tuple(v["kv"]), last_hidden_state=v["hidden"]) for k, v in c["prefilled"].items()}
+    # prompt state from ids (fp32 throughout: 1e-5) / imported from the reference's cached-prompt format (K/V stored as bf16, like the pool)
+    for extra, tol in (({}, 1e-5), ({"all_prefilled_outputs": prefilled, "tts_lm_input_ids": c["prompt"][None]}, 5e-3)):
+        torch.manual_seed(c["seed"])
+        out = m.generate(input_ids=c["prompt"][None], tts_text_ids=c["text"][None], neg_text_input_id=g["neg_id"], cfg_scale=c["cfg_scale"],
+                         max_new_tokens=c["max_new_tokens"], **extra)
+        assert torch.equal(out.sequences, c["sequences"])
+        assert torch.equal(out.reach_max_step_sample, c["reach_max"])
+        a, b = out.speech_outputs[0], c["audio"]
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert a.shape == b.shape and float((a.double() - b.double()).norm() / b.double().norm()) < tol

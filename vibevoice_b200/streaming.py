@@ -137,11 +137,55 @@ class VibeVoiceStreamingForConditionalGenerationInference:
         eng.sync()
         return float(p[0])
 
+    def _prefill_from_ids(self, input_ids: torch.Tensor, neg_id: int):
+        """No cached prompt given: compute the four streams' prompt state through the decode kernels."""
+        eng = self.engine
+        self._lower_then_upper_text([neg_id], neg=True)
+        eng.kv_set_len(ROW_TEXT, 0)                            # the negative text stack is not used again (:527-534 only keep its kwargs)
+        with torch.cuda.stream(eng.stream):
+            neg_hidden = eng.hidden[ROW_NEG].clone()
+        self._lower_then_upper_text(input_ids.tolist())
+        with torch.cuda.stream(eng.stream):
+            eng.hidden[ROW_NEG].copy_(neg_hidden)               # conditions of the first frame: last prompt position of both TTS-LM streams
+
+    def _import_prefilled(self, outs):
+        """`all_prefilled_outputs` (:517-534; the cached voice prompts of demo/streaming_inference_from_file.py:291 carry these four
+        outputs): dict lm / tts_lm / neg_lm / neg_tts_lm of model outputs whose `past_key_values` expose per-layer key/value tensors
+        [1, kv_heads, L, head_dim] (rotated keys, as HF caches them) and whose `last_hidden_state` is [1, L, H].  K/V go to the paged
+        pool through `vv_kv_write`; the last hidden state of the two TTS-LM streams conditions the first frame."""
+        eng = self.engine
+
+        def layers_of(cache):
+            if hasattr(cache, "key_cache"):                      # transformers 4.x DynamicCache
+                return list(zip(cache.key_cache, cache.value_cache))
+            if hasattr(cache, "layers"):                         # transformers 5.x
+                return [(l.keys, l.values) for l in cache.layers if getattr(l, "keys", None) is not None]
+            return [(kv[0], kv[1]) for kv in cache]              # legacy tuple-of-tuples
+
+        def put(cache, seq: int, layer0: int, n_layers: int) -> int:
+            kvs = layers_of(cache)
+            if len(kvs) != n_layers:
+                raise ValueError("prefilled cache has %d layers, expected %d" % (len(kvs), n_layers))
+            L = int(kvs[0][0].shape[2])
+            for j, (k, v) in enumerate(kvs):
+                k = k[0].transpose(0, 1).to(device=eng.device, dtype=torch.bfloat16).contiguous()      # [L, kv_heads, head_dim]
+                v = v[0].transpose(0, 1).to(device=eng.device, dtype=torch.bfloat16).contiguous()
+                eng.kv_write(seq, layer0 + j, 0, k, v)
+            eng.kv_set_len(seq, L)
+            return L
+        put(outs["lm"].past_key_values, ROW_TEXT, 0, self.low)
+        put(outs["tts_lm"].past_key_values, ROW_POS, self.low, self.tts_layers)
+        put(outs["neg_tts_lm"].past_key_values, ROW_NEG, self.low, self.tts_layers)
+        with torch.cuda.stream(eng.stream):
+            eng.hidden[ROW_POS].copy_(outs["tts_lm"].last_hidden_state[0, -1].to(eng.device, torch.float32))
+            eng.hidden[ROW_NEG].copy_(outs["neg_tts_lm"].last_hidden_state[0, -1].to(eng.device, torch.float32))
+
     @torch.no_grad()
     def generate(self, inputs=None, tts_text_ids=None, cfg_scale: float = 1.0, audio_streamer=None, return_speech: bool = True,
                  stop_check_fn: Optional[Callable[[], bool]] = None, **kwargs) -> VibeVoiceGenerationOutput:
-        """`:412-725`.  The prompt is given as `input_ids` (the text LM's prompt) -- its KV is computed here through the same decode
-        kernels; the negative streams start from the single token `<|image_pad|>` (`:465, :475-482`)."""
+        """`:412-725`.  The prompt state comes from `all_prefilled_outputs` (the reference's cached-prompt format) when given, else it is
+        computed from `input_ids` through the same decode kernels; the negative streams start from the single token `<|image_pad|>`
+        (`:465, :475-482`)."""
         tokenizer = kwargs.pop("tokenizer", None)
         neg_id = kwargs.pop("neg_text_input_id", None)
         neg_id = int(tokenizer.convert_tokens_to_ids("<|image_pad|>") if neg_id is None else neg_id)           # :465
@@ -150,10 +194,13 @@ class VibeVoiceStreamingForConditionalGenerationInference:
             if input_ids.shape[0] != 1:
                 raise ValueError("Currently only supports batch size == 1")                       # :511
             input_ids = input_ids[0]
+        tts_ids = kwargs.pop("tts_lm_input_ids", None)          # the TTS-LM's view of the prompt (:468); equals input_ids for text prompts
+        tts_ids = input_ids if tts_ids is None else torch.as_tensor(tts_ids).cpu().long().reshape(-1)
+        kwargs.pop("tts_lm_attention_mask", None)
         text = torch.as_tensor(tts_text_ids).cpu().long().reshape(-1)
         eng = self.engine
         dc = self.config.decoder_config
-        L0 = int(input_ids.numel())
+        L0 = int(tts_ids.numel())
         if kwargs.get("max_new_tokens", None) is None:
             kwargs["max_new_tokens"] = dc.max_position_embeddings - L0                              # :472-473
         max_length = L0 + int(kwargs["max_new_tokens"])
@@ -164,15 +211,13 @@ class VibeVoiceStreamingForConditionalGenerationInference:
         for s in range(4):
             eng.kv_set_len(s, 0)
         # ---- prefill: what `all_prefilled_outputs` carries (lm / tts_lm and their negatives) ----
-        self._lower_then_upper_text([neg_id], neg=True)
-        eng.kv_set_len(ROW_TEXT, 0)                            # the negative text stack is not used again (:527-534 only keep its kwargs)
-        with torch.cuda.stream(eng.stream):
-            neg_hidden = eng.hidden[ROW_NEG].clone()
-        self._lower_then_upper_text(input_ids.tolist())
-        with torch.cuda.stream(eng.stream):
-            eng.hidden[ROW_NEG].copy_(neg_hidden)               # conditions of the first frame: last prompt position of both TTS-LM streams
+        prefilled = kwargs.pop("all_prefilled_outputs", None)
+        if prefilled is not None:
+            self._import_prefilled(prefilled)
+        else:
+            self._prefill_from_ids(input_ids, neg_id)
 
-        seq: List[int] = input_ids.tolist()
+        seq: List[int] = tts_ids.tolist()
         chunks: List[torch.Tensor] = []
         finished, reach_max, win = False, False, 0
         vae = self.config.acoustic_vae_dim
