@@ -160,6 +160,9 @@ class FakeEngine:
     def read_tokens(self):
         return self.tokens.numpy().copy(), self.logits.numpy().copy()
 
+    def lm_logits_full(self) -> torch.Tensor:
+        return self.hidden[:self.B] @ O.lm_head_weight(self.w, self.config.decoder_config).float().T
+
     def upload_frame_inputs(self, noise_rows: torch.Tensor, active_rows):
         self.noise.zero_()
         self.active.zero_()

@@ -334,7 +334,7 @@ def test_generate_do_sample_vs_oracle(tiny2):
     for seed in range(4):
         torch.manual_seed(3)
         out = model.generate(input_ids=ids, tokenizer=tok, cfg_scale=1.3, is_prefill=False, max_new_tokens=8, show_progress_bar=False,
-                             generation_config={"do_sample": True}, sample_generator=torch.Generator().manual_seed(100 + seed))
+                             generation_config={"do_sample": True, "top_k": 0}, sample_generator=torch.Generator().manual_seed(100 + seed))
         torch.manual_seed(3)
         ref = O.generate(sd, cfg, ids, None, tok, cfg_scale=1.3, num_steps=4, max_new_tokens=8, kv_bf16=True, do_sample=True,
                          sample_generator=torch.Generator().manual_seed(100 + seed))

@@ -329,7 +329,8 @@ def test_from_pretrained_reads_an_hf_checkpoint_directory(tmp_path, monkeypatch,
     for i, part in enumerate((keys[:half], keys[half:])):
         save_file({k: sd[k].contiguous() for k in part}, str(ck / ("model-%05d-of-00002.safetensors" % (i + 1))))
     monkeypatch.setattr(modeling, "Engine", fake_engine.FakeEngine)
-    m = VibeVoiceForConditionalGenerationInference.from_pretrained(str(ck), torch_dtype=torch.bfloat16, device_map="cuda:0", tokenizer=tok)
+    m = VibeVoiceForConditionalGenerationInference.from_pretrained(str(ck), torch_dtype=torch.bfloat16, device_map="cuda:0", tokenizer=tok,
+                                                                   torch_prefill=False)   # exact comparison: same prompt ingestion on both sides
     assert m.engine.finalized and m.config.decoder_config.hidden_size == cfg.decoder_config.hidden_size
     assert abs(float(m.model.speech_scaling_factor) - float(sd["model.speech_scaling_factor"])) < 1e-6
     ref = fake_engine.make_model(cfg, tok, sd, max_batch=1)

@@ -53,10 +53,12 @@ SYMBOLS = {
     "vv_kv_set_len": (_I, [_P, _I, _L, _P]),
     "vv_kv_write": (_I, [_P, _I, _I, _L, _L, _P, _P, _P]),
     "vv_kv_pages_free": (_L, [_P]),
+    "vv_kv_pages_total": (_L, [_P]),
     "vv_set_rope_inv_freq": (_I, [_P, _P, _I]),
     "vv_set_row_mode": (_I, [_P, _P, _P]),
     "vv_lm_decode": (_I, [_P, _P, _P, _P, _P, _P]),
     "vv_lm_head": (_I, [_P, _P, _P, _P, _P]),
+    "vv_lm_logits_full": (_I, [_P, _P, _P, _P]),
     "vv_lm_decode_range": (_I, [_P, _P, _I, _I, _I, _P, _P]),
     "vv_kv_commit": (_I, [_P, _P, _P]),
     "vv_kv_len": (_L, [_P, _I]),

@@ -331,13 +331,7 @@ __global__ void __launch_bounds__(256) gemv_kernel(GemvP p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// GEMV v3: same math / task mapping as gemv_kernel, but the weights are moved by the TMA engine.
-//   producer warp : cp.async.bulk (1-D bulk tensor-less TMA, SASS UBLKCP) of [rows x KT] weight slabs
-//                   into an S-stage shared-memory ring, completion signalled on `full` mbarriers;
-//                   it runs ahead across task boundaries and starts before the activations are staged,
-//                   so ~100 KB of weights are in flight per SM regardless of how short a task is.
-//   8 consumer warps: wait `full`, read their rows/k-chunks of the slab with conflict-free LDS.128,
-//                   FMA against the staged activations, release the stage on the `empty` mbarrier.
+// mbarrier / bulk-copy primitives (shared by the tcgen05 GEMM below and the weight-stream kernel in vv_stream.cuh)
 // ---------------------------------------------------------------------------------------------
 VV_DEVINL unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 VV_DEVINL void mbar_init(unsigned long long* bar, int count) {
@@ -362,196 +356,6 @@ VV_DEVINL void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsign
                ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 VV_DEVINL void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-constexpr int TMA_MAX_STAGES = 6;
-struct GemvTmaCfg { int KT; int stages; };   // slab width (elements, multiple of 256) and ring depth
-
-template <int MB>
-__global__ void __launch_bounds__(288) gemv_tma_kernel(GemvP p, GemvTmaCfg cfg) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int K = p.K, N = p.N;
-  const int Kp = (K + 255) & ~255;
-  const int WK = p.WK, WR = 8 / WK, RW = 4 * WR;
-  const int KT = cfg.KT, S = cfg.stages;
-  const int stage_elems = RW * KT;
-  bf16* ring = reinterpret_cast<bf16*>(smem_raw);                                   // [S][RW][KT]
-  float* xs = reinterpret_cast<float*>(smem_raw + (size_t)S * stage_elems * 2);     // [MB][Kp]
-  float* red = xs + MB * Kp;                                                        // [2][8][4*MB]
-  __shared__ unsigned long long full_bar[TMA_MAX_STAGES], empty_bar[TMA_MAX_STAGES];
-  __shared__ float s_inv[MB];
-  __shared__ float s_part[8];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ntasks = (N + RW - 1) / RW;
-  const int nslabs = (K + KT - 1) / KT;
-
-  if (tid == 0) {
-    for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 8); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  pdl_trigger();
-  if (warp == 8) {
-    // ===================== producer ===================== (weights only: never waits on the predecessor grid)
-    int it = 0;
-    for (int m0 = 0; m0 < p.M; m0 += MB) {
-      for (int task = blockIdx.x; task < ntasks; task += gridDim.x) {
-        for (int sl = 0; sl < nslabs; ++sl, ++it) {
-          const int st = it % S;
-          const unsigned ph = (unsigned)((it / S) & 1);
-          mbar_wait(&empty_bar[st], ph ^ 1u);
-          const int k0 = sl * KT;
-          const unsigned bytes = (unsigned)(min(KT, K - k0) * 2);
-          if (lane == 0) mbar_expect_tx(&full_bar[st], bytes * (unsigned)RW);
-          __syncwarp();
-          if (lane < RW) {
-            const int row = min(task * RW + lane, N - 1);
-            bulk_g2s(ring + (size_t)st * stage_elems + (size_t)lane * KT, p.W + (size_t)row * K + k0, bytes, &full_bar[st]);
-          }
-        }
-      }
-    }
-    return;
-  }
-
-  // ===================== consumers (warps 0..7) =====================
-  const int wr = warp / WK, wk = warp % WK;
-  const int cps = KT >> 8;               // 256-element chunks per slab
-  int it = 0;
-  pdl_wait();
-  for (int m0 = 0; m0 < p.M; m0 += MB) {
-    consumer_sync();
-    const bool need_inv = (p.pro == PRO_RMSNORM || p.pro == PRO_ADALN);
-    const int K4 = K >> 2;
-    if (need_inv) {
-      for (int m = 0; m < MB; ++m) {
-        float ss = 0.f;
-        if (m0 + m < p.M) {
-          const float4* xr = reinterpret_cast<const float4*>(p.x + p.xmap.off(m0 + m));
-          for (int q = tid; q < K4; q += 256) { const float4 v = xr[q]; ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
-        }
-        ss = warp_sum(ss);
-        if (lane == 0) s_part[warp] = ss;
-        consumer_sync();
-        if (tid == 0) {
-          float t = 0.f;
-          for (int i = 0; i < 8; ++i) t += s_part[i];
-          s_inv[m] = rsqrtf(t / (float)K + p.pro_eps);
-        }
-        consumer_sync();
-      }
-    }
-    for (int m = 0; m < MB; ++m) {
-      const bool valid = (m0 + m < p.M);
-      const float* xr = p.x + (valid ? p.xmap.off(m0 + m) : 0);
-      const float inv = need_inv ? s_inv[m] : 1.f;
-      for (int q = tid; q < (Kp >> 2); q += 256) {
-        const int k = q << 2;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid && k < K) {
-          v = *reinterpret_cast<const float4*>(xr + k);
-          if (p.pro == PRO_RMSNORM) {
-            const float4 w = *reinterpret_cast<const float4*>(p.pro_w + k);
-            v.x *= inv * w.x; v.y *= inv * w.y; v.z *= inv * w.z; v.w *= inv * w.w;
-          } else if (p.pro == PRO_ADALN) {
-            float4 w = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (p.pro_w) w = *reinterpret_cast<const float4*>(p.pro_w + k);
-            const long long o = (long long)(m0 + m) * p.pro_ld + k;
-            const float4 sc = *reinterpret_cast<const float4*>(p.pro_scale + o);
-            const float4 sh = *reinterpret_cast<const float4*>(p.pro_shift + o);
-            v.x = v.x * inv * w.x * (1.f + sc.x) + sh.x; v.y = v.y * inv * w.y * (1.f + sc.y) + sh.y;
-            v.z = v.z * inv * w.z * (1.f + sc.z) + sh.z; v.w = v.w * inv * w.w * (1.f + sc.w) + sh.w;
-          } else if (p.pro == PRO_SILU) {
-            v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
-          }
-        }
-        *reinterpret_cast<float4*>(xs + m * Kp + xs_pos(k)) = v;
-      }
-    }
-    consumer_sync();
-
-    int parity = 0;
-    for (int task = blockIdx.x; task < ntasks; task += gridDim.x, parity ^= 1) {
-      float acc[4][MB];
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int m = 0; m < MB; ++m) acc[r][m] = 0.f;
-      for (int sl = 0; sl < nslabs; ++sl, ++it) {
-        const int st = it % S;
-        mbar_wait(&full_bar[st], (unsigned)((it / S) & 1));
-        const bf16* slab = ring + (size_t)st * stage_elems + (size_t)(wr * 4) * KT;
-        const int k0 = sl * KT;
-        for (int cc = wk; cc < cps; cc += WK) {
-          const int kk = (cc << 8) + lane * 8;          // offset inside the slab
-          if (k0 + kk < K) {
-            uint4 wv[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) wv[r] = *reinterpret_cast<const uint4*>(slab + (size_t)r * KT + kk);
-            const int cg = (k0 >> 8) + cc;               // global chunk index
-            float xv[MB][8];
-#pragma unroll
-            for (int m = 0; m < MB; ++m) {
-              const float4 a = *reinterpret_cast<const float4*>(xs + m * Kp + (cg << 8) + (lane << 2));
-              const float4 b = *reinterpret_cast<const float4*>(xs + m * Kp + (cg << 8) + 128 + (lane << 2));
-              xv[m][0] = a.x; xv[m][1] = a.y; xv[m][2] = a.z; xv[m][3] = a.w;
-              xv[m][4] = b.x; xv[m][5] = b.y; xv[m][6] = b.z; xv[m][7] = b.w;
-            }
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              float wf[8];
-              bf16x8_unpack(wv[r], wf);
-#pragma unroll
-              for (int m = 0; m < MB; ++m)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[r][m] = fmaf(wf[j], xv[m][j], acc[r][m]);
-            }
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[st]);
-      }
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int m = 0; m < MB; ++m) acc[r][m] = warp_sum(acc[r][m]);
-      float* rbuf = red + parity * (8 * 4 * MB);
-      if (lane == 0) {
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int m = 0; m < MB; ++m) rbuf[warp * (4 * MB) + r * MB + m] = acc[r][m];
-      }
-      consumer_sync();
-      if (p.epi == EPI_SWIGLU) {
-        if (tid < WR * 2 * MB) {
-          const int q = tid / (2 * MB), pr = (tid / MB) % 2, m = tid % MB;
-          const int n0 = (task * WR + q) * 4 + pr * 2;
-          if (n0 + 1 < N && m0 + m < p.M) {
-            float g = 0.f, u = 0.f;
-            for (int s_ = 0; s_ < WK; ++s_) {
-              g += rbuf[(q * WK + s_) * (4 * MB) + (pr * 2) * MB + m];
-              u += rbuf[(q * WK + s_) * (4 * MB) + (pr * 2 + 1) * MB + m];
-            }
-            if (p.bias) { g += p.bias[n0]; u += p.bias[n0 + 1]; }
-            p.y[(long long)(m0 + m) * p.ldy + (n0 >> 1)] = silu_f(g) * u;
-          }
-        }
-      } else {
-        if (tid < WR * 4 * MB) {
-          const int q = tid / (4 * MB), r = (tid / MB) % 4, m = tid % MB;
-          const int n = (task * WR + q) * 4 + r;
-          if (n < N && m0 + m < p.M) {
-            float v = 0.f;
-            for (int s_ = 0; s_ < WK; ++s_) v += rbuf[(q * WK + s_) * (4 * MB) + r * MB + m];
-            if (p.bias) v += p.bias[n];
-            epi_store(p, m0 + m, n, v);
-          }
-        }
-      }
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
 // Tensor-core GEMM for the codec stages with many rows (M > 8): C[M,N] = A[M,K] * W[N,K]^T.
@@ -1161,93 +965,6 @@ __global__ void dwconv_res_kernel(const float* __restrict__ x, const float* __re
   out[idx] = x[idx] + gamma[c] * acc;
 }
 
-// Fused Block1D mixer: out = x + gamma * (bias + depthwise_causal_conv7(RMSNorm(x) * wn)) in ONE launch (replaces
-// assemble_window(norm) + dwconv_res).  grid (time tiles of MIX_TT, batch, channel slabs of MIX_CC); block 256, thread <-> one fixed
-// channel (its 7 taps, norm weight, gamma and bias are fetched BEFORE griddepcontrol.wait -- they do not depend on the producer).
-// ONE dependent global round trip: the tile's rows (6 halo rows + MIX_TT) are read once -- full rows for the sum of squares, the
-// CTA's channel slab kept in shared memory -- then norm, taps, residual and the next streaming history all come from shared memory.
-// (The first fused version read x through global memory in two dependent phases and was 3.6 us per launch slower than the two
-// kernels it replaced.)  Requires C % 256 == 0 or 256 % C == 0 (host checks; other widths use the two-kernel path).
-constexpr int MIX_TT = 8, MIX_CC = 256;
-__global__ void __launch_bounds__(256) mixer_fused_kernel(const float* __restrict__ x, const float* __restrict__ hist, float* __restrict__ hist_next,
-                                                          const float* __restrict__ wn, const float* __restrict__ w /*[7][C]*/,
-                                                          const float* __restrict__ bias, const float* __restrict__ gamma, float* __restrict__ out,
-                                                          int T, int C, float eps) {
-  __shared__ float xs[MIX_TT + 6][MIX_CC];
-  __shared__ float s_ss[MIX_TT + 6];
-  const int b = blockIdx.y, t0 = blockIdx.x * MIX_TT, t1 = min(T, t0 + MIX_TT);
-  const int nc = min(C, MIX_CC), c0 = blockIdx.z * nc;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int nrow = (t1 - t0) + 6;
-  const int ci = tid % nc, c = c0 + ci, rp = 256 / nc;          // this thread's channel; rp rows are produced per pass
-  pdl_trigger();
-  float wt[7];
-#pragma unroll
-  for (int j = 0; j < 7; ++j) wt[j] = w[j * C + c];
-  const float wnc = wn[c], gc = gamma[c], bc = bias[c];
-  if (tid < nrow) s_ss[tid] = 0.f;
-  __syncthreads();
-  pdl_wait();
-  const float* xb = x + (size_t)b * T * C;
-  const float* hb = hist + (size_t)b * 6 * C;
-  // rows before the frame (tau < 0): only this CTA's channel slab of the (already normalised) history is needed
-  const int nh = max(0, min(6, -(t0 - 6)));                       // tile rows 0 .. nh-1 come from the history
-  for (int r = tid / nc; r < nh; r += rp) xs[r][ci] = hb[(size_t)(t0 + r) * C + c];      // tau + 6 = t0 - 6 + r + 6
-  // rows inside the frame: all loads of a thread are issued back to back (no reduction in between -- a shuffle/atomic after every
-  // load serialises the L2 round trips, which made the first version of this loop 10+ us), then reduced row by row
-  if (C >= MIX_CC) {
-    const int per = C / MIX_CC;                                    // 1, 2, 4 or 8 elements of a row per thread
-    for (int r = nh; r < nrow; ++r) {
-      const float* xr = xb + (size_t)(t0 - 6 + r) * C;
-      float v[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = (k < per) ? xr[tid + k * MIX_CC] : 0.f;
-      float sq = 0.f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) sq = fmaf(v[k], v[k], sq);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) if (k < per && k == (int)blockIdx.z) xs[r][tid] = v[k];
-      sq = warp_sum(sq);
-      if (lane == 0) atomicAdd(&s_ss[r], sq);
-    }
-  } else {
-    // C < 256: a thread owns (row tid / C + k * rp, channel tid % C); at most ceil(14 / rp) <= 8 rows per thread when C >= 128 ...
-    const int r0 = nh + tid / nc;
-    for (int rb = r0; rb < nrow; rb += 8 * rp) {
-      float v[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { const int r = rb + k * rp; v[k] = (r < nrow) ? xb[(size_t)(t0 - 6 + r) * C + c] : 0.f; }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int r = rb + k * rp;
-        if (r < nrow) xs[r][ci] = v[k];
-        if ((C % 32) == 0) {                                       // the 32 lanes of a warp sit in one row
-          const float sq = warp_sum(v[k] * v[k]);
-          if (lane == 0 && r < nrow) atomicAdd(&s_ss[r], sq);
-        } else if (r < nrow) {
-          atomicAdd(&s_ss[r], v[k] * v[k]);
-        }
-      }
-    }
-  }
-  __syncthreads();
-  if (tid < nrow) s_ss[tid] = (t0 - 6 + tid >= 0) ? rsqrtf(s_ss[tid] / (float)C + eps) : 0.f;
-  __syncthreads();
-  auto nval = [&](int r) -> float { return (t0 - 6 + r < 0) ? xs[r][ci] : xs[r][ci] * s_ss[r] * wnc; };
-  for (int tl = tid / nc; tl < t1 - t0; tl += rp) {
-    float acc = bc;
-#pragma unroll
-    for (int j = 0; j < 7; ++j) acc = fmaf(wt[j], nval(tl + j), acc);
-    out[((size_t)b * T + t0 + tl) * C + c] = xs[tl + 6][ci] + gc * acc;
-  }
-  // next history = normalised rows T-6 .. T-1 (rows before the frame come from the old history, held by the first tile)
-  for (int r6 = tid / nc; r6 < 6; r6 += rp) {
-    const int tau = T - 6 + r6;
-    const bool mine = (tau >= t0 && tau < t1) || (tau < 0 && blockIdx.x == 0);
-    if (mine) hist_next[((size_t)b * 6 + r6) * C + c] = nval(tau - t0 + 6);
-  }
-}
-
 struct StateSeg { float* hist; float* next; int n; };   // n floats per batch row
 
 constexpr int ADV_SLICES = 8;     // CTAs per (segment, batch row): the widest histories (6 x 2048 floats) are a latency chain for one CTA
@@ -1732,7 +1449,7 @@ struct DpmCoef { float a0, s0, ks, kx, rinv; int order; float kn; };   // kn: pe
 __global__ void __launch_bounds__(256) dpm_update_proj_kernel(const float* __restrict__ z_in, float* __restrict__ z_out,
                                                               const float* __restrict__ x0_in, float* __restrict__ x0_out,
                                                               const float* __restrict__ v, const float* __restrict__ noise,
-                                                              const DpmCoef* __restrict__ coef, int step, float cfg,
+                                                              const DpmCoef* __restrict__ coef, int step, const float* __restrict__ cfg_p,
                                                               const bf16* __restrict__ w_noisy /*[H][64]*/, float* __restrict__ xout,
                                                               float* __restrict__ latent_out, int B, int H, int do_proj,
                                                               const float* __restrict__ step_noise) {
@@ -1746,6 +1463,7 @@ __global__ void __launch_bounds__(256) dpm_update_proj_kernel(const float* __res
       zn = noise[b * 64 + tid];                           // z_0 = CPU-RNG noise (:701)
     } else {
       const DpmCoef c = coef[step];
+      const float cfg = *cfg_p;
       const float vc = v[(size_t)b * 64 + tid], vu = v[(size_t)(B + b) * 64 + tid];
       const float vv = vu + cfg * (vc - vu);
       const float zo = z_in[b * 64 + tid];

@@ -6,11 +6,12 @@
 // sketches the C ABI this file implements.
 #include "../../include/vibevoice_b200.h"
 #include "vv_kernels.cuh"
-#include "vv_mega.cuh"
+#include "vv_stream.cuh"
 
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <initializer_list>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -82,7 +83,6 @@ struct vv_ctx {
   int device = 0;
   bool finalized = false;
   bool use_graphs = true;
-  bool use_tma = false;    // TMA-ring GEMV (gemv_tma_kernel) measured slower than the register-pipelined one; VV_TMA=1 selects it
   bool use_pdl = true;
   bool use_mma_attn = true;
   bool use_splitk = true;
@@ -93,8 +93,6 @@ struct vv_ctx {
   bool ring_rms = true;     // RMSNorm folded into gemm_mma_ring_kernel (row scale in the epilogue) instead of rows_norm_kernel (VV_NO_RING_RMS=1 -> off)
   int codec_mma_min_rows = 9;   // codec GEMMs with at least this many rows use the tensor-core ring kernel (VV_CODEC_MMA_MIN_ROWS)
   bool mma_ring = true;     // 6-stage cp.async ring for both GEMM operands (gemm_mma_ring_kernel); VV_NO_MMA_RING=1 -> old 1-ahead kernel
-  bool fuse_mixer = false, norm_in_gemm = false;   // the two halves of fuse_codec, separately selectable (VV_FUSE_MIXER / VV_NORM_IN_GEMM)
-  bool fuse_codec = false;  // fused mixer + norm-in-GEMM measured 5% slower than the separate small kernels (VV_FUSE_CODEC=1 to enable)
   bf16* head_slab = nullptr; size_t head_slab_bytes = 0; size_t l2_persist_bytes = 0; size_t l2_window_max = 0;
   int wr_tasks_min = 296;
   int wr_force = 0;
@@ -106,7 +104,7 @@ struct vv_ctx {
   float speech_scale = NAN, speech_bias = NAN;
   // LM
   std::vector<LmLayer> lm;
-  float* lm_norm = nullptr; bf16* embed = nullptr; bf16* head_valid = nullptr; int* valid_ids_dev = nullptr; float* inv_freq = nullptr;
+  float* lm_norm = nullptr; bf16* embed = nullptr; const bf16* lm_head_w = nullptr; bf16* head_valid = nullptr; int* valid_ids_dev = nullptr; float* inv_freq = nullptr;
   int Nqkv = 0;
   // head
   bf16 *h_noisy = nullptr, *h_cond = nullptr, *h_t0 = nullptr, *h_t2 = nullptr, *h_mod = nullptr, *h_final = nullptr;
@@ -120,7 +118,7 @@ struct vv_ctx {
   int64_t wbytes[6] = {0, 0, 0, 0, 0, 0};
   // KV
   int64_t n_pages = 0; int max_pages = 0; bf16 *kpool = nullptr, *vpool = nullptr;
-  int* page_table_dev = nullptr; int* page_table_host = nullptr; int* kv_len_dev = nullptr; int* row_mode_dev = nullptr;
+  int* page_table_dev = nullptr; int* kv_len_dev = nullptr; int* row_mode_dev = nullptr;
   std::vector<int64_t> kv_len_host; std::vector<std::vector<int>> seq_pages; std::vector<int> free_pages;
   // scratch
   float *s_h = nullptr, *s_qkv = nullptr, *s_qrot = nullptr, *s_attn = nullptr, *s_act = nullptr, *s_pacc = nullptr, *s_pml = nullptr;
@@ -131,10 +129,8 @@ struct vv_ctx {
   float *s_e = nullptr, *s_c1 = nullptr, *s_feat = nullptr, *s_audio = nullptr, *s_latent = nullptr;
   int* s_tok = nullptr;
   std::map<std::string, GraphEntry> graphs;
-  struct Program { Op* ops_dev = nullptr; int n_ops = 0; int smem = 0; int MB = 0; int grid = 0; };
-  std::map<std::string, Program> programs;
   GridBar* gridbar = nullptr;
-  bool use_mega = false;   // persistent program kernel (vv_mega.cuh): correct, but measured slower than kernel-per-stage graphs; VV_MEGA=1 selects it
+  float* cfg_dev = nullptr; float cfg_last = NAN;   // CFG scale lives in device memory so captured graphs do not depend on its value
   int64_t launches = 0;
   std::map<long long, int> occ_cache;
 };
@@ -210,13 +206,6 @@ static int gemv_occupancy(vv_ctx* c, int smem) {
   return occ;
 }
 
-template <int MB>
-static int launch_gemv_tma_t(const L& l, GemvP& p, GemvTmaCfg cfg, int grid, int smem) {
-  CK(cudaFuncSetAttribute(gemv_tma_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-  CK(launch_k(l, gemv_tma_kernel<MB>, dim3(grid), dim3(288), smem, p, cfg));
-  return 0;
-}
-
 // y = epi(W * pro(x) + bias); dispatches GEMV (M <= 16) or the tiled GEMM.
 static int linear(const L& l, GemvP p) {
   if (p.K % 8 != 0) return fail(VV_ERR_INVALID, "linear: K=%d not a multiple of 8", p.K);
@@ -261,25 +250,6 @@ static int linear(const L& l, GemvP p) {
   if (l.c->wr_force) WR = l.c->wr_force;
   p.WK = 8 / WR;
   const int ntasks = (p.N + 4 * WR - 1) / (4 * WR);
-  if (l.c->use_tma) {
-    // TMA-fed ring: slab = [4*WR rows][KT], ~32 KB per stage, as many stages as fit beside the staged activations
-    const int Kp = (p.K + 255) & ~255;
-    GemvTmaCfg cfg;
-    cfg.KT = std::min(Kp, 16384 / (4 * WR));
-    const int stage_bytes = 4 * WR * cfg.KT * 2;
-    const int fixed = gemv_smem_bytes(MB, p.K) + 256;
-    cfg.stages = std::min(TMA_MAX_STAGES, (215 * 1024 - fixed) / stage_bytes);
-    if (cfg.stages >= 2) {
-      const int smem_t = cfg.stages * stage_bytes + fixed;
-      const int grid_t = std::min(ntasks, l.c->sm_count);
-      switch (MB) {
-        case 1: return launch_gemv_tma_t<1>(l, p, cfg, grid_t, smem_t);
-        case 2: return launch_gemv_tma_t<2>(l, p, cfg, grid_t, smem_t);
-        case 4: return launch_gemv_tma_t<4>(l, p, cfg, grid_t, smem_t);
-        default: return launch_gemv_tma_t<8>(l, p, cfg, grid_t, smem_t);
-      }
-    }
-  }
   const int smem = gemv_smem_bytes(MB, p.K);
   int occ = MB == 1 ? gemv_occupancy<1>(l.c, smem) : MB == 2 ? gemv_occupancy<2>(l.c, smem) : MB == 4 ? gemv_occupancy<4>(l.c, smem)
                                                                                                           : gemv_occupancy<8>(l.c, smem);
@@ -299,61 +269,6 @@ static GemvP mk(const bf16* W, const float* bias, const float* x, long long ldx,
   p.W = W; p.bias = bias; p.x = x; p.xmap = dense_rows(ldx); p.y = y; p.ldy = ldy; p.M = M; p.N = N; p.K = K;
   p.pro = PRO_NONE; p.epi = EPI_NONE; p.WK = 1;
   return p;
-}
-
-// ------------------------------------------------------------------------------------------------
-// persistent program kernel (vv_mega.cuh): host side
-// ------------------------------------------------------------------------------------------------
-static void gemv_cfg(vv_ctx* c, GemvP& p) {
-  int WR = 8;
-  while (WR > 1 && (p.N + 4 * WR - 1) / (4 * WR) < 2 * c->sm_count) WR >>= 1;
-  const int nchunks = (p.K + 255) / 256;
-  while (WR < 8 && 8 / WR > nchunks) WR <<= 1;
-  p.WK = 8 / WR;
-}
-static Op op_gemv(vv_ctx* c, GemvP p, bool barrier) {
-  Op o;
-  memset(&o, 0, sizeof o);
-  o.kind = OP_GEMV; o.barrier_before = barrier ? 1 : 0;
-  gemv_cfg(c, p);
-  o.g = p;
-  return o;
-}
-template <int MB>
-static int program_occ(int smem, int* occ) {
-  CK(cudaFuncSetAttribute(program_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, program_kernel<MB>, 256, smem));
-  return 0;
-}
-// returns 1 if the program cannot run as one resident grid (caller falls back to kernel-per-stage)
-static int finish_program(vv_ctx* c, const std::vector<Op>& ops, int M, vv_ctx::Program* pr) {
-  const int MB = M <= 2 ? 2 : (M <= 4 ? 4 : 8);
-  int smem = 2 * ATT_GROUP_SMEM;
-  for (const Op& o : ops)
-    if (o.kind == OP_GEMV) smem = std::max(smem, gemv_smem_bytes(MB, o.g.K));
-  if (smem > 200 * 1024) return 1;
-  int occ = 0;
-  if (MB == 2) RET(program_occ<2>(smem, &occ)); else if (MB == 4) RET(program_occ<4>(smem, &occ)); else RET(program_occ<8>(smem, &occ));
-  if (occ < 1) return 1;
-  pr->MB = MB; pr->smem = smem; pr->grid = c->sm_count * std::min(occ, 2); pr->n_ops = (int)ops.size();
-  RET(dmalloc(c, &pr->ops_dev, ops.size(), false));
-  CK(cudaMemcpy(pr->ops_dev, ops.data(), ops.size() * sizeof(Op), cudaMemcpyHostToDevice));
-  return 0;
-}
-static int launch_program(const L& l, const vv_ctx::Program& pr) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof cfg);
-  cfg.gridDim = dim3(pr.grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = pr.smem; cfg.stream = l.s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;
-  attr[0].val.cooperative = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  const Op* ops = pr.ops_dev; int n = pr.n_ops; GridBar* gb = l.c->gridbar;
-  l.c->launches++;
-  if (pr.MB == 2) CK(cudaLaunchKernelEx(&cfg, program_kernel<2>, ops, n, gb));
-  else if (pr.MB == 4) CK(cudaLaunchKernelEx(&cfg, program_kernel<4>, ops, n, gb));
-  else CK(cudaLaunchKernelEx(&cfg, program_kernel<8>, ops, n, gb));
-  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -429,10 +344,6 @@ extern "C" int vv_create(const vv_model_desc* desc, int device, vv_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   const char* ng = getenv("VV_NO_GRAPH");
   c->use_graphs = !(ng && ng[0] == '1');
-  const char* nt = getenv("VV_TMA");
-  c->use_tma = (nt && nt[0] == '1');
-  const char* nm = getenv("VV_MEGA");
-  c->use_mega = (nm && nm[0] == '1');
   const char* na = getenv("VV_SCALAR_ATTN");
   c->use_mma_attn = !(na && na[0] == '1');
   c->wr_tasks_min = c->sm_count;      // measured (tools/bench_gemv.py): one task per SM beats two for the N=1536 shapes, neutral elsewhere
@@ -446,9 +357,6 @@ extern "C" int vv_create(const vv_model_desc* desc, int device, vv_ctx** out) {
   if (getenv("VV_NO_RING_RMS")) c->ring_rms = false;
   if (getenv("VV_CODEC_MMA_MIN_ROWS")) c->codec_mma_min_rows = atoi(getenv("VV_CODEC_MMA_MIN_ROWS"));
   else if (getenv("VV_MMA_MIN_ROWS")) c->codec_mma_min_rows = c->mma_min_rows;
-  if (getenv("VV_FUSE_CODEC")) c->fuse_codec = true;
-  c->fuse_mixer = c->fuse_codec || getenv("VV_FUSE_MIXER");
-  c->norm_in_gemm = c->fuse_codec || getenv("VV_NORM_IN_GEMM");
   const char* ns = getenv("VV_NO_SPLITK");
   c->use_splitk = !(ns && ns[0] == '1');
   const char* np = getenv("VV_NO_PDL");
@@ -465,7 +373,6 @@ extern "C" void vv_destroy(vv_ctx* c) {
   for (auto& g : c->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   for (auto& r : c->raw) if (r.second.p) cudaFree(r.second.p);
   for (void* p : c->allocs) cudaFree(p);
-  if (c->page_table_host) cudaFreeHost(c->page_table_host);
   delete c;
 }
 
@@ -714,6 +621,7 @@ extern "C" int vv_finalize_weights(vv_ctx* c) {
       RET(take_bf16(c, "lm_head.weight", {d.vocab_size, H}, &lmh, nullptr));
       table = lmh;
     }
+    c->lm_head_w = table;
     gather_rows_kernel<<<d.n_valid_ids, 256>>>(table, c->valid_ids_dev, c->head_valid, H);
     CKL();
     *wb += (int64_t)d.n_valid_ids * H * 2;
@@ -791,6 +699,7 @@ extern "C" int vv_finalize_weights(vv_ctx* c) {
     RET(dmalloc(c, &c->s_condp, (size_t)M2 * H));
     RET(dmalloc(c, &c->s_call, (size_t)NS * M2 * H));
     RET(dmalloc(c, &c->s_mod, (size_t)NS * M2 * modrows));
+    RET(dmalloc(c, &c->cfg_dev, 4));
     RET(dmalloc(c, &c->gridbar, 2));
     RET(dmalloc(c, &c->s_hx, (size_t)M2 * H));
     RET(dmalloc(c, &c->s_hg, (size_t)M2 * F));
@@ -941,46 +850,85 @@ static int run_cached(vv_ctx* c, const std::string& key, cudaStream_t s, F&& enq
 // ------------------------------------------------------------------------------------------------
 // KV pages
 // ------------------------------------------------------------------------------------------------
+template <class T>
+static void dfree(vv_ctx* c, T** p) {
+  if (!*p) return;
+  auto it = std::find(c->allocs.begin(), c->allocs.end(), (void*)*p);
+  if (it != c->allocs.end()) c->allocs.erase(it);
+  cudaFree(*p);
+  *p = nullptr;
+}
+static void drop_graphs(vv_ctx* c, std::initializer_list<const char*> prefixes) {
+  for (auto it = c->graphs.begin(); it != c->graphs.end();) {
+    bool hit = false;
+    for (const char* pre : prefixes) hit = hit || it->first.rfind(pre, 0) == 0;
+    if (hit) { cudaGraphExecDestroy(it->second.exec); it = c->graphs.erase(it); }
+    else ++it;
+  }
+}
+
+// (Re-)size the page pool.  Calling it again drops every sequence (lengths 0, all pages free) and re-allocates the pool, so a
+// long-lived service can grow the cache between generate() calls; captured LM graphs bake the pool pointers and are re-captured.
 extern "C" int vv_kv_init(vv_ctx* c, int64_t n_pages) {
   if (!c || !c->finalized) return fail(VV_ERR_STATE, "vv_kv_init before vv_finalize_weights");
-  if (c->kpool) return fail(VV_ERR_STATE, "KV pool already initialised");
+  if (n_pages < 2 * c->d.max_batch) return fail(VV_ERR_INVALID, "vv_kv_init: need at least one page per sequence (%d)", 2 * c->d.max_batch);
   CK(cudaSetDevice(c->device));
+  if (c->kpool) {
+    CK(cudaDeviceSynchronize());
+    dfree(c, &c->kpool); dfree(c, &c->vpool); dfree(c, &c->page_table_dev);
+    drop_graphs(c, {"lm:", "lmr:", "frame:"});
+    std::fill(c->kv_len_host.begin(), c->kv_len_host.end(), 0);
+    for (auto& pg : c->seq_pages) pg.clear();
+  }
   const auto& d = c->d;
-  const size_t per_layer = (size_t)n_pages * d.num_kv_heads * KV_PAGE * HD;
+  const size_t per_layer = (size_t)n_pages * d.num_kv_heads * KV_PAGE * d.head_dim;
   RET(dmalloc(c, &c->kpool, per_layer * d.num_layers));
   RET(dmalloc(c, &c->vpool, per_layer * d.num_layers));
   c->n_pages = n_pages;
   c->max_pages = (int)n_pages;
   const size_t nt = (size_t)2 * d.max_batch * c->max_pages;
   RET(dmalloc(c, &c->page_table_dev, nt));
-  CK(cudaMallocHost(&c->page_table_host, nt * sizeof(int)));
-  memset(c->page_table_host, 0, nt * sizeof(int));
   c->free_pages.clear();
   for (int i = (int)n_pages - 1; i >= 0; --i) c->free_pages.push_back(i);
   return 0;
 }
 extern "C" int64_t vv_kv_pages_free(vv_ctx* c) { return c ? (int64_t)c->free_pages.size() : -1; }
+extern "C" int64_t vv_kv_pages_total(vv_ctx* c) { return c ? c->n_pages : -1; }
 extern "C" int64_t vv_kv_len(vv_ctx* c, int seq) { return (c && seq >= 0 && seq < (int)c->kv_len_host.size()) ? c->kv_len_host[seq] : -1; }
+
+// page-table entries travel BY VALUE in the launch arguments: pages return to the free list when a sequence shrinks, so an entry can be
+// rewritten while copies of its previous value are still queued on the stream -- an asynchronous copy out of a host mirror would race
+struct PageVals { int v[32]; };
+__global__ void page_table_set_kernel(int* dst, PageVals pv, int n) { if ((int)threadIdx.x < n) dst[threadIdx.x] = pv.v[threadIdx.x]; }
 
 extern "C" int vv_kv_reserve(vv_ctx* c, int seq, int64_t n_tokens, void* stream) {
   if (!c || !c->kpool) return fail(VV_ERR_STATE, "KV pool not initialised");
   if (seq < 0 || seq >= 2 * c->d.max_batch) return fail(VV_ERR_INVALID, "bad seq %d", seq);
   auto& pg = c->seq_pages[seq];
   const int64_t needp = (n_tokens + KV_PAGE - 1) / KV_PAGE;
-  const size_t first = pg.size();
+  if (needp > c->max_pages) return fail(VV_ERR_NOMEM, "KV page pool too small (seq %d needs %lld pages of %d)", seq, (long long)needp, c->max_pages);
+  size_t first = pg.size();
   while ((int64_t)pg.size() < needp) {
     if (c->free_pages.empty()) return fail(VV_ERR_NOMEM, "KV page pool exhausted (seq %d needs %lld pages)", seq, (long long)needp);
-    int p = c->free_pages.back();
+    pg.push_back(c->free_pages.back());
     c->free_pages.pop_back();
-    c->page_table_host[(size_t)seq * c->max_pages + pg.size()] = p;
-    pg.push_back(p);
   }
-  if (pg.size() > first) {
-    const size_t o = (size_t)seq * c->max_pages + first;
-    CK(cudaMemcpyAsync(c->page_table_dev + o, c->page_table_host + o, (pg.size() - first) * sizeof(int), cudaMemcpyHostToDevice,
-                       (cudaStream_t)stream));
+  while (first < pg.size()) {
+    PageVals pv;
+    const int n = (int)std::min<size_t>(32, pg.size() - first);
+    for (int i = 0; i < 32; ++i) pv.v[i] = i < n ? pg[first + i] : 0;
+    page_table_set_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(c->page_table_dev + (size_t)seq * c->max_pages + first, pv, n);
+    CKL();
+    c->launches++;
+    first += n;
   }
   return 0;
+}
+// pages beyond the new length go back to the free list (a negative stream restarts at every <speech_start>; a server reuses rows)
+static void release_pages(vv_ctx* c, int seq, int64_t len) {
+  auto& pg = c->seq_pages[seq];
+  const size_t keep = (size_t)((len + KV_PAGE - 1) / KV_PAGE);
+  while (pg.size() > keep) { c->free_pages.push_back(pg.back()); pg.pop_back(); }
 }
 
 struct Lens { int v[16]; };
@@ -998,7 +946,9 @@ static int push_lens(vv_ctx* c, cudaStream_t s) {
 extern "C" int vv_kv_set_len(vv_ctx* c, int seq, int64_t len, void* stream) {
   if (!c || !c->kpool) return fail(VV_ERR_STATE, "KV pool not initialised");
   if (seq < 0 || seq >= 2 * c->d.max_batch) return fail(VV_ERR_INVALID, "bad seq %d", seq);
+  if (len < 0 || len > (int64_t)c->seq_pages[seq].size() * KV_PAGE) return fail(VV_ERR_INVALID, "vv_kv_set_len: %lld outside the reserved range of seq %d", (long long)len, seq);
   c->kv_len_host[seq] = len;
+  release_pages(c, seq, len);
   return push_lens(c, (cudaStream_t)stream);
 }
 extern "C" int vv_kv_commit(vv_ctx* c, const int32_t* adv, void* stream) {
@@ -1119,74 +1069,28 @@ static int enqueue_lm_range(const L& l, const float* embeds, int li0, int li1, i
   return 0;
 }
 
-static int build_lm_program(vv_ctx* c, const float* embeds, float* hidden, float* logits, int32_t* tokens, vv_ctx::Program* pr) {
-  const auto& d = c->d;
-  const int H = d.hidden_size, I = d.intermediate_size, M = 2 * d.max_batch, nq = d.num_q_heads * HD;
-  const size_t per_layer = (size_t)c->n_pages * d.num_kv_heads * KV_PAGE * HD;
-  std::vector<Op> ops;
-  for (int li = 0; li < d.num_layers; ++li) {
-    const LmLayer& y = c->lm[li];
-    const float* xin = li == 0 ? embeds : c->s_h;          // layer 0 reads the caller's embeddings; the residual stream lives in s_h
-    GemvP p = mk(y.wqkv, y.bqkv, xin, H, c->s_qkv, c->Nqkv, M, c->Nqkv, H);
-    p.pro = PRO_RMSNORM; p.pro_w = y.ln1; p.pro_eps = d.rms_norm_eps;
-    ops.push_back(op_gemv(c, p, li > 0));
-    Op a;
-    memset(&a, 0, sizeof a);
-    a.kind = OP_ATTN; a.barrier_before = 1;
-    a.a.qkv = c->s_qkv;
-    a.a.kv.kpool = c->kpool + per_layer * li; a.a.kv.vpool = c->vpool + per_layer * li;
-    a.a.kv.page_table = c->page_table_dev; a.a.kv.max_pages = c->max_pages; a.a.kv.kv_len = c->kv_len_dev; a.a.kv.row_mode = c->row_mode_dev;
-    a.a.kv.kv_heads = d.num_kv_heads; a.a.kv.q_heads = d.num_q_heads;
-    a.a.part_acc = c->s_pacc; a.a.part_ml = c->s_pml; a.a.attn_out = c->s_attn; a.a.inv_freq = c->inv_freq;
-    a.a.nsplit = c->nsplit; a.a.M = M; a.a.scale = 1.0f / sqrtf((float)HD);
-    ops.push_back(a);
-    a.kind = OP_COMBINE;
-    ops.push_back(a);
-    p = mk(y.wo, nullptr, c->s_attn, nq, c->s_h, H, M, H, nq);
-    p.epi = EPI_RESID; p.res = xin; p.ldres = H;
-    ops.push_back(op_gemv(c, p, true));
-    p = mk(y.wgu, nullptr, c->s_h, H, c->s_act, I, M, 2 * I, H);
-    p.pro = PRO_RMSNORM; p.pro_w = y.ln2; p.pro_eps = d.rms_norm_eps; p.epi = EPI_SWIGLU;
-    ops.push_back(op_gemv(c, p, true));
-    p = mk(y.wdown, nullptr, c->s_act, I, c->s_h, H, M, H, I);
-    p.epi = EPI_RESID; p.res = c->s_h; p.ldres = H;
-    ops.push_back(op_gemv(c, p, true));
-  }
-  Op f;
-  memset(&f, 0, sizeof f);
-  f.kind = OP_FINAL; f.barrier_before = 1;
-  f.f.h = c->s_h; f.f.norm_w = c->lm_norm; f.f.hidden = hidden; f.f.w_valid = c->head_valid; f.f.valid_ids = c->valid_ids_dev;
-  f.f.logits = logits; f.f.tokens = tokens; f.f.M = M; f.f.B = d.max_batch; f.f.H = H; f.f.n_valid = d.n_valid_ids; f.f.eps = d.rms_norm_eps;
-  ops.push_back(f);
-  return finish_program(c, ops, M, pr);
-}
-
 extern "C" int vv_lm_decode(vv_ctx* c, const float* embeds, float* hidden, float* logits, int32_t* tokens, void* stream) {
   if (!c || !c->kpool) return fail(VV_ERR_STATE, "vv_lm_decode: KV pool not initialised");
   CK(cudaSetDevice(c->device));
   for (int s = 0; s < 2 * c->d.max_batch; ++s) RET(vv_kv_reserve(c, s, c->kv_len_host[s] + 1, stream));
   char key[256];
   snprintf(key, sizeof key, "lm:%p:%p:%p:%p", (const void*)embeds, (void*)hidden, (void*)logits, (void*)tokens);
-  if (c->use_mega) {
-    auto it = c->programs.find(key);
-    if (it == c->programs.end()) {
-      vv_ctx::Program pr;
-      int r = build_lm_program(c, embeds, hidden, logits, tokens, &pr);
-      if (r < 0) return r;
-      if (r == 1) pr.n_ops = 0;                 // does not fit as one resident grid: kernel-per-stage path below
-      it = c->programs.emplace(key, pr).first;
-    }
-    if (it->second.n_ops > 0) {
-      L l{c, (cudaStream_t)stream};
-      return launch_program(l, it->second);
-    }
-  }
   return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_lm_decode(l, embeds, hidden, logits, tokens); });
 }
 extern "C" int vv_lm_head(vv_ctx* c, const float* hidden, float* logits, int32_t* tokens, void* stream) {
   if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
   L l{c, (cudaStream_t)stream};
   return enqueue_lm_head(l, hidden, logits, tokens);
+}
+// Full-vocabulary logits for the positive rows: only needed when the caller installs its own LogitsProcessor objects or samples with
+// top-k / top-p warpers, which rank the whole vocabulary BEFORE the token constraint (modeling_vibevoice_inference.py:310-319, 488-490).
+// One GEMV over the (tied) embedding / lm_head matrix; the default path never calls this (it computes the <= 5 surviving logits only).
+extern "C" int vv_lm_logits_full(vv_ctx* c, const float* hidden, float* logits_out, void* stream) {
+  if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
+  CK(cudaSetDevice(c->device));
+  L l{c, (cudaStream_t)stream};
+  GemvP p = mk(c->lm_head_w, nullptr, hidden, c->d.hidden_size, logits_out, c->d.vocab_size, c->d.max_batch, c->d.vocab_size, c->d.hidden_size);
+  return linear(l, p);
 }
 struct Toks { int v[16]; };
 __global__ void embed_gather_val_kernel(const bf16* __restrict__ table, Toks t, float* __restrict__ out, int H) {
@@ -1230,10 +1134,7 @@ extern "C" int vv_set_diffusion_steps_sde(vv_ctx* c, int n_steps, const float* t
 extern "C" int vv_set_step_noise(vv_ctx* c, const float* step_noise) {
   if (!c) return fail(VV_ERR_INVALID, "null ctx");
   if (c->step_noise != step_noise) {            // captured graphs hold the old pointer
-    for (auto it = c->graphs.begin(); it != c->graphs.end();) {
-      if (it->first.rfind("tail:", 0) == 0 || it->first.rfind("diff:", 0) == 0) { cudaGraphExecDestroy(it->second.exec); it = c->graphs.erase(it); }
-      else ++it;
-    }
+    drop_graphs(c, {"tail:", "diff:", "frame:"});
   }
   c->step_noise = step_noise;
   return 0;
@@ -1241,7 +1142,6 @@ extern "C" int vv_set_step_noise(vv_ctx* c, const float* step_noise) {
 static int set_diffusion_steps(vv_ctx* c, int n_steps, const float* timesteps, const float* coef, int ncol, void* stream) {
   if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
   if (n_steps < 1 || n_steps > c->d.max_diffusion_steps) return fail(VV_ERR_INVALID, "n_steps %d outside [1,%d]", n_steps, c->d.max_diffusion_steps);
-  if (ncol == 7 && c->use_mega) return fail(VV_ERR_INVALID, "sde-dpmsolver++ is not available in the persistent program kernel (VV_MEGA)");
   CK(cudaSetDevice(c->device));
   cudaStream_t s = (cudaStream_t)stream;
   const int H = c->d.hidden_size;
@@ -1267,10 +1167,7 @@ static int set_diffusion_steps(vv_ctx* c, int n_steps, const float* timesteps, c
   CK(cudaStreamSynchronize(s));
   c->n_steps = n_steps;
   // programs captured with another step count are stale
-  for (auto it = c->graphs.begin(); it != c->graphs.end();) {
-    if (it->first.rfind("tail:", 0) == 0 || it->first.rfind("diff:", 0) == 0) { cudaGraphExecDestroy(it->second.exec); it = c->graphs.erase(it); }
-    else ++it;
-  }
+  drop_graphs(c, {"tail:", "diff:", "frame:"});
   return 0;
 }
 
@@ -1296,38 +1193,19 @@ static void head_step_gemvs(vv_ctx* c, int i, std::vector<GemvP>* out) {
   p.pro_shift = mod + (size_t)LH * 3 * H; p.pro_scale = mod + (size_t)LH * 3 * H + H; p.pro_ld = modld;
   out->push_back(p);
 }
-static DpmOp dpm_op(vv_ctx* c, int i, const float* noise, float cfg, float* latent_out) {
-  const int B = c->d.max_batch, N = c->n_steps;
-  DpmOp o;
-  memset(&o, 0, sizeof o);
-  if (i < 0) { o.z_in = c->s_z + B * 64; o.z_out = c->s_z; o.x0_in = c->s_x0 + B * 64; o.x0_out = c->s_x0; }
-  else {
-    o.z_in = c->s_z + (size_t)(i & 1) * B * 64; o.z_out = c->s_z + (size_t)((i + 1) & 1) * B * 64;
-    o.x0_in = c->s_x0 + (size_t)(i & 1) * B * 64; o.x0_out = c->s_x0 + (size_t)((i + 1) & 1) * B * 64;
-  }
-  const bool last = (i == N - 1);
-  o.v = c->s_v; o.noise = noise; o.coef = c->coef_dev; o.w_noisy = c->h_noisy; o.xout = c->s_hx; o.latent_out = last ? latent_out : nullptr;
-  o.step = i; o.B = B; o.H = c->d.hidden_size; o.do_proj = last ? 0 : 1; o.cfg = cfg;
-  return o;
-}
-static int build_sampler_program(vv_ctx* c, const float* noise, float cfg, float* latent_out, vv_ctx::Program* pr) {
-  std::vector<Op> ops;
-  Op o;
-  memset(&o, 0, sizeof o);
-  o.kind = OP_DPM; o.barrier_before = 0; o.d = dpm_op(c, -1, noise, cfg, latent_out);
-  ops.push_back(o);
-  for (int i = 0; i < c->n_steps; ++i) {
-    std::vector<GemvP> g;
-    head_step_gemvs(c, i, &g);
-    for (auto& p : g) ops.push_back(op_gemv(c, p, true));
-    memset(&o, 0, sizeof o);
-    o.kind = OP_DPM; o.barrier_before = 1; o.d = dpm_op(c, i, noise, cfg, latent_out);
-    ops.push_back(o);
-  }
-  return finish_program(c, ops, 2 * c->d.max_batch, pr);
+__global__ void set_float_kernel(float* p, float v) { *p = v; }
+// the CFG scale is read from device memory by the solver kernels, so one captured graph serves every value (a service with a
+// user-controlled cfg_scale would otherwise capture and keep one frame-tail graph per distinct float)
+static int set_cfg(vv_ctx* c, float cfg, cudaStream_t s) {
+  if (memcmp(&cfg, &c->cfg_last, sizeof(float)) == 0) return 0;
+  set_float_kernel<<<1, 1, 0, s>>>(c->cfg_dev, cfg);
+  CKL();
+  c->launches++;
+  c->cfg_last = cfg;
+  return 0;
 }
 
-static int enqueue_diffusion(const L& l, const float* cond, const float* noise, float cfg, float* latent_out, const vv_ctx::Program* prog) {
+static int enqueue_diffusion(const L& l, const float* cond, const float* noise, float* latent_out) {
   vv_ctx* c = l.c;
   const auto& d = c->d;
   const int H = d.hidden_size, B = d.max_batch, M = 2 * B, LH = d.head_layers, N = c->n_steps;
@@ -1344,9 +1222,8 @@ static int enqueue_diffusion(const L& l, const float* cond, const float* noise, 
   // (the reference recomputes Linear(silu(c)) inside every head call, diffusion_head.py:159, 185; c depends only on (cond, t_i))
   p = mk(c->h_mod, nullptr, c->s_call, H, c->s_mod, modld, N * M, modld, H);
   RET(linear(l, p));
-  if (prog && prog->n_ops > 0) return launch_program(l, *prog);
   CK(launch_k(l, dpm_update_proj_kernel, dim3(B, (H + 255) / 256), dim3(256), 0, c->s_z + B * 64, c->s_z, c->s_x0 + B * 64, c->s_x0, c->s_v, noise,
-              c->coef_dev, -1, cfg, c->h_noisy, c->s_hx, nullptr, B, H, 1, (const float*)nullptr));
+              c->coef_dev, -1, (const float*)c->cfg_dev, c->h_noisy, c->s_hx, nullptr, B, H, 1, (const float*)nullptr));
   L lh = l;
   if (c->l2_persist_bytes && c->head_slab_bytes) {
     lh.win_base = c->head_slab;
@@ -1358,27 +1235,12 @@ static int enqueue_diffusion(const L& l, const float* cond, const float* noise, 
     head_step_gemvs(c, i, &g);
     for (auto& q : g) RET(linear(lh, q));
     const bool last = (i == N - 1);
-    const DpmOp o = dpm_op(c, i, noise, cfg, latent_out);
-    CK(launch_k(l, dpm_update_proj_kernel, dim3(B, last ? 1 : (H + 255) / 256), dim3(256), 0, o.z_in, o.z_out, o.x0_in, o.x0_out, o.v, noise, o.coef, i,
-                cfg, o.w_noisy, o.xout, o.latent_out, B, H, o.do_proj, c->sde ? c->step_noise : (const float*)nullptr));
+    const float* z_in = c->s_z + (size_t)(i & 1) * B * 64; float* z_out = c->s_z + (size_t)((i + 1) & 1) * B * 64;
+    const float* x0_in = c->s_x0 + (size_t)(i & 1) * B * 64; float* x0_out = c->s_x0 + (size_t)((i + 1) & 1) * B * 64;
+    CK(launch_k(l, dpm_update_proj_kernel, dim3(B, last ? 1 : (H + 255) / 256), dim3(256), 0, z_in, z_out, x0_in, x0_out, (const float*)c->s_v, noise,
+                (const DpmCoef*)c->coef_dev, i, (const float*)c->cfg_dev, (const bf16*)c->h_noisy, c->s_hx, last ? latent_out : (float*)nullptr, B, H,
+                last ? 0 : 1, c->sde ? c->step_noise : (const float*)nullptr));
   }
-  return 0;
-}
-
-static int sampler_program(vv_ctx* c, const float* noise, float cfg, float* latent_out, const vv_ctx::Program** out) {
-  *out = nullptr;
-  if (!c->use_mega) return 0;
-  char key[256];
-  snprintf(key, sizeof key, "samp:%p:%p:%a:%d", (const void*)noise, (void*)latent_out, cfg, c->n_steps);
-  auto it = c->programs.find(key);
-  if (it == c->programs.end()) {
-    vv_ctx::Program pr;
-    int r = build_sampler_program(c, noise, cfg, latent_out, &pr);
-    if (r < 0) return r;
-    if (r == 1) pr.n_ops = 0;
-    it = c->programs.emplace(key, pr).first;
-  }
-  *out = &it->second;
   return 0;
 }
 
@@ -1387,11 +1249,10 @@ extern "C" int vv_diffusion_sample(vv_ctx* c, const float* cond, const float* no
   (void)active;   // rows are independent; inactive rows are computed and ignored (static shapes keep the program graph-replayable)
   if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
   CK(cudaSetDevice(c->device));
+  RET(set_cfg(c, cfg, (cudaStream_t)stream));
   char key[256];
-  snprintf(key, sizeof key, "diff:%p:%p:%p:%a", (const void*)cond, (const void*)noise, (void*)latent_out, cfg);
-  const vv_ctx::Program* prog = nullptr;
-  RET(sampler_program(c, noise, cfg, latent_out, &prog));
-  return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_diffusion(l, cond, noise, cfg, latent_out, prog); });
+  snprintf(key, sizeof key, "diff:%p:%p:%p", (const void*)cond, (const void*)noise, (void*)latent_out);
+  return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_diffusion(l, cond, noise, latent_out); });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1409,15 +1270,13 @@ static int assemble(const L& l, const float* src, const float* hist, float* win,
 static int enqueue_block(const L& l, const Block& b, const float* xin, float* xout, int B, int T, float eps) {
   vv_ctx* c = l.c;
   const int C = b.C, M = B * T;
-  if (c->fuse_mixer && (C >= MIX_CC ? C % MIX_CC == 0 : MIX_CC % C == 0)) {
-    CK(launch_k(l, mixer_fused_kernel, dim3((T + MIX_TT - 1) / MIX_TT, B, (C + MIX_CC - 1) / MIX_CC), dim3(256), 0, xin, b.hist, b.next, b.norm_w, b.dw_w, b.dw_b, b.gamma, xout, T, C, eps));
-  } else {
-    RET(assemble(l, xin, b.hist, c->s_win, b.next, B, T, 6, C, b.norm_w, eps, 1.f, 0.f));
+  RET(assemble(l, xin, b.hist, c->s_win, b.next, B, T, 6, C, b.norm_w, eps, 1.f, 0.f));
+  {
     const long long n = (long long)M * C;
     CK(launch_k(l, dwconv_res_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, xin, c->s_win, b.dw_w, b.dw_b, b.gamma, xout, B, T, C));
   }
   GemvP p;
-  if (M < c->mma_min_rows || c->norm_in_gemm || (c->ring_rms && c->mma_ring && C <= MR_MAXK_NORM && c->use_tc5 != 2)) {
+  if (M < c->mma_min_rows || (c->ring_rms && c->mma_ring && C <= MR_MAXK_NORM && c->use_tc5 != 2)) {
     p = mk(b.w1, b.b1, xout, C, c->s_u, 4 * C, M, 4 * C, C);
     p.pro = PRO_RMSNORM; p.pro_w = b.ffn_norm_w; p.pro_eps = eps; p.epi = EPI_GELU;
     RET(linear(l, p));
@@ -1555,12 +1414,11 @@ extern "C" int vv_frame_tail(vv_ctx* c, const float* hidden, const float* noise,
   if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
   CK(cudaSetDevice(c->device));
   char key[320];
-  snprintf(key, sizeof key, "tail:%p:%p:%p:%p:%p:%p:%a", (const void*)hidden, (const void*)noise, (const void*)active, (void*)latent_out,
-           (void*)audio_out, (void*)embeds, cfg);
-  const vv_ctx::Program* prog = nullptr;
-  RET(sampler_program(c, noise, cfg, latent_out, &prog));
+  RET(set_cfg(c, cfg, (cudaStream_t)stream));
+  snprintf(key, sizeof key, "tail:%p:%p:%p:%p:%p:%p", (const void*)hidden, (const void*)noise, (const void*)active, (void*)latent_out,
+           (void*)audio_out, (void*)embeds);
   return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) {
-    RET(enqueue_diffusion(l, hidden, noise, cfg, latent_out, prog));
+    RET(enqueue_diffusion(l, hidden, noise, latent_out));
     RET(enqueue_decode(l, latent_out, active, audio_out));
     RET(enqueue_encode(l, audio_out, active, c->s_feat));
     return enqueue_connect(l, latent_out, c->s_feat, active, embeds);

@@ -222,6 +222,16 @@ class Engine:
         N.check(self.lib.vv_lm_head(self.h, C.c_void_p(hidden.data_ptr()), C.c_void_p(self.logits.data_ptr()),
                                     C.c_void_p(self.tokens.data_ptr()), self.s), "vv_lm_head")
 
+    def lm_logits_full(self) -> torch.Tensor:
+        """[B, vocab] fp32 logits of the positive rows from the current `hidden` (device tensor, valid after the call returns)."""
+        if getattr(self, "_logits_full", None) is None:
+            with torch.cuda.device(self.device):
+                self._logits_full = torch.zeros(self.B, self.config.decoder_config.vocab_size, dtype=torch.float32, device=self.device)
+        N.check(self.lib.vv_lm_logits_full(self.h, C.c_void_p(self.hidden.data_ptr()), C.c_void_p(self._logits_full.data_ptr()), self.s),
+                "vv_lm_logits_full")
+        self.stream.synchronize()
+        return self._logits_full
+
     def read_tokens(self):
         """device -> pinned host, synchronising the engine stream (the one host sync per frame)."""
         with torch.cuda.stream(self.stream):

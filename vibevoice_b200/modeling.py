@@ -65,6 +65,45 @@ def sample_valid_tokens(logits_valid, valid_ids, generator=None) -> np.ndarray:
     return np.asarray(valid_ids, dtype=np.int64)[idx.numpy()]
 
 
+class WeightModule:
+    """Stand-in for an `nn.Module` of the reference's module tree whose parameters live, packed, inside the engine:
+    `model.model.prediction_head`, `.acoustic_connector`, `.semantic_connector`.  The reference's fine-tuning loader only ever calls
+    `load_state_dict(sd, strict=False)` and `.to(device)` on them (`lora_loading.py:57-66, 104-112, 163-169`); both work here --
+    a loaded state dict is folded into the checkpoint stream and the engine re-packs its weights.  PEFT wrapping (`PeftModel.from_pretrained`
+    on these objects, lora_loading.py:88-91, 129-137) needs real `nn.Linear` modules and is served by `lora.load_lora_assets` instead,
+    which merges the adapter pairs into the base matrices."""
+
+    def __init__(self, owner: "VibeVoiceForConditionalGenerationInference", prefix: str):
+        self._owner, self._prefix = owner, prefix
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        repl = {self._prefix + k: v for k, v in state_dict.items()}
+        known = set(self._owner._tensor_names(self._prefix))
+        unexpected = sorted(k[len(self._prefix):] for k in repl if k not in known)
+        missing = sorted(k[len(self._prefix):] for k in known if k not in repl)
+        if strict and (missing or unexpected):
+            raise RuntimeError("Error(s) in loading state_dict: missing %s, unexpected %s" % (missing, unexpected))
+        repl = {k: v for k, v in repl.items() if k in known}
+
+        def transform(items):
+            for name, t in items:
+                yield name, (repl[name] if name in repl else t)
+        self._owner._reload_with(transform)
+        return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
+
+    def state_dict(self):
+        return {k[len(self._prefix):]: v for k, v in self._owner._weights_source() if k.startswith(self._prefix)}
+
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
+    def parameters(self):
+        return iter(())
+
+
 class VibeVoiceForConditionalGenerationInference:
     def __init__(self, config: VibeVoiceConfig, tokenizer_ids=None, max_batch: int = 1, device: int = 0,
                  max_diffusion_steps: int = 64, torch_prefill: bool = False):
@@ -88,8 +127,16 @@ class VibeVoiceForConditionalGenerationInference:
         # attribute surface other reference code pokes at (demo/inference_from_file.py:367-368, gradio_demo.py:142-146)
         self.model = SimpleNamespace(
             language_model=SimpleNamespace(config=config.decoder_config),
-            noise_scheduler=None, prediction_head=None, acoustic_connector=None, semantic_connector=None,
+            noise_scheduler=None,
+            prediction_head=WeightModule(self, "model.prediction_head."),
+            acoustic_connector=WeightModule(self, "model.acoustic_connector."),
+            semantic_connector=WeightModule(self, "model.semantic_connector."),
             speech_scaling_factor=torch.tensor(float("nan")), speech_bias_factor=torch.tensor(float("nan")))
+        if not hasattr(config.decoder_config, "_attn_implementation"):
+            try:
+                config.decoder_config._attn_implementation = "b200_paged_split_kv"     # read at demo/inference_from_file.py:367-368
+            except Exception:
+                pass
 
     # ---- construction ---------------------------------------------------------------------------------
     def _ensure_engine(self, valid_ids):
@@ -97,6 +144,14 @@ class VibeVoiceForConditionalGenerationInference:
             self.engine = Engine(self.config, valid_ids, self._max_batch, self._device_index, self._max_steps)
             self.model.noise_scheduler = self.engine.scheduler
         return self.engine
+
+    def _tensor_names(self, prefix: str) -> List[str]:
+        from .synth import param_specs
+        return [n for n, _, _ in param_specs(self.config) if n.startswith(prefix)]
+
+    def parameters(self):
+        """`next(model.parameters()).device` is how the reference's adapter loader finds the device (lora_loading.py:160)."""
+        yield torch.empty(0, dtype=self.dtype, device=self.device)
 
     @staticmethod
     def _valid_ids(tok) -> List[int]:
@@ -141,16 +196,21 @@ class VibeVoiceForConditionalGenerationInference:
                         max_batch: int = 1, **kw):
         """HF checkpoint directory (config.json + *.safetensors), as `demo/inference_from_file.py:295-332` calls it.
         `torch_dtype` / `attn_implementation` are accepted for drop-in compatibility; storage is bf16 and attention is
-        the built-in paged split-KV kernel."""
+        the built-in paged split-KV kernel.  The prompt prefill and the voice-prompt encoder (a-9) are enabled by default, so the
+        demo's `generate(**inputs, is_prefill=True)` works on the returned object; `torch_prefill=False` drops the second (bf16) copy of the
+        LM weights that prefill keeps and leaves only token-by-token prompt ingestion through the decode kernels.
+        Special-token ids come from the tokenizer files next to the checkpoint when there are any, else from the public Qwen2.5
+        vocabulary (`modular_vibevoice_text_tokenizer.py:175-181`); `generate()` checks them against the tokenizer it is handed."""
         from safetensors import safe_open
         cfg = VibeVoiceConfig.from_pretrained(path)
         dev = 0
         if isinstance(device_map, str) and device_map.startswith("cuda:"):
             dev = int(device_map.split(":")[1])
+        elif isinstance(device_map, str) and device_map not in ("cuda", "auto"):
+            raise N.VVError("vibevoice_b200 runs on CUDA devices only (device_map=%r); there is no CPU path" % device_map)
         if tokenizer is None:
-            from .synth import SynthTokenizer
-            tokenizer = SynthTokenizer(cfg.decoder_config.vocab_size)
-        m = cls(cfg, tokenizer, max_batch=max_batch, device=dev)
+            tokenizer = cls._tokenizer_ids_from_dir(path, cfg.decoder_config.vocab_size)
+        m = cls(cfg, tokenizer, max_batch=max_batch, device=dev, torch_prefill=bool(kw.pop("torch_prefill", True)))
 
         def it():
             files = sorted(glob.glob(os.path.join(path, "*.safetensors")))
@@ -169,6 +229,21 @@ class VibeVoiceForConditionalGenerationInference:
         else:
             m.load_state_dict(it(), tokenizer)
         return m
+
+    @staticmethod
+    def _tokenizer_ids_from_dir(path: str, vocab_size: int):
+        if any(os.path.exists(os.path.join(path, f)) for f in ("tokenizer.json", "vocab.json", "tokenizer_config.json")):
+            try:
+                from transformers import AutoTokenizer
+                t = AutoTokenizer.from_pretrained(path)
+                ids = t.convert_tokens_to_ids
+                return SimpleNamespace(speech_start_id=ids("<|vision_start|>"), speech_end_id=ids("<|vision_end|>"),
+                                       speech_diffusion_id=ids("<|vision_pad|>"), pad_id=ids("<|image_pad|>"), pad_token_id=ids("<|image_pad|>"),
+                                       eos_token_id=t.eos_token_id, bos_token_id=getattr(t, "bos_token_id", None))
+            except Exception:
+                pass
+        from .synth import SynthTokenizer
+        return SynthTokenizer(vocab_size)
 
     def _reload_with(self, transform):
         """Re-stream the weights through `transform` (an iterator -> iterator function) and pack them again; used by
@@ -206,13 +281,34 @@ class VibeVoiceForConditionalGenerationInference:
         self.ddpm_inference_steps = num_steps or self.config.diffusion_head_config.ddpm_num_inference_steps
 
     # ---- generate ----------------------------------------------------------------------------------------
+    @staticmethod
+    def _config_processors(gcfg: dict, do_sample: bool) -> list:
+        """The generation-config-driven subset of HF `GenerationMixin._get_logits_processor` that acts per step on [B, vocab] scores:
+        repetition penalty always; temperature -> top-k -> top-p when sampling.  HF's sampling defaults apply (top_k = 50 unless the
+        caller sets it; pass top_k=0 to sample from the plain constrained softmax like `oracle/make_golden.py` does)."""
+        out = []
+        rp = gcfg.get("repetition_penalty")
+        if rp is not None and float(rp) != 1.0:
+            from transformers import RepetitionPenaltyLogitsProcessor
+            out.append(RepetitionPenaltyLogitsProcessor(penalty=float(rp)))
+        if do_sample:
+            from transformers import TemperatureLogitsWarper, TopKLogitsWarper, TopPLogitsWarper
+            t = gcfg.get("temperature")
+            if t is not None and float(t) != 1.0:
+                out.append(TemperatureLogitsWarper(float(t)))
+            k = gcfg.get("top_k", 50)
+            if k is not None and int(k) != 0:
+                out.append(TopKLogitsWarper(top_k=int(k), min_tokens_to_keep=1))
+            tp = gcfg.get("top_p")
+            if tp is not None and float(tp) < 1.0:
+                out.append(TopPLogitsWarper(top_p=float(tp), min_tokens_to_keep=1))
+        return out
+
     def _reserve_kv(self, total_tokens: int):
         eng = self.engine
-        if eng.kv_pages == 0:
-            eng.kv_init(total_tokens)
-        elif eng.kv_pages * 64 < total_tokens:
-            raise N.VVError("KV pool too small for this call: %d tokens needed, %d available; create the model with a "
-                            "larger first generate() or call engine.kv_init explicitly" % (total_tokens, eng.kv_pages * 64))
+        need_pages = (total_tokens + 63) // 64 + 4 * eng.B          # every sequence may hold one partially filled page
+        if eng.kv_pages < need_pages:
+            eng.kv_init(total_tokens)                                # first call, or a later call that needs more: the pool is re-sized
 
     @torch.no_grad()
     def generate(self, inputs=None, generation_config=None, logits_processor=None, stopping_criteria=None,
@@ -225,32 +321,34 @@ class VibeVoiceForConditionalGenerationInference:
         kwargs.pop("parsed_scripts", None); kwargs.pop("all_speakers_list", None)
         max_length_times = kwargs.pop("max_length_times", 2)
         verbose = kwargs.get("verbose", False)
-        do_sample = bool(generation_config is not None and dict(generation_config).get("do_sample", False))
+        gcfg = {}
+        if generation_config is not None:
+            gcfg = dict(generation_config) if isinstance(generation_config, dict) else {k: v for k, v in vars(generation_config).items() if not k.startswith("_")}
+        do_sample = bool(gcfg.get("do_sample", False))
         sample_gen = kwargs.get("sample_generator", None)          # torch.Generator for the token draw; never the noise RNG
         if do_sample and sample_gen is None:
             sample_gen = torch.Generator().manual_seed(torch.initial_seed())
-        temperature = 1.0
-        if do_sample:
-            gc = dict(generation_config)
-            temperature = float(gc.get("temperature", 1.0) or 1.0)      # scaling commutes with the -inf constraint: exact
-            if gc.get("top_k") not in (None, 0) or float(gc.get("top_p", 1.0) or 1.0) < 1.0:
-                import warnings
-                warnings.warn("top_k / top_p act on the full-vocabulary ranking before the token constraint in the reference "
-                              "(HF warpers, modeling_vibevoice_inference.py:310-319); this path never materialises full-vocab logits "
-                              "and samples from the softmax over the constrained ids only (= top_k 0, top_p 1)")
         refresh_negative = bool(kwargs.get("refresh_negative", True))
         use_voice = bool(is_prefill and speech_tensors is not None)
         if use_voice and (self._voice is None or self._prefill is None):
-            raise N.VVError("voice-prompt prefill needs torch_prefill=True and the acoustic-encoder weights (a-9 runs on PyTorch library kernels)")
+            raise N.VVError("voice-prompt prefill needs torch_prefill=True (the from_pretrained default) and the acoustic-encoder weights "
+                            "(a-9 runs on PyTorch library kernels)")
         forced: Optional[ForcedTokenScript] = None
+        user_procs = []
         if logits_processor is not None:
             procs = logits_processor if isinstance(logits_processor, (list, tuple)) else [logits_processor]
             for p in procs:
                 if isinstance(p, ForcedTokenScript):
                     forced = p
                 else:
-                    raise NotImplementedError("arbitrary LogitsProcessor objects need full-vocab logits, which this path never "
-                                              "materialises; use ForcedTokenScript")
+                    user_procs.append(p)
+        # Score processors that rank the WHOLE vocabulary before the token constraint (`_get_logits_processor` from the generation config,
+        # :310-319, then VibeVoiceTokenConstraintProcessor appended last, :415-418): they need full-vocabulary logits, which the default path
+        # never materialises.  With any of them present every step computes them with one extra GEMV over the lm_head (vv_lm_logits_full).
+        # NB the reference overwrites a caller-supplied `logits_processor` with the list built from the generation config (:375-377), i.e.
+        # it silently ignores such objects; here they are applied (before the config-derived ones), which is what a caller expects.
+        warpers = self._config_processors(gcfg, do_sample) + []
+        full_vocab_procs = user_procs + warpers
         input_ids = kwargs["input_ids"] if "input_ids" in kwargs else inputs
         input_ids = torch.as_tensor(input_ids).cpu().long()
         attention_mask = kwargs.get("attention_mask", None)
@@ -272,6 +370,10 @@ class VibeVoiceForConditionalGenerationInference:
                                       "depends on its cache-shift guard; see DESIGN section 4)")
         tok = tokenizer
         start_id, end_id, diff_id, eos_id = tok.speech_start_id, tok.speech_end_id, tok.speech_diffusion_id, tok.eos_token_id
+        if self._valid_ids(tok) != list(eng.valid_ids):
+            # the lm_head rows and the constrained argmax were fixed when the weights were packed (:405-419 resolves them per call)
+            raise ValueError("tokenizer special ids %s differ from the ids the engine was built with %s; load the model with this "
+                             "tokenizer (from_pretrained(..., tokenizer=tok))" % (self._valid_ids(tok), list(eng.valid_ids)))
 
         if kwargs.get("max_new_tokens", None) is None:
             kwargs["max_new_tokens"] = dc.max_position_embeddings - L0                      # :372-373
@@ -364,8 +466,18 @@ class VibeVoiceForConditionalGenerationInference:
                 eng.lm_decode()                                                             # :480-482 (+ speculative negative rows)
             toks_dev, logits_valid = eng.read_tokens()
             next_tokens = toks_dev.astype(np.int64).copy()
-            if do_sample:
-                next_tokens[:b] = sample_valid_tokens(logits_valid[:b] / temperature, eng.valid_ids, sample_gen)     # :493-496
+            if full_vocab_procs:                                                              # :488-498 on full-vocabulary scores
+                scores = eng.lm_logits_full()[:b].clone()
+                cur_ids = torch.tensor([s_ for s_ in seqs], dtype=torch.long, device=scores.device)
+                for p_ in full_vocab_procs:
+                    scores = p_(cur_ids, scores)
+                sv = scores[:, eng.valid_ids].float().cpu()                                   # the constraint keeps these ids only (:55-66)
+                if do_sample:
+                    next_tokens[:b] = sample_valid_tokens(sv.numpy(), eng.valid_ids, sample_gen)
+                else:
+                    next_tokens[:b] = np.asarray(eng.valid_ids, dtype=np.int64)[sv.argmax(dim=-1).numpy()]
+            elif do_sample:
+                next_tokens[:b] = sample_valid_tokens(logits_valid[:b], eng.valid_ids, sample_gen)                   # :493-496
             if forced is not None:
                 for r in range(b):
                     next_tokens[r] = forced.token(r, step)
