@@ -161,6 +161,11 @@ int vv_debug_gemv(vv_ctx* ctx, const void* w_bf16, const float* bias, const floa
                   int prologue, const float* pro_w, float eps, int epilogue, void* stream);
 
 int vv_debug_barrier_bench(vv_ctx* ctx, int iters, int ctas_per_sm, float* ms_out);
+/* one linear through the persistent weight-stream kernel (tcgen05 + TMA, csrc/vv_stream.cuh): y = [y +] alpha * (W pro(x) + bias).
+ * prologue: 0 none, 1 RMSNorm(pro_w, eps), 3 SwiGLU pairs (x is [M][2K]), 4 GELU, 6 SiLU; alpha_kind: 0 one, 2 gamma[n]. Synchronises. */
+int vv_debug_stream_gemv(vv_ctx* ctx, const void* w_bf16, const float* bias, const float* x, float* y, int M, int N, int K, int prologue,
+                         const float* pro_w, float eps, int alpha_kind, const float* alpha, int accumulate, void* stream);
+int vv_stream_diag(vv_ctx* ctx, unsigned* out6);   /* watchdog record of a trapped stream kernel: code, cta, thread, stage, iteration, extra */
 
 #ifdef __cplusplus
 }

@@ -117,7 +117,7 @@ def test_demo_inference_from_file_body(tmp_path):
     assert set(generated) <= valid and output_tokens > input_tokens
     n_diff = generated.count(tok.speech_diffusion_id)
     assert n_diff >= 1 and audio_samples == 3200 * n_diff             # one 3200-sample chunk per <speech_diffusion> (:646-650)
-    assert int(inputs["speech_input_mask"].sum()) == 3 + 3             # ceil(0.45 s * 24 kHz / 3200) + ceil(0.30 s * 24 kHz / 3200)
+    assert int(inputs["speech_input_mask"].sum()) == 4 + 3             # ceil(0.45 s * 24 kHz / 3200) + ceil(0.30 s * 24 kHz / 3200)
     from scipy.io import wavfile
     sr, wav = wavfile.read(output_path)
     assert sr == 24000 and wav.shape[0] == audio_samples and np.isfinite(wav).all() and float(np.abs(wav).max()) > 0

@@ -76,6 +76,8 @@ SYMBOLS = {
     "vv_launch_count": (_L, [_P]),
     "vv_debug_barrier_bench": (_I, [_P, _I, _I, C.POINTER(C.c_float)]),
     "vv_debug_gemv": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _F, _I, _P]),
+    "vv_debug_stream_gemv": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _F, _I, _P, _I, _P]),
+    "vv_stream_diag": (_I, [_P, _P]),
 }
 
 _lib = None

@@ -8,6 +8,7 @@
 #include "vv_kernels.cuh"
 #include "vv_stream.cuh"
 
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -124,12 +125,18 @@ struct vv_ctx {
   float *s_h = nullptr, *s_qkv = nullptr, *s_qrot = nullptr, *s_attn = nullptr, *s_act = nullptr, *s_pacc = nullptr, *s_pml = nullptr;
   int nsplit = 128;
   float *s_condp = nullptr, *s_call = nullptr, *s_mod = nullptr, *s_hx = nullptr, *s_hg = nullptr, *s_v = nullptr, *s_z = nullptr,
-        *s_x0 = nullptr, *s_tfeat = nullptr, *s_t1 = nullptr;
+        *s_x0 = nullptr, *s_tfeat = nullptr, *s_t1 = nullptr, *s_hgu = nullptr;
   float *s_xa = nullptr, *s_xb = nullptr, *s_u = nullptr, *s_win = nullptr, *s_xn = nullptr;
   float *s_e = nullptr, *s_c1 = nullptr, *s_feat = nullptr, *s_audio = nullptr, *s_latent = nullptr;
   int* s_tok = nullptr;
   std::map<std::string, GraphEntry> graphs;
   GridBar* gridbar = nullptr;
+  // weight-stream programs (vv_stream.cuh)
+  struct StreamProg { SOp* ops = nullptr; int n_ops = 0; CUtensorMap* tmaps = nullptr; SDpm* dpm = nullptr; int n_stages = 0; int b_bytes = 0; int smem = 0; int gemv_ops = 0; };
+  std::map<std::string, StreamProg> sprogs;
+  unsigned* st_bar = nullptr;            // grid-barrier counter of the stream kernel
+  unsigned* st_diag_host = nullptr; unsigned* st_diag_dev = nullptr;   // host-mapped watchdog record
+  int use_stream = 1;                    // VV_STREAM=0 -> kernel-per-stage path everywhere
   float* cfg_dev = nullptr; float cfg_last = NAN;   // CFG scale lives in device memory so captured graphs do not depend on its value
   int64_t launches = 0;
   std::map<long long, int> occ_cache;
@@ -272,6 +279,125 @@ static GemvP mk(const bf16* W, const float* bias, const float* x, long long ldx,
 }
 
 // ------------------------------------------------------------------------------------------------
+// weight-stream programs (vv_stream.cuh): host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// W [N][K] bf16 row-major -> 2-D tensor map, box = 64 k (128 B) x 128 rows, 128-byte swizzle, out-of-bounds rows / columns read as zero
+static int make_weight_tmap(const bf16* W, int N, int K, CUtensorMap* out) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return fail(VV_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  if (K % 8 || ((uintptr_t)W & 15)) return fail(VV_ERR_INVALID, "stream: weight [%d x %d] must have K %% 8 == 0 and a 16-byte aligned base", N, K);
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  const cuuint32_t box[2] = {64, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)W, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VV_ERR_CUDA, "cuTensorMapEncodeTiled([%d x %d]) failed with %d", N, K, (int)r);
+  return 0;
+}
+
+struct StreamBuilder {
+  vv_ctx* c;
+  std::vector<SOp> ops;
+  std::vector<CUtensorMap> tmaps;
+  std::vector<int> tmap_of;        // op -> tensor map index (or -1)
+  std::vector<SDpm> dpms;
+  std::vector<int> dpm_of;
+  explicit StreamBuilder(vv_ctx* c_) : c(c_) {}
+  SOp& push(int kind, bool sync) {
+    SOp o;
+    memset(&o, 0, sizeof o);
+    o.kind = kind; o.sync_before = sync ? 1 : 0; o.nB = 16;
+    ops.push_back(o); tmap_of.push_back(-1); dpm_of.push_back(-1);
+    return ops.back();
+  }
+  // y[m][n] (+)= alpha * (W x'[m] + bias); x' = pro(x)
+  int gemv(const bf16* W, const float* bias, const float* x, long long ldx, float* y, long long ldy, int M, int N, int K, bool sync, SOp** out) {
+    if (M < 1 || M > 32) return fail(VV_ERR_INVALID, "stream gemv: M=%d outside [1,32]", M);
+    CUtensorMap tm;
+    RET(make_weight_tmap(W, N, K, &tm));
+    SOp& o = push(SK_GEMV, sync);
+    o.M = M; o.N = N; o.K = K; o.nB = M <= 8 ? 16 : (M <= 16 ? 32 : 64);
+    o.x = x; o.ldx = ldx; o.y = y; o.ldy = ldy; o.bias = bias; o.pro = SP_NONE; o.alpha_kind = SA_ONE;
+    tmaps.push_back(tm);
+    tmap_of.back() = (int)tmaps.size() - 1;
+    *out = &ops.back();
+    return 0;
+  }
+  void nop(bool sync, float* init_dst, long long init_n) {
+    SOp& o = push(SK_NOP, sync);
+    o.init_dst = init_dst; o.init_n = init_n;
+  }
+  void attach_dpm(const SDpm& d) { dpms.push_back(d); dpm_of.back() = (int)dpms.size() - 1; }
+};
+
+static int finish_stream(StreamBuilder& b, vv_ctx::StreamProg* pr) {
+  vv_ctx* c = b.c;
+  const int G = c->sm_count;
+  int b_bytes = 2048;
+  for (const SOp& o : b.ops) {
+    if (o.kind != SK_GEMV) continue;
+    const long long KB = (o.K + 63) / 64, R = (o.N + 127) / 128, U = R * KB;
+    const long long per = (U + G - 1) / G;
+    const long long count = std::min(per, KB);
+    b_bytes = std::max<long long>(b_bytes, count * o.nB * 128);
+    const long long segs = (per + KB - 1) / KB + 1;
+    if (segs > ST_MAXSEG || segs * o.nB > 512) return fail(VV_ERR_INVALID, "stream: stage [%d x %d] needs %lld accumulators per CTA", o.N, o.K, segs);
+    if (o.store && KB != 1) return fail(VV_ERR_INVALID, "stream: store epilogue needs K <= 64");
+  }
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, stream_kernel));
+  const int max_dyn = 232448 - (int)fa.sharedSizeBytes - 256;
+  int ns = (max_dyn - 1024 - b_bytes) / ST_TILE;
+  ns = std::min(ns, ST_MAX_STAGES);
+  if (getenv("VV_STREAM_STAGES")) ns = std::min(ns, atoi(getenv("VV_STREAM_STAGES")));
+  if (ns < 2) return fail(VV_ERR_INVALID, "stream: activation operand of %d bytes leaves no room for the weight ring", b_bytes);
+  pr->n_stages = ns; pr->b_bytes = b_bytes; pr->smem = ns * ST_TILE + b_bytes + 1024;
+  pr->n_ops = (int)b.ops.size();
+  RET(dmalloc(c, &pr->tmaps, std::max<size_t>(b.tmaps.size(), 1), false));
+  RET(dmalloc(c, &pr->dpm, std::max<size_t>(b.dpms.size(), 1), false));
+  RET(dmalloc(c, &pr->ops, b.ops.size(), false));
+  for (size_t i = 0; i < b.ops.size(); ++i) {
+    if (b.tmap_of[i] >= 0) b.ops[i].tmap = (unsigned long long)(uintptr_t)(pr->tmaps + b.tmap_of[i]);
+    if (b.dpm_of[i] >= 0) b.ops[i].dpm = pr->dpm + b.dpm_of[i];
+    pr->gemv_ops += b.ops[i].kind == SK_GEMV;
+  }
+  if (!b.tmaps.empty()) CK(cudaMemcpy(pr->tmaps, b.tmaps.data(), b.tmaps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+  if (!b.dpms.empty()) CK(cudaMemcpy(pr->dpm, b.dpms.data(), b.dpms.size() * sizeof(SDpm), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(pr->ops, b.ops.data(), b.ops.size() * sizeof(SOp), cudaMemcpyHostToDevice));
+  CK(cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  return 0;
+}
+
+static int launch_stream(const L& l, const vv_ctx::StreamProg& pr) {
+  vv_ctx* c = l.c;
+  CK(cudaMemsetAsync(c->st_bar, 0, sizeof(unsigned), l.s));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(c->sm_count); cfg.blockDim = dim3(ST_THREADS); cfg.dynamicSmemBytes = pr.smem; cfg.stream = l.s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;      // all CTAs must be co-resident: they synchronise through a grid barrier
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  SParams P;
+  P.ops = pr.ops; P.n_ops = pr.n_ops; P.bar_count = c->st_bar; P.diag = c->st_diag_dev; P.n_stages = pr.n_stages; P.b_bytes = pr.b_bytes;
+  c->launches++;
+  CK(cudaLaunchKernelEx(&cfg, stream_kernel, P));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // expected tensor names (same as vibevoice_b200/synth.py::param_specs, i.e. the HF checkpoint keys)
 // ------------------------------------------------------------------------------------------------
 static std::string S(const char* fmt, ...) {
@@ -351,6 +477,7 @@ extern "C" int vv_create(const vv_model_desc* desc, int device, vv_ctx** out) {
   if (getenv("VV_WR_FORCE")) c->wr_force = atoi(getenv("VV_WR_FORCE"));
   if (getenv("VV_GEMV_GRID_CAP")) c->gemv_grid_cap = atoi(getenv("VV_GEMV_GRID_CAP"));
   if (getenv("VV_NO_FUSE_ROPE")) c->fuse_rope = false;
+  if (getenv("VV_STREAM")) c->use_stream = atoi(getenv("VV_STREAM"));
   if (getenv("VV_TC5")) c->use_tc5 = atoi(getenv("VV_TC5"));
   if (getenv("VV_MMA_MIN_ROWS")) c->mma_min_rows = atoi(getenv("VV_MMA_MIN_ROWS"));
   if (getenv("VV_NO_MMA_RING")) c->mma_ring = false;
@@ -373,6 +500,7 @@ extern "C" void vv_destroy(vv_ctx* c) {
   for (auto& g : c->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   for (auto& r : c->raw) if (r.second.p) cudaFree(r.second.p);
   for (void* p : c->allocs) cudaFree(p);
+  if (c->st_diag_host) cudaFreeHost(c->st_diag_host);
   delete c;
 }
 
@@ -701,8 +829,13 @@ extern "C" int vv_finalize_weights(vv_ctx* c) {
     RET(dmalloc(c, &c->s_mod, (size_t)NS * M2 * modrows));
     RET(dmalloc(c, &c->cfg_dev, 4));
     RET(dmalloc(c, &c->gridbar, 2));
+    RET(dmalloc(c, &c->st_bar, 32));
+    CK(cudaHostAlloc((void**)&c->st_diag_host, 64, cudaHostAllocMapped));
+    memset(c->st_diag_host, 0, 64);
+    CK(cudaHostGetDevicePointer((void**)&c->st_diag_dev, c->st_diag_host, 0));
     RET(dmalloc(c, &c->s_hx, (size_t)M2 * H));
     RET(dmalloc(c, &c->s_hg, (size_t)M2 * F));
+    RET(dmalloc(c, &c->s_hgu, (size_t)2 * M2 * 2 * F));
     RET(dmalloc(c, &c->s_v, (size_t)M2 * 64));
     RET(dmalloc(c, &c->s_z, (size_t)2 * B * 64));
     RET(dmalloc(c, &c->s_x0, (size_t)2 * B * 64));
@@ -1205,7 +1338,67 @@ static int set_cfg(vv_ctx* c, float cfg, cudaStream_t s) {
   return 0;
 }
 
-static int enqueue_diffusion(const L& l, const float* cond, const float* noise, float* latent_out) {
+// The N-step sampler as ONE weight-stream program (vv_stream.cuh): per step 4 x (gate/up with AdaLN prologue -> raw sums; down with SwiGLU
+// prologue, gated-residual epilogue) + final layer + noisy_images_proj whose prologue is the CFG / DPM-Solver++ update.  10 grid barriers
+// per step instead of 10 kernels, and the TMA ring keeps streaming head weights across all of them.
+static int sampler_stream_prog(vv_ctx* c, const float* noise, float* latent_out, const vv_ctx::StreamProg** out) {
+  char key[256];
+  snprintf(key, sizeof key, "samp:%p:%p:%d:%d:%p", (const void*)noise, (void*)latent_out, c->n_steps, (int)c->sde, (const void*)c->step_noise);
+  auto it = c->sprogs.find(key);
+  if (it != c->sprogs.end()) { *out = &it->second; return 0; }
+  const auto& d = c->d;
+  const int H = d.hidden_size, F = d.head_ffn_dim, B = d.max_batch, M = 2 * B, LH = d.head_layers, N = c->n_steps;
+  const long long modld = (long long)(3 * LH + 2) * H;
+  StreamBuilder b(c);
+  auto dpm = [&](int i) {
+    SDpm o;
+    memset(&o, 0, sizeof o);
+    if (i < 0) { o.z_in = c->s_z + B * 64; o.z_out = c->s_z; o.x0_in = c->s_x0 + B * 64; o.x0_out = c->s_x0; }
+    else {
+      o.z_in = c->s_z + (size_t)(i & 1) * B * 64; o.z_out = c->s_z + (size_t)((i + 1) & 1) * B * 64;
+      o.x0_in = c->s_x0 + (size_t)(i & 1) * B * 64; o.x0_out = c->s_x0 + (size_t)((i + 1) & 1) * B * 64;
+    }
+    o.v = c->s_v; o.noise = noise; o.coef = c->coef_dev; o.cfg_p = c->cfg_dev; o.step_noise = c->sde ? c->step_noise : nullptr;
+    o.latent_out = (i == N - 1) ? latent_out : nullptr; o.step = i; o.B = B;
+    return o;
+  };
+  auto proj = [&](int i, bool sync) -> int {       // x = noisy_images_proj(z'), z' = solver update of step i (i = -1: the initial noise)
+    SOp* o;
+    RET(b.gemv(c->h_noisy, nullptr, nullptr, 0, c->s_hx, H, M, H, 64, sync, &o));
+    o->pro = SP_DPM; o->store = 1;
+    b.attach_dpm(dpm(i));
+    return 0;
+  };
+  float* gu[2] = {c->s_hgu, c->s_hgu + (size_t)M * 2 * F};
+  RET(proj(-1, false));
+  b.ops.back().init_dst = gu[0]; b.ops.back().init_n = (long long)M * 2 * F;
+  for (int i = 0; i < N; ++i) {
+    const float* mod = c->s_mod + (size_t)i * M * modld;
+    for (int li = 0; li < LH; ++li) {
+      const HeadLayer& hl = c->head[li];
+      SOp* o;
+      RET(b.gemv(hl.wgu, nullptr, c->s_hx, H, gu[li & 1], 2 * F, M, 2 * F, H, true, &o));
+      o->pro = SP_ADALN; o->pro_w = hl.norm; o->pro_eps = d.head_rms_eps;
+      o->pro_shift = mod + (size_t)li * 3 * H; o->pro_scale = mod + (size_t)li * 3 * H + H; o->pro_ld = modld;
+      o->init_dst = gu[(li + 1) & 1]; o->init_n = (long long)M * 2 * F;           // the other buffer: its reader (down of li-1) is done
+      RET(b.gemv(hl.wdown, nullptr, gu[li & 1], 2 * F, c->s_hx, H, M, H, F, true, &o));
+      o->pro = SP_SWIGLU; o->alpha_kind = SA_GATE; o->alpha = mod + (size_t)li * 3 * H + 2 * H; o->lda = modld;
+      if (li == 0) { o->init_dst = c->s_v; o->init_n = (long long)M * 64; }        // final layer of this step accumulates into s_v
+    }
+    SOp* o;
+    RET(b.gemv(c->h_final, nullptr, c->s_hx, H, c->s_v, 64, M, 64, H, true, &o));
+    o->pro = SP_ADALN; o->pro_w = nullptr; o->pro_eps = d.head_rms_eps;
+    o->pro_shift = mod + (size_t)LH * 3 * H; o->pro_scale = mod + (size_t)LH * 3 * H + H; o->pro_ld = modld;
+    RET(proj(i, true));
+  }
+  vv_ctx::StreamProg pr;
+  RET(finish_stream(b, &pr));
+  it = c->sprogs.emplace(key, pr).first;
+  *out = &it->second;
+  return 0;
+}
+
+static int enqueue_diffusion(const L& l, const float* cond, const float* noise, float* latent_out, const vv_ctx::StreamProg* sprog) {
   vv_ctx* c = l.c;
   const auto& d = c->d;
   const int H = d.hidden_size, B = d.max_batch, M = 2 * B, LH = d.head_layers, N = c->n_steps;
@@ -1222,6 +1415,7 @@ static int enqueue_diffusion(const L& l, const float* cond, const float* noise, 
   // (the reference recomputes Linear(silu(c)) inside every head call, diffusion_head.py:159, 185; c depends only on (cond, t_i))
   p = mk(c->h_mod, nullptr, c->s_call, H, c->s_mod, modld, N * M, modld, H);
   RET(linear(l, p));
+  if (sprog) return launch_stream(l, *sprog);
   CK(launch_k(l, dpm_update_proj_kernel, dim3(B, (H + 255) / 256), dim3(256), 0, c->s_z + B * 64, c->s_z, c->s_x0 + B * 64, c->s_x0, c->s_v, noise,
               c->coef_dev, -1, (const float*)c->cfg_dev, c->h_noisy, c->s_hx, nullptr, B, H, 1, (const float*)nullptr));
   L lh = l;
@@ -1252,7 +1446,9 @@ extern "C" int vv_diffusion_sample(vv_ctx* c, const float* cond, const float* no
   RET(set_cfg(c, cfg, (cudaStream_t)stream));
   char key[256];
   snprintf(key, sizeof key, "diff:%p:%p:%p", (const void*)cond, (const void*)noise, (void*)latent_out);
-  return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_diffusion(l, cond, noise, latent_out); });
+  const vv_ctx::StreamProg* sprog = nullptr;      // built outside stream capture (it allocates and copies)
+  if (c->use_stream) RET(sampler_stream_prog(c, noise, latent_out, &sprog));
+  return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_diffusion(l, cond, noise, latent_out, sprog); });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1417,8 +1613,10 @@ extern "C" int vv_frame_tail(vv_ctx* c, const float* hidden, const float* noise,
   RET(set_cfg(c, cfg, (cudaStream_t)stream));
   snprintf(key, sizeof key, "tail:%p:%p:%p:%p:%p:%p", (const void*)hidden, (const void*)noise, (const void*)active, (void*)latent_out,
            (void*)audio_out, (void*)embeds);
+  const vv_ctx::StreamProg* sprog = nullptr;
+  if (c->use_stream) RET(sampler_stream_prog(c, noise, latent_out, &sprog));
   return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) {
-    RET(enqueue_diffusion(l, hidden, noise, latent_out));
+    RET(enqueue_diffusion(l, hidden, noise, latent_out, sprog));
     RET(enqueue_decode(l, latent_out, active, audio_out));
     RET(enqueue_encode(l, audio_out, active, c->s_feat));
     return enqueue_connect(l, latent_out, c->s_feat, active, embeds);
@@ -1464,6 +1662,33 @@ extern "C" int vv_debug_gemv(vv_ctx* c, const void* w, const float* bias, const 
   p.pro = prologue; p.pro_w = pro_w; p.pro_eps = eps; p.epi = epilogue;
   if (epilogue == EPI_RESID) { p.res = y; p.ldres = N; }
   return linear(l, p);
+}
+
+// one linear through the weight-stream kernel (tests): y = [y +] alpha * (W pro(x) + bias); pro = SPro, alpha_kind = SAlpha
+extern "C" int vv_debug_stream_gemv(vv_ctx* c, const void* w, const float* bias, const float* x, float* y, int M, int N, int K, int pro,
+                                    const float* pro_w, float eps, int alpha_kind, const float* alpha, int accumulate, void* stream) {
+  if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
+  CK(cudaSetDevice(c->device));
+  StreamBuilder b(c);
+  if (!accumulate) b.nop(false, y, (long long)M * N);
+  SOp* o;
+  RET(b.gemv((const bf16*)w, bias, x, pro == SP_SWIGLU ? 2LL * K : (long long)K, y, N, M, N, K, !accumulate, &o));
+  o->pro = pro; o->pro_w = pro_w; o->pro_eps = eps; o->alpha_kind = alpha_kind; o->alpha = alpha; o->lda = N;
+  vv_ctx::StreamProg pr;
+  RET(finish_stream(b, &pr));
+  L l{c, (cudaStream_t)stream};
+  RET(launch_stream(l, pr));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  dfree(c, &pr.ops); dfree(c, &pr.tmaps); dfree(c, &pr.dpm);
+  if (c->st_diag_host[0]) return fail(VV_ERR_CUDA, "stream kernel watchdog: code %u cta %u thread %u a %u b %u c %u", c->st_diag_host[0], c->st_diag_host[1],
+                                      c->st_diag_host[2], c->st_diag_host[3], c->st_diag_host[4], c->st_diag_host[5]);
+  return 0;
+}
+// watchdog record of the last stream kernel that trapped: out[0] = code (0 = none), out[1..5] = cta, thread, stage, iteration, extra
+extern "C" int vv_stream_diag(vv_ctx* c, unsigned* out6) {
+  if (!c || !c->st_diag_host) return fail(VV_ERR_STATE, "no context");
+  for (int i = 0; i < 6; ++i) out6[i] = c->st_diag_host[i];
+  return 0;
 }
 
 // time `iters` grid barriers of a cooperative launch with `per_sm` CTAs per SM (debug / profiling aid)
