@@ -165,6 +165,10 @@ int vv_debug_barrier_bench(vv_ctx* ctx, int iters, int ctas_per_sm, float* ms_ou
  * prologue: 0 none, 1 RMSNorm(pro_w, eps), 3 SwiGLU pairs (x is [M][2K]), 4 GELU, 6 SiLU; alpha_kind: 0 one, 2 gamma[n]. Synchronises. */
 int vv_debug_stream_gemv(vv_ctx* ctx, const void* w_bf16, const float* bias, const float* x, float* y, int M, int N, int K, int prologue,
                          const float* pro_w, float eps, int alpha_kind, const float* alpha, int accumulate, void* stream);
+int vv_stream_trace_read2(vv_ctx* ctx, long long* out /*[max_ops][sm_count][2]*/, int max_ops);  /* every CTA's barrier arrival / release (globaltimer ns); returns sm_count */
+int vv_stream_trace_read(vv_ctx* ctx, long long* out /*[max_ops][12]*/, int* out_meta /*[max_ops][4]*/, int max_ops, const char* program_prefix);
+                                                   /* VV_STREAM_TRACE=<cta>: per-stage clock stamps of one CTA of the last traced launch */
+int vv_debug_mma_rate(vv_ctx* ctx, int n_mma, int nB, int mode, int n_accumulators, int ctas, long long* cycles_out);   /* tcgen05.mma 128 x nB x 16 micro-benchmark */
 int vv_stream_diag(vv_ctx* ctx, unsigned* out6);   /* watchdog record of a trapped stream kernel: code, cta, thread, stage, iteration, extra */
 
 #ifdef __cplusplus

@@ -111,6 +111,7 @@ struct vv_ctx {
   bf16 *h_noisy = nullptr, *h_cond = nullptr, *h_t0 = nullptr, *h_t2 = nullptr, *h_mod = nullptr, *h_final = nullptr;
   std::vector<HeadLayer> head;
   int n_steps = 0; float* temb = nullptr; DpmCoef* coef_dev = nullptr; float* tfreqs = nullptr;
+  std::vector<DpmCoef> coef_host; int coef_version = 0;
   bool sde = false; const float* step_noise = nullptr;   // sde-dpmsolver++: per-step variance noise [n_steps][B][64] (vv_set_step_noise)
   // connectors
   bf16 *ca_fc1 = nullptr, *ca_fc2 = nullptr, *cs_fc1 = nullptr, *cs_fc2 = nullptr;
@@ -122,6 +123,7 @@ struct vv_ctx {
   int* page_table_dev = nullptr; int* kv_len_dev = nullptr; int* row_mode_dev = nullptr;
   std::vector<int64_t> kv_len_host; std::vector<std::vector<int>> seq_pages; std::vector<int> free_pages;
   // scratch
+  float* s_lgu = nullptr;   // LM gate/up raw sums [2B][2I] (weight-stream path)
   float *s_h = nullptr, *s_qkv = nullptr, *s_qrot = nullptr, *s_attn = nullptr, *s_act = nullptr, *s_pacc = nullptr, *s_pml = nullptr;
   int nsplit = 128;
   float *s_condp = nullptr, *s_call = nullptr, *s_mod = nullptr, *s_hx = nullptr, *s_hg = nullptr, *s_v = nullptr, *s_z = nullptr,
@@ -132,11 +134,15 @@ struct vv_ctx {
   std::map<std::string, GraphEntry> graphs;
   GridBar* gridbar = nullptr;
   // weight-stream programs (vv_stream.cuh)
-  struct StreamProg { SOp* ops = nullptr; int n_ops = 0; CUtensorMap* tmaps = nullptr; SDpm* dpm = nullptr; int n_stages = 0; int b_bytes = 0; int smem = 0; int gemv_ops = 0; };
+  struct StreamProg { SOp* ops = nullptr; int n_ops = 0; CUtensorMap* tmaps = nullptr; int n_stages = 0; int b_bytes = 0; int smem = 0; int gemv_ops = 0; };
   std::map<std::string, StreamProg> sprogs;
   unsigned* st_bar = nullptr;            // grid-barrier counter of the stream kernel
   unsigned* st_diag_host = nullptr; unsigned* st_diag_dev = nullptr;   // host-mapped watchdog record
-  int use_stream = 1;                    // VV_STREAM=0 -> kernel-per-stage path everywhere
+  int st_inflight = 4;                   // VV_STREAM_INFLIGHT: TMA tiles (16 KB) a CTA keeps in flight
+  int use_stream = 3;                    // VV_STREAM bit 0: sampler, bit 1: LM linears through the weight-stream kernel; 0 -> kernel-per-stage everywhere
+  std::map<const bf16*, bf16*> tiled; size_t tiled_bytes = 0;   // tile-major copies of the weights the stream kernel reads
+  long long* st_trace2 = nullptr;
+  long long* st_trace = nullptr; int st_trace_ops = 0; int st_trace_cta = 0; int st_trace_last_ops = 0;   // VV_STREAM_TRACE=<cta>: per-stage clock stamps of one CTA
   float* cfg_dev = nullptr; float cfg_last = NAN;   // CFG scale lives in device memory so captured graphs do not depend on its value
   int64_t launches = 0;
   std::map<long long, int> occ_cache;
@@ -292,18 +298,38 @@ static EncodeTiledFn encode_tiled_fn() {
   }
   return fn;
 }
-// W [N][K] bf16 row-major -> 2-D tensor map, box = 64 k (128 B) x 128 rows, 128-byte swizzle, out-of-bounds rows / columns read as zero
-static int make_weight_tmap(const bf16* W, int N, int K, CUtensorMap* out) {
+// tile-major weight copy [n_tiles][128][64] bf16 -> 2-D tensor map over [n_tiles*128][64], box = one 16 KB tile, 128-byte swizzle
+static int make_weight_tmap(const bf16* T, long long n_tiles, CUtensorMap* out) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return fail(VV_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-  if (K % 8 || ((uintptr_t)W & 15)) return fail(VV_ERR_INVALID, "stream: weight [%d x %d] must have K %% 8 == 0 and a 16-byte aligned base", N, K);
-  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
-  const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  const int N = (int)n_tiles, K = 64;
+  const cuuint64_t dims[2] = {64, (cuuint64_t)n_tiles * 128};
+  const cuuint64_t strides[1] = {128};
   const cuuint32_t box[2] = {64, 128};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)W, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(VV_ERR_CUDA, "cuTensorMapEncodeTiled([%d x %d]) failed with %d", N, K, (int)r);
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)T, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(VV_ERR_CUDA, "cuTensorMapEncodeTiled([%d tiles x %d]) failed with %d", N, K, (int)r);
+  return 0;
+}
+// tile-major copy of W [N][K] (cached per weight pointer; `fresh` = never cache: the caller's buffer may be re-used with other contents)
+static int tiled_weight(vv_ctx* c, const bf16* W, int N, int K, bool fresh, bf16** out, long long* n_tiles) {
+  if (K % 8 || ((uintptr_t)W & 15)) return fail(VV_ERR_INVALID, "stream: weight [%d x %d] must have K %% 8 == 0 and a 16-byte aligned base", N, K);
+  const long long KB = (K + 63) / 64, R = (N + 127) / 128;
+  *n_tiles = R * KB;
+  if (!fresh) {
+    auto it = c->tiled.find(W);
+    if (it != c->tiled.end()) { *out = it->second; return 0; }
+  }
+  bf16* T = nullptr;
+  RET(dmalloc(c, &T, (size_t)(*n_tiles) * 8192, false));
+  const long long n_chunks = *n_tiles * 1024;
+  tile_pack_kernel<<<(unsigned)std::min<long long>((n_chunks + 255) / 256, 148 * 32), 256>>>(W, T, N, K, (int)KB, n_chunks);
+  CKL();
+  CK(cudaDeviceSynchronize());
+  if (!fresh) c->tiled[W] = T;
+  c->tiled_bytes += (size_t)(*n_tiles) * 16384;
+  *out = T;
   return 0;
 }
 
@@ -312,21 +338,24 @@ struct StreamBuilder {
   std::vector<SOp> ops;
   std::vector<CUtensorMap> tmaps;
   std::vector<int> tmap_of;        // op -> tensor map index (or -1)
-  std::vector<SDpm> dpms;
-  std::vector<int> dpm_of;
   explicit StreamBuilder(vv_ctx* c_) : c(c_) {}
   SOp& push(int kind, bool sync) {
     SOp o;
     memset(&o, 0, sizeof o);
     o.kind = kind; o.sync_before = sync ? 1 : 0; o.nB = 16;
-    ops.push_back(o); tmap_of.push_back(-1); dpm_of.push_back(-1);
+    ops.push_back(o); tmap_of.push_back(-1);
     return ops.back();
   }
   // y[m][n] (+)= alpha * (W x'[m] + bias); x' = pro(x)
+  bool fresh_weights = false;
+  std::vector<bf16*> owned;         // tile-major copies made with fresh_weights (freed by the caller)
   int gemv(const bf16* W, const float* bias, const float* x, long long ldx, float* y, long long ldy, int M, int N, int K, bool sync, SOp** out) {
     if (M < 1 || M > 32) return fail(VV_ERR_INVALID, "stream gemv: M=%d outside [1,32]", M);
     CUtensorMap tm;
-    RET(make_weight_tmap(W, N, K, &tm));
+    bf16* T; long long n_tiles;
+    RET(tiled_weight(c, W, N, K, fresh_weights, &T, &n_tiles));
+    if (fresh_weights) owned.push_back(T);
+    RET(make_weight_tmap(T, n_tiles, &tm));
     SOp& o = push(SK_GEMV, sync);
     o.M = M; o.N = N; o.K = K; o.nB = M <= 8 ? 16 : (M <= 16 ? 32 : 64);
     o.x = x; o.ldx = ldx; o.y = y; o.ldy = ldy; o.bias = bias; o.pro = SP_NONE; o.alpha_kind = SA_ONE;
@@ -339,7 +368,6 @@ struct StreamBuilder {
     SOp& o = push(SK_NOP, sync);
     o.init_dst = init_dst; o.init_n = init_n;
   }
-  void attach_dpm(const SDpm& d) { dpms.push_back(d); dpm_of.back() = (int)dpms.size() - 1; }
 };
 
 static int finish_stream(StreamBuilder& b, vv_ctx::StreamProg* pr) {
@@ -355,6 +383,7 @@ static int finish_stream(StreamBuilder& b, vv_ctx::StreamProg* pr) {
     const long long segs = (per + KB - 1) / KB + 1;
     if (segs > ST_MAXSEG || segs * o.nB > 512) return fail(VV_ERR_INVALID, "stream: stage [%d x %d] needs %lld accumulators per CTA", o.N, o.K, segs);
     if (o.store && KB != 1) return fail(VV_ERR_INVALID, "stream: store epilogue needs K <= 64");
+    if (U * (G + 1) >= (1ll << 32)) return fail(VV_ERR_INVALID, "stream: stage [%d x %d] has too many tiles for 32-bit scheduling", o.N, o.K);
   }
   cudaFuncAttributes fa;
   CK(cudaFuncGetAttributes(&fa, stream_kernel));
@@ -366,22 +395,20 @@ static int finish_stream(StreamBuilder& b, vv_ctx::StreamProg* pr) {
   pr->n_stages = ns; pr->b_bytes = b_bytes; pr->smem = ns * ST_TILE + b_bytes + 1024;
   pr->n_ops = (int)b.ops.size();
   RET(dmalloc(c, &pr->tmaps, std::max<size_t>(b.tmaps.size(), 1), false));
-  RET(dmalloc(c, &pr->dpm, std::max<size_t>(b.dpms.size(), 1), false));
   RET(dmalloc(c, &pr->ops, b.ops.size(), false));
   for (size_t i = 0; i < b.ops.size(); ++i) {
     if (b.tmap_of[i] >= 0) b.ops[i].tmap = (unsigned long long)(uintptr_t)(pr->tmaps + b.tmap_of[i]);
-    if (b.dpm_of[i] >= 0) b.ops[i].dpm = pr->dpm + b.dpm_of[i];
     pr->gemv_ops += b.ops[i].kind == SK_GEMV;
   }
   if (!b.tmaps.empty()) CK(cudaMemcpy(pr->tmaps, b.tmaps.data(), b.tmaps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-  if (!b.dpms.empty()) CK(cudaMemcpy(pr->dpm, b.dpms.data(), b.dpms.size() * sizeof(SDpm), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(pr->ops, b.ops.data(), b.ops.size() * sizeof(SOp), cudaMemcpyHostToDevice));
   CK(cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   return 0;
 }
 
-static int launch_stream(const L& l, const vv_ctx::StreamProg& pr) {
+static int launch_stream(const L& l, const vv_ctx::StreamProg& pr, int op_begin = 0, int op_count = -1) {
   vv_ctx* c = l.c;
+  if (op_count < 0) op_count = pr.n_ops - op_begin;
   CK(cudaMemsetAsync(c->st_bar, 0, sizeof(unsigned), l.s));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
@@ -391,7 +418,11 @@ static int launch_stream(const L& l, const vv_ctx::StreamProg& pr) {
   attr[0].val.cooperative = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   SParams P;
-  P.ops = pr.ops; P.n_ops = pr.n_ops; P.bar_count = c->st_bar; P.diag = c->st_diag_dev; P.n_stages = pr.n_stages; P.b_bytes = pr.b_bytes;
+  P.ops = pr.ops + op_begin; P.n_ops = op_count; P.bar_count = c->st_bar; P.diag = c->st_diag_dev; P.n_stages = pr.n_stages; P.b_bytes = pr.b_bytes;
+  P.max_inflight = std::max(1, std::min(pr.n_stages, c->st_inflight));
+  P.trace = (c->st_trace && op_count == pr.n_ops && pr.n_ops <= c->st_trace_ops) ? c->st_trace : nullptr; P.trace_cta = c->st_trace_cta;
+  P.trace2 = P.trace ? c->st_trace2 : nullptr;
+  if (P.trace) c->st_trace_last_ops = pr.n_ops;
   c->launches++;
   CK(cudaLaunchKernelEx(&cfg, stream_kernel, P));
   return 0;
@@ -478,6 +509,7 @@ extern "C" int vv_create(const vv_model_desc* desc, int device, vv_ctx** out) {
   if (getenv("VV_GEMV_GRID_CAP")) c->gemv_grid_cap = atoi(getenv("VV_GEMV_GRID_CAP"));
   if (getenv("VV_NO_FUSE_ROPE")) c->fuse_rope = false;
   if (getenv("VV_STREAM")) c->use_stream = atoi(getenv("VV_STREAM"));
+  if (getenv("VV_STREAM_INFLIGHT")) c->st_inflight = atoi(getenv("VV_STREAM_INFLIGHT"));
   if (getenv("VV_TC5")) c->use_tc5 = atoi(getenv("VV_TC5"));
   if (getenv("VV_MMA_MIN_ROWS")) c->mma_min_rows = atoi(getenv("VV_MMA_MIN_ROWS"));
   if (getenv("VV_NO_MMA_RING")) c->mma_ring = false;
@@ -830,6 +862,12 @@ extern "C" int vv_finalize_weights(vv_ctx* c) {
     RET(dmalloc(c, &c->cfg_dev, 4));
     RET(dmalloc(c, &c->gridbar, 2));
     RET(dmalloc(c, &c->st_bar, 32));
+    if (getenv("VV_STREAM_TRACE")) {
+      c->st_trace_cta = atoi(getenv("VV_STREAM_TRACE"));
+      c->st_trace_ops = 4096;
+      RET(dmalloc(c, &c->st_trace, (size_t)c->st_trace_ops * ST_TRACE));
+      RET(dmalloc(c, &c->st_trace2, (size_t)c->st_trace_ops * c->sm_count * 2));
+    }
     CK(cudaHostAlloc((void**)&c->st_diag_host, 64, cudaHostAllocMapped));
     memset(c->st_diag_host, 0, 64);
     CK(cudaHostGetDevicePointer((void**)&c->st_diag_dev, c->st_diag_host, 0));
@@ -930,6 +968,7 @@ extern "C" int vv_finalize_weights(vv_ctx* c) {
   RET(dmalloc(c, &c->s_qrot, (size_t)M2 * nq));
   RET(dmalloc(c, &c->s_attn, (size_t)M2 * nq));
   RET(dmalloc(c, &c->s_act, (size_t)M2 * I));
+  RET(dmalloc(c, &c->s_lgu, (size_t)M2 * 2 * I));
   RET(dmalloc(c, &c->s_pacc, (size_t)M2 * d.num_q_heads * c->nsplit * HD));
   RET(dmalloc(c, &c->s_pml, (size_t)M2 * d.num_q_heads * c->nsplit * 2));
   RET(dmalloc(c, &c->s_tok, 64));
@@ -1126,18 +1165,59 @@ static int enqueue_lm_head(const L& l, const float* hidden, float* logits, int32
   return 0;
 }
 
+// The linears of decoder layers [li0, li1) as one weight-stream program (vv_stream.cuh), launched in pieces around the attention kernels:
+//   [zero s_qkv | QKV(li0)]  attention(li0)  [O(li0) GU(li0) DN(li0) QKV(li0+1)]  attention(li0+1)  ...  [O GU DN](li1-1)
+// QKV: RMSNorm prologue, bias; O: accumulates into the residual stream; GU: RMSNorm prologue -> raw gate/up sums; DN: SwiGLU prologue,
+// accumulates into the residual stream.  Zero-fill jobs ride on the O stage (s_qkv and the gate/up buffer are dead at that point).
+static int lm_stream_prog(vv_ctx* c, int li0, int li1, const vv_ctx::StreamProg** out) {
+  char key[64];
+  snprintf(key, sizeof key, "lm:%d:%d", li0, li1);
+  auto it = c->sprogs.find(key);
+  if (it != c->sprogs.end()) { *out = &it->second; return 0; }
+  const auto& d = c->d;
+  const int H = d.hidden_size, I = d.intermediate_size, M = 2 * d.max_batch, nq = d.num_q_heads * HD;
+  StreamBuilder b(c);
+  b.nop(false, c->s_qkv, (long long)M * c->Nqkv);
+  auto qkv = [&](int li) -> int {
+    const LmLayer& y = c->lm[li];
+    SOp* o;
+    RET(b.gemv(y.wqkv, y.bqkv, c->s_h, H, c->s_qkv, c->Nqkv, M, c->Nqkv, H, true, &o));
+    o->pro = SP_RMSNORM; o->pro_w = y.ln1; o->pro_eps = d.rms_norm_eps;
+    return 0;
+  };
+  RET(qkv(li0));
+  for (int li = li0; li < li1; ++li) {
+    const LmLayer& y = c->lm[li];
+    SOp* o;
+    RET(b.gemv(y.wo, nullptr, c->s_attn, nq, c->s_h, H, M, H, nq, false, &o));
+    o->init_dst = c->s_qkv; o->init_n = (long long)M * c->Nqkv;
+    o->init2_dst = c->s_lgu; o->init2_n = (long long)M * 2 * I;
+    RET(b.gemv(y.wgu, nullptr, c->s_h, H, c->s_lgu, 2 * I, M, 2 * I, H, true, &o));
+    o->pro = SP_RMSNORM; o->pro_w = y.ln2; o->pro_eps = d.rms_norm_eps;
+    RET(b.gemv(y.wdown, nullptr, c->s_lgu, 2 * I, c->s_h, H, M, H, I, true, &o));
+    o->pro = SP_SWIGLU;
+    if (li + 1 < li1) RET(qkv(li + 1));
+  }
+  vv_ctx::StreamProg pr;
+  RET(finish_stream(b, &pr));
+  it = c->sprogs.emplace(key, pr).first;
+  *out = &it->second;
+  return 0;
+}
+
 // decoder layers [li0, li1) over the residual stream s_h (rows = 2B sequences; rows with row_mode 0 neither read nor append KV)
-static int enqueue_lm_layers(const L& l, int li0, int li1) {
+static int enqueue_lm_layers(const L& l, int li0, int li1, const vv_ctx::StreamProg* sprog = nullptr) {
   vv_ctx* c = l.c;
   const auto& d = c->d;
   const int H = d.hidden_size, I = d.intermediate_size, M = 2 * d.max_batch, nq = d.num_q_heads * HD;
   const size_t per_layer = (size_t)c->n_pages * d.num_kv_heads * KV_PAGE * HD;
   const float scale = 1.0f / sqrtf((float)HD);
+  if (sprog) RET(launch_stream(l, *sprog, 0, 2));
   for (int li = li0; li < li1; ++li) {
     const LmLayer& y = c->lm[li];
     GemvP p = mk(y.wqkv, y.bqkv, c->s_h, H, c->s_qkv, c->Nqkv, M, c->Nqkv, H);
     p.pro = PRO_RMSNORM; p.pro_w = y.ln1; p.pro_eps = d.rms_norm_eps;
-    RET(linear(l, p));
+    if (!sprog) RET(linear(l, p));
     KvView kv;
     kv.kpool = c->kpool + per_layer * li; kv.vpool = c->vpool + per_layer * li;
     kv.page_table = c->page_table_dev; kv.max_pages = c->max_pages; kv.kv_len = c->kv_len_dev; kv.row_mode = c->row_mode_dev;
@@ -1157,6 +1237,7 @@ static int enqueue_lm_layers(const L& l, int li0, int li1) {
       }
     }
     CK(launch_k(l, attn_combine_kernel, dim3(d.num_q_heads, M), dim3(128), 0, c->s_pacc, c->s_pml, c->row_mode_dev, c->s_attn, d.num_q_heads, c->nsplit));
+    if (sprog) { RET(launch_stream(l, *sprog, 2 + 4 * (li - li0), li + 1 < li1 ? 4 : 3)); continue; }
     p = mk(y.wo, nullptr, c->s_attn, nq, c->s_h, H, M, H, nq);
     p.epi = EPI_RESID; p.res = c->s_h; p.ldres = H;
     RET(linear(l, p));
@@ -1179,11 +1260,11 @@ static int enqueue_final_norm(const L& l, float* hidden) {
   return 0;
 }
 
-static int enqueue_lm_decode(const L& l, const float* embeds, float* hidden, float* logits, int32_t* tokens) {
+static int enqueue_lm_decode(const L& l, const float* embeds, float* hidden, float* logits, int32_t* tokens, const vv_ctx::StreamProg* sprog) {
   vv_ctx* c = l.c;
   const int H = c->d.hidden_size, M = 2 * c->d.max_batch;
   CK(cudaMemcpyAsync(c->s_h, embeds, (size_t)M * H * 4, cudaMemcpyDeviceToDevice, l.s));
-  RET(enqueue_lm_layers(l, 0, c->d.num_layers));
+  RET(enqueue_lm_layers(l, 0, c->d.num_layers, sprog));
   RET(enqueue_final_norm(l, hidden));
   return enqueue_lm_head(l, hidden, logits, tokens);
 }
@@ -1192,11 +1273,11 @@ static int enqueue_lm_decode(const L& l, const float* embeds, float* hidden, flo
 // (modeling_vibevoice_streaming.py:134-146); each stack keeps its own KV sequences (lengths differ: the upper stack also sees the speech
 // positions).  One call runs layers [begin, end) for the rows enabled by vv_set_row_mode, appends their K/V speculatively at kv_len (commit
 // with vv_kv_commit as for vv_lm_decode) and returns the residual stream -- normalised with the model's final norm iff final_norm != 0.
-static int enqueue_lm_range(const L& l, const float* embeds, int li0, int li1, int final_norm, float* hidden) {
+static int enqueue_lm_range(const L& l, const float* embeds, int li0, int li1, int final_norm, float* hidden, const vv_ctx::StreamProg* sprog) {
   vv_ctx* c = l.c;
   const int H = c->d.hidden_size, M = 2 * c->d.max_batch;
   CK(cudaMemcpyAsync(c->s_h, embeds, (size_t)M * H * 4, cudaMemcpyDeviceToDevice, l.s));
-  RET(enqueue_lm_layers(l, li0, li1));
+  RET(enqueue_lm_layers(l, li0, li1, sprog));
   if (final_norm) return enqueue_final_norm(l, hidden);
   CK(cudaMemcpyAsync(hidden, c->s_h, (size_t)M * H * 4, cudaMemcpyDeviceToDevice, l.s));
   return 0;
@@ -1208,7 +1289,9 @@ extern "C" int vv_lm_decode(vv_ctx* c, const float* embeds, float* hidden, float
   for (int s = 0; s < 2 * c->d.max_batch; ++s) RET(vv_kv_reserve(c, s, c->kv_len_host[s] + 1, stream));
   char key[256];
   snprintf(key, sizeof key, "lm:%p:%p:%p:%p", (const void*)embeds, (void*)hidden, (void*)logits, (void*)tokens);
-  return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_lm_decode(l, embeds, hidden, logits, tokens); });
+  const vv_ctx::StreamProg* sprog = nullptr;      // built outside stream capture
+  if (c->use_stream & 2) RET(lm_stream_prog(c, 0, c->d.num_layers, &sprog));
+  return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_lm_decode(l, embeds, hidden, logits, tokens, sprog); });
 }
 extern "C" int vv_lm_head(vv_ctx* c, const float* hidden, float* logits, int32_t* tokens, void* stream) {
   if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
@@ -1237,7 +1320,9 @@ extern "C" int vv_lm_decode_range(vv_ctx* c, const float* embeds, int layer_begi
   for (int s = 0; s < 2 * c->d.max_batch; ++s) RET(vv_kv_reserve(c, s, c->kv_len_host[s] + 1, stream));
   char key[256];
   snprintf(key, sizeof key, "lmr:%p:%p:%d:%d:%d", (const void*)embeds, (void*)hidden, layer_begin, layer_end, final_norm);
-  return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_lm_range(l, embeds, layer_begin, layer_end, final_norm, hidden); });
+  const vv_ctx::StreamProg* sprog = nullptr;
+  if (c->use_stream & 2) RET(lm_stream_prog(c, layer_begin, layer_end, &sprog));
+  return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_lm_range(l, embeds, layer_begin, layer_end, final_norm, hidden, sprog); });
 }
 
 extern "C" int vv_embed_tokens(vv_ctx* c, const int32_t* tokens_host, int n, float* out, void* stream) {
@@ -1284,6 +1369,8 @@ static int set_diffusion_steps(vv_ctx* c, int n_steps, const float* timesteps, c
     cf[i].rinv = coef[i * ncol + 4]; cf[i].order = (int)coef[i * ncol + 5]; cf[i].kn = ncol == 7 ? coef[i * ncol + 6] : 0.f;
   }
   c->sde = (ncol == 7);
+  c->coef_host = cf;
+  c->coef_version++;
   CK(cudaStreamSynchronize(s));
   CK(cudaMemcpy(c->coef_dev, cf.data(), sizeof(DpmCoef) * n_steps, cudaMemcpyHostToDevice));
   float* tdev = c->s_t1;   // reuse as staging for the timesteps (n floats) before it is overwritten below
@@ -1343,7 +1430,8 @@ static int set_cfg(vv_ctx* c, float cfg, cudaStream_t s) {
 // per step instead of 10 kernels, and the TMA ring keeps streaming head weights across all of them.
 static int sampler_stream_prog(vv_ctx* c, const float* noise, float* latent_out, const vv_ctx::StreamProg** out) {
   char key[256];
-  snprintf(key, sizeof key, "samp:%p:%p:%d:%d:%p", (const void*)noise, (void*)latent_out, c->n_steps, (int)c->sde, (const void*)c->step_noise);
+  snprintf(key, sizeof key, "samp:%p:%p:%d:%d:%p:%d", (const void*)noise, (void*)latent_out, c->n_steps, (int)c->sde, (const void*)c->step_noise,
+           c->coef_version);       // solver coefficients are baked into the program
   auto it = c->sprogs.find(key);
   if (it != c->sprogs.end()) { *out = &it->second; return 0; }
   const auto& d = c->d;
@@ -1358,15 +1446,15 @@ static int sampler_stream_prog(vv_ctx* c, const float* noise, float* latent_out,
       o.z_in = c->s_z + (size_t)(i & 1) * B * 64; o.z_out = c->s_z + (size_t)((i + 1) & 1) * B * 64;
       o.x0_in = c->s_x0 + (size_t)(i & 1) * B * 64; o.x0_out = c->s_x0 + (size_t)((i + 1) & 1) * B * 64;
     }
-    o.v = c->s_v; o.noise = noise; o.coef = c->coef_dev; o.cfg_p = c->cfg_dev; o.step_noise = c->sde ? c->step_noise : nullptr;
+    o.v = c->s_v; o.noise = noise; o.cfg_p = c->cfg_dev; o.step_noise = c->sde ? c->step_noise : nullptr;
     o.latent_out = (i == N - 1) ? latent_out : nullptr; o.step = i; o.B = B;
+    if (i >= 0) o.c = c->coef_host[i];
     return o;
   };
   auto proj = [&](int i, bool sync) -> int {       // x = noisy_images_proj(z'), z' = solver update of step i (i = -1: the initial noise)
     SOp* o;
     RET(b.gemv(c->h_noisy, nullptr, nullptr, 0, c->s_hx, H, M, H, 64, sync, &o));
-    o->pro = SP_DPM; o->store = 1;
-    b.attach_dpm(dpm(i));
+    o->pro = SP_DPM; o->store = 1; o->dpm = dpm(i);
     return 0;
   };
   float* gu[2] = {c->s_hgu, c->s_hgu + (size_t)M * 2 * F};
@@ -1447,7 +1535,7 @@ extern "C" int vv_diffusion_sample(vv_ctx* c, const float* cond, const float* no
   char key[256];
   snprintf(key, sizeof key, "diff:%p:%p:%p", (const void*)cond, (const void*)noise, (void*)latent_out);
   const vv_ctx::StreamProg* sprog = nullptr;      // built outside stream capture (it allocates and copies)
-  if (c->use_stream) RET(sampler_stream_prog(c, noise, latent_out, &sprog));
+  if (c->use_stream & 1) RET(sampler_stream_prog(c, noise, latent_out, &sprog));
   return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_diffusion(l, cond, noise, latent_out, sprog); });
 }
 
@@ -1614,7 +1702,7 @@ extern "C" int vv_frame_tail(vv_ctx* c, const float* hidden, const float* noise,
   snprintf(key, sizeof key, "tail:%p:%p:%p:%p:%p:%p", (const void*)hidden, (const void*)noise, (const void*)active, (void*)latent_out,
            (void*)audio_out, (void*)embeds);
   const vv_ctx::StreamProg* sprog = nullptr;
-  if (c->use_stream) RET(sampler_stream_prog(c, noise, latent_out, &sprog));
+  if (c->use_stream & 1) RET(sampler_stream_prog(c, noise, latent_out, &sprog));
   return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) {
     RET(enqueue_diffusion(l, hidden, noise, latent_out, sprog));
     RET(enqueue_decode(l, latent_out, active, audio_out));
@@ -1670,6 +1758,7 @@ extern "C" int vv_debug_stream_gemv(vv_ctx* c, const void* w, const float* bias,
   if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
   CK(cudaSetDevice(c->device));
   StreamBuilder b(c);
+  b.fresh_weights = true;
   if (!accumulate) b.nop(false, y, (long long)M * N);
   SOp* o;
   RET(b.gemv((const bf16*)w, bias, x, pro == SP_SWIGLU ? 2LL * K : (long long)K, y, N, M, N, K, !accumulate, &o));
@@ -1679,9 +1768,55 @@ extern "C" int vv_debug_stream_gemv(vv_ctx* c, const void* w, const float* bias,
   L l{c, (cudaStream_t)stream};
   RET(launch_stream(l, pr));
   CK(cudaStreamSynchronize((cudaStream_t)stream));
-  dfree(c, &pr.ops); dfree(c, &pr.tmaps); dfree(c, &pr.dpm);
+  dfree(c, &pr.ops); dfree(c, &pr.tmaps);
+  for (bf16* t : b.owned) dfree(c, &t);
   if (c->st_diag_host[0]) return fail(VV_ERR_CUDA, "stream kernel watchdog: code %u cta %u thread %u a %u b %u c %u", c->st_diag_host[0], c->st_diag_host[1],
                                       c->st_diag_host[2], c->st_diag_host[3], c->st_diag_host[4], c->st_diag_host[5]);
+  return 0;
+}
+// clock stamps of the last traced stream launch (VV_STREAM_TRACE=<cta>): out [n_ops][12] int64; returns the number of stages, 0 if tracing is off.
+// Stage kinds / shapes are appended per stage in out_meta [n_ops][4] = {kind, N, K, prologue}.
+extern "C" int vv_stream_trace_read2(vv_ctx* c, long long* out, int max_ops) {     // [n_ops][sm_count][2] barrier arrival / release (ns)
+  if (!c || !c->st_trace2) return 0;
+  CK(cudaDeviceSynchronize());
+  const int n = std::min(max_ops, c->st_trace_last_ops);
+  CK(cudaMemcpy(out, c->st_trace2, (size_t)n * c->sm_count * 2 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return c->sm_count;
+}
+extern "C" int vv_stream_trace_read(vv_ctx* c, long long* out, int* out_meta, int max_ops, const char* prog_prefix) {
+  if (!c || !c->st_trace) return 0;
+  CK(cudaDeviceSynchronize());
+  const int n = std::min(max_ops, c->st_trace_last_ops);
+  CK(cudaMemcpy(out, c->st_trace, (size_t)n * ST_TRACE * sizeof(long long), cudaMemcpyDeviceToHost));
+  for (auto& kv : c->sprogs) {
+    if (kv.first.rfind(prog_prefix, 0) != 0 || kv.second.n_ops != c->st_trace_last_ops) continue;
+    std::vector<SOp> ops(kv.second.n_ops);
+    CK(cudaMemcpy(ops.data(), kv.second.ops, ops.size() * sizeof(SOp), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) { out_meta[4 * i] = ops[i].kind; out_meta[4 * i + 1] = ops[i].N; out_meta[4 * i + 2] = ops[i].K; out_meta[4 * i + 3] = ops[i].pro; }
+    break;
+  }
+  return n;
+}
+// tcgen05.mma 128 x nB x 16 rate micro-benchmark (vv_stream.cuh: mma_rate_kernel); cycles_out = median over CTAs of the loop's SM cycles
+extern "C" int vv_debug_mma_rate(vv_ctx* c, int n, int nB, int mode, int nacc, int ctas, long long* cycles_out) {
+  if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
+  CK(cudaSetDevice(c->device));
+  if (nacc < 1 || nacc * nB > 512 || nB > 256) return fail(VV_ERR_INVALID, "nacc * nB must be <= 512, nB <= 256");
+  long long* d = nullptr;
+  CK(cudaMalloc(&d, sizeof(long long) * 2 * ctas));
+  CK(cudaMemset(d, 0, sizeof(long long) * 2 * ctas));
+  const int smem = 8 * ST_TILE + 32768 + 1024;
+  CK(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  mma_rate_kernel<<<ctas, 128, smem>>>(n, nB, mode, nacc, d);
+  CKL();
+  CK(cudaDeviceSynchronize());
+  std::vector<long long> h(2 * ctas);
+  CK(cudaMemcpy(h.data(), d, sizeof(long long) * 2 * ctas, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  std::sort(h.begin(), h.begin() + ctas);
+  std::sort(h.begin() + ctas, h.end());
+  cycles_out[0] = h[ctas / 2];              // whole loop incl. completion
+  cycles_out[1] = h[ctas + ctas / 2];       // issue loop only
   return 0;
 }
 // watchdog record of the last stream kernel that trapped: out[0] = code (0 = none), out[1..5] = cta, thread, stage, iteration, extra

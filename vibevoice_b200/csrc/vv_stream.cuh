@@ -85,6 +85,7 @@ constexpr int ST_WORKERS = 128;
 constexpr int ST_TILE = 16384;           // one weight tile: 128 rows x 64 bf16
 constexpr int ST_MAXSEG = 8;             // (row tile, k range) segments a CTA may own in one stage
 constexpr int ST_MAX_STAGES = 12;
+constexpr int ST_BAR_REP = 0;
 
 enum SKind { SK_GEMV = 0, SK_NOP = 1 };
 enum SPro { SP_NONE = 0, SP_RMSNORM = 1, SP_ADALN = 2, SP_SWIGLU = 3, SP_GELU = 4, SP_DPM = 5, SP_SILU = 6 };
@@ -93,36 +94,60 @@ enum SAlpha { SA_ONE = 0, SA_GATE = 1 /* alpha[m][n], row stride lda */, SA_GAMM
 // CFG + DPM-Solver++ update of step `step` (same arithmetic as dpm_update_proj_kernel), evaluated in the prologue of the stage that
 // projects the new latent (noisy_images_proj): B-operand row m = z'[m mod B].
 struct SDpm {
-  const float* z_in; float* z_out; const float* x0_in; float* x0_out; const float* v; const float* noise; const DpmCoef* coef;
+  const float* z_in; float* z_out; const float* x0_in; float* x0_out; const float* v; const float* noise;
   const float* cfg_p; const float* step_noise; float* latent_out;
   int step, B;
+  DpmCoef c;                // coefficients of this step, by value (no dependent loads on the critical path)
 };
 
-struct SOp {
+struct alignas(16) SOp {
   int kind;
   int sync_before;          // wait until every CTA has finished the previous stage (grid barrier) before touching activations
   int M, N, K;              // activation rows, weight rows (outputs), reduction length (K % 8 == 0)
   int nB;                   // MMA N: 16, 32 or 64 (rows [0,nB/2) = hi, [nB/2,nB) = lo)
-  unsigned long long tmap;  // device address of the CUtensorMap of W [N][K] bf16 (box 64 x 128, SWIZZLE_128B)
+  unsigned long long tmap;  // device address of the CUtensorMap of the TILE-MAJOR copy of W: [R*KB tiles][128 rows][64 k] bf16, zero padded
+                            // (seen as a 2-D tensor [R*KB*128][64]; box 64 x 128 = one contiguous 16 KB tile, SWIZZLE_128B)
   int pro;
   const float* x; long long ldx;         // activations, row stride in floats (SP_SWIGLU: interleaved gate/up sums, row length 2K)
   const float* pro_w; float pro_eps;     // norm weight [K] (may be null for SP_ADALN)
   const float* pro_shift; const float* pro_scale; long long pro_ld;
-  const SDpm* dpm;
+  SDpm dpm;                              // SP_DPM only
   float* y; long long ldy;               // y[m][n] += alpha * (acc + bias[n] if the segment starts at k = 0);  store != 0: y = ... (KB == 1 only)
   const float* bias;
   int alpha_kind; const float* alpha; long long lda;
   int store;
-  float* init_dst; long long init_n;     // optional: zero-fill job (a buffer a LATER stage accumulates into), spread over the grid
+  float* init_dst; long long init_n;     // optional: zero-fill jobs (buffers a LATER stage accumulates into), spread over the grid
+  float* init2_dst; long long init2_n;
 };
 
 struct SParams {
   const SOp* ops; int n_ops;
-  unsigned* bar_count;      // zeroed by the host before every launch
+  unsigned* bar_count;      // arrival counter of the grid barrier, zeroed by the host before every launch
   unsigned* diag;           // host-mapped: [0] = error code, [1..7] = where (watchdog)
   int n_stages;             // ring depth
   int b_bytes;              // bytes of the activation-operand region
+  int max_inflight;         // TMA tiles a CTA may have in flight (<= n_stages)
+  long long* trace;         // optional [n_ops][ST_TRACE] clock64 stamps of CTA `trace_cta` (tools/stream_trace.py), else null
+  int trace_cta;
+  long long* trace2;        // optional [n_ops][G][2] globaltimer (ns) of every CTA: arrival at / release from the grid barrier
 };
+constexpr int ST_TRACE = 12;   // 0 op start, 1 barrier passed, 2 row stats done, 3 B operand staged, 4 accumulators complete, 5 epilogue issued,
+                               // 6 MMA saw b_ready, 7 MMA saw the last tile, 8 MMA committed, 9 producer issued the last tile of the stage
+
+// W [N][K] row-major -> tile-major [R][KB][128][64], zero padded.  Measured (profiles/r02_stream_trace_1.txt): TMA boxes cut out of the
+// row-major matrix (128 rows x 128 B, 3 KB apart) stream at 2.4 TB/s -- every row is its own DRAM burst -- so the kernel reads tiles that are
+// contiguous in HBM instead; units of a stage are consecutive tiles, i.e. every CTA reads ONE contiguous byte range per stage.
+__global__ void tile_pack_kernel(const bf16* __restrict__ W, bf16* __restrict__ T, int N, int K, int KB, long long n_chunks) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_chunks; i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i & 7), r = (int)((i >> 3) & 127);
+    const long long tile = i >> 10;
+    const int kb = (int)(tile % KB), rt = (int)(tile / KB);
+    const int n = rt * 128 + r, k = kb * 64 + ch * 8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (n < N && k < K) v = *reinterpret_cast<const uint4*>(W + (size_t)n * K + k);       // K % 8 == 0: a chunk never straddles K
+    *reinterpret_cast<uint4*>(T + i * 8) = v;
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------------------------------------
 // device helpers
@@ -156,17 +181,19 @@ VV_DEVINL void tma_load_2d(void* smem_dst, unsigned long long tmap, int c0, int 
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
                ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
+VV_DEVINL long long gtime_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 VV_DEVINL float ldcg1(const float* p) { return __ldcg(p); }
 VV_DEVINL float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 VV_DEVINL void red_add_f32(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 VV_DEVINL void worker_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // this CTA's unit range of a stage: units are (row tile, k-block) pairs in row-tile-major order
-VV_DEVINL void st_part(const SOp& op, long long& u0, long long& u1, int& KB) {
+// (32-bit arithmetic: U * gridDim < 2^32 is checked on the host; 64-bit divisions here cost ~0.3 us per stage on the critical path)
+VV_DEVINL void st_part(const SOp& op, unsigned& u0, unsigned& u1, int& KB) {
   KB = (op.K + 63) >> 6;
-  const long long U = (long long)((op.N + 127) >> 7) * KB;
-  u0 = U * (long long)blockIdx.x / (long long)gridDim.x;
-  u1 = U * (long long)(blockIdx.x + 1) / (long long)gridDim.x;
+  const unsigned U = (unsigned)((op.N + 127) >> 7) * (unsigned)KB;
+  u0 = U * blockIdx.x / gridDim.x;
+  u1 = U * (blockIdx.x + 1u) / gridDim.x;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------
@@ -180,6 +207,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
   __shared__ float s_red[4][8];
   __shared__ float s_inv[64];
   __shared__ float s_z[8 * 64];
+  __shared__ __align__(16) unsigned char s_opbuf[2][sizeof(SOp)];
   const unsigned raw_addr = smem_u32(st_raw);
   unsigned char* sm = st_raw + ((1024u - (raw_addr & 1023u)) & 1023u);      // 1024 B aligned (swizzle atom)
   unsigned char* ring = sm;
@@ -208,58 +236,90 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
     if (lane == 0) {
       unsigned long long policy;
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-      unsigned it = 0;
+      unsigned it = 0, done = 0;
+      const unsigned cap = (unsigned)P.max_inflight;
       for (int oi = 0; oi < P.n_ops; ++oi) {
         const SOp& op = P.ops[oi];
         if (op.kind != SK_GEMV) continue;
-        long long u0, u1; int KB;
+        unsigned u0, u1; int KB;
         st_part(op, u0, u1, KB);
         const unsigned long long tmap = op.tmap;
-        int rt = (int)(u0 / KB), kb = (int)(u0 % KB);
-        for (long long u = u0; u < u1; ++u, ++it) {
+        for (unsigned u = u0; u < u1; ++u, ++it) {
           const unsigned slot = it % (unsigned)NS, ph = (it / (unsigned)NS) & 1u;
+          // at most `cap` tiles of this CTA are in flight: the ring may be deep (it buffers ARRIVED tiles across the barriers), but every
+          // request queued in the memory system delays the latency-critical activation loads and barrier traffic of the other warps
+          while (it - done >= cap) {
+            mbar_wait_wd(&full_bar[done % (unsigned)NS], (done / (unsigned)NS) & 1u, P.diag, 6u, (unsigned)oi, done);
+            ++done;
+          }
           mbar_wait_wd(&empty_bar[slot], ph ^ 1u, P.diag, 1u, (unsigned)oi, it);
           mbar_expect_tx(&full_bar[slot], (unsigned)ST_TILE);
-          tma_load_2d(ring + (size_t)slot * ST_TILE, tmap, kb * 64, rt * 128, &full_bar[slot], policy);
-          if (++kb == KB) { kb = 0; ++rt; }
+          // tile-major weights: unit u = (row tile, k-block) is the contiguous 16 KB block u, so a CTA streams one contiguous range
+          tma_load_2d(ring + (size_t)slot * ST_TILE, tmap, 0, (int)(u * 128), &full_bar[slot], policy);
         }
+        if (P.trace && (int)blockIdx.x == P.trace_cta) P.trace[(size_t)oi * ST_TRACE + 9] = clock64();
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      unsigned it = 0, gi = 0;
-      for (int oi = 0; oi < P.n_ops; ++oi) {
-        const SOp& op = P.ops[oi];
-        if (op.kind != SK_GEMV) continue;
-        long long u0, u1; int KB;
-        st_part(op, u0, u1, KB);
-        if (u0 == u1) continue;
-        const int nB = op.nB;
-        // instruction descriptor: D = f32, A = B = bf16, both K-major, N = nB, M = 128
-        const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(nB >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
-        const int kb_first = (int)(u0 % KB), rt_first = (int)(u0 / KB);
-        mbar_wait_wd(&b_ready, gi & 1u, P.diag, 2u, (unsigned)oi, gi);
+    // The WHOLE warp runs this loop converged and one elected lane issues (elect.sync inside the asm block).  Measured
+    // (profiles/r02_mma_rate.txt): tcgen05.mma issued from `if (lane == 0)` with per-iteration operands costs 424 cycles per instruction
+    // (the compiler wraps UTCHMMA in a per-thread uniformisation loop), 84 from a converged warp, 46 with loop-invariant operands --
+    // at 4 MMAs per 16 KB tile the first form alone capped a CTA at HBM speed.
+    unsigned slot = 0, ph = 0, gi = 0;
+    for (int oi = 0; oi < P.n_ops; ++oi) {
+      const SOp& op = P.ops[oi];
+      if (op.kind != SK_GEMV) continue;
+      unsigned u0, u1; int KB;
+      st_part(op, u0, u1, KB);
+      if (u0 == u1) continue;
+      const int nB = op.nB;
+      // instruction descriptor: D = f32, A = B = bf16, both K-major, N = nB, M = 128
+      const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(nB >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+      const int kb_first = (int)(u0 % (unsigned)KB);
+      const int units = (int)(u1 - u0);
+      const unsigned long long db0 = umma_desc_sw128(smem_u32(breg));
+      const unsigned long long da0 = umma_desc_sw128(smem_u32(ring));
+      const unsigned bstep = (unsigned)(nB * 128) >> 4;          // descriptor start-address units (16 B) per k-block of the B operand
+      mbar_wait_wd(&b_ready, gi & 1u, P.diag, 2u, (unsigned)oi, gi);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const bool tr = P.trace && (int)blockIdx.x == P.trace_cta && lane == 0;
+      if (tr) P.trace[(size_t)oi * ST_TRACE + 6] = clock64();
+      int kb = kb_first;                                         // k-block of the current unit; jloc = position in the staged B region
+      unsigned jloc = 0, dcol = tmem, fresh = 1;
+      for (int ui = 0; ui < units; ++ui) {
+        mbar_wait_wd(&full_bar[slot], ph, P.diag, 3u, (unsigned)oi, (unsigned)ui);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        int rt = rt_first, kb = kb_first;
-        bool fresh = true;                              // first k-block of a segment overwrites its accumulator
-        for (long long u = u0; u < u1; ++u, ++it) {
-          const unsigned slot = it % (unsigned)NS, ph = (it / (unsigned)NS) & 1u;
-          mbar_wait_wd(&full_bar[slot], ph, P.diag, 3u, (unsigned)oi, it);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          int jloc = kb - kb_first; if (jloc < 0) jloc += KB;
-          const unsigned long long da = umma_desc_sw128(smem_u32(ring + (size_t)slot * ST_TILE));
-          const unsigned long long db = umma_desc_sw128(smem_u32(breg + (size_t)jloc * (size_t)(nB * 128)));
-          const unsigned dcol = tmem + (unsigned)((rt - rt_first) * nB);
-#pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) tc5_mma(dcol, da + 2 * k4, db + 2 * k4, idesc, (fresh && k4 == 0) ? 0u : 1u);
-          tc5_commit(&empty_bar[slot]);                 // slot is free once these MMAs have read it
-          fresh = false;
-          if (++kb == KB) { kb = 0; ++rt; fresh = true; }
-        }
-        tc5_commit(&acc_full);                          // accumulators of this stage are complete
-        ++gi;
+        const unsigned long long da = da0 + (unsigned long long)(slot * (unsigned)(ST_TILE >> 4));
+        const unsigned long long db = db0 + (unsigned long long)(jloc * bstep);
+        const unsigned ebar = smem_u32(&empty_bar[slot]);
+        asm volatile(
+            "{\n\t.reg .pred e, p, t;\n\t"
+            "elect.sync _|e, 0xffffffff;\n\t"
+            "setp.eq.b32 p, %5, 0;\n\t"
+            "setp.eq.b32 t, 0, 0;\n\t"
+            "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %6, %7, %3, t;\n\t"
+            "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %8, %9, %3, t;\n\t"
+            "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %10, %11, %3, t;\n\t"
+            "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%4];\n\t"
+            "}"
+            ::"r"(dcol), "l"(da), "l"(db), "r"(idesc), "r"(ebar), "r"(fresh),
+              "l"(da + 2), "l"(db + 2), "l"(da + 4), "l"(db + 4), "l"(da + 6), "l"(db + 6) : "memory");
+        fresh = 0;
+        if (++slot == (unsigned)NS) { slot = 0; ph ^= 1u; }
+        ++jloc;
+        if (++kb == KB) { kb = 0; dcol += (unsigned)nB; fresh = 1; }     // next row tile: its own accumulator, first MMA overwrites
+        if (jloc == (unsigned)KB) jloc = 0;                                // (only when the CTA holds >= KB units: B region = all k-blocks)
       }
+      if (tr) P.trace[(size_t)oi * ST_TRACE + 7] = clock64();
+      {
+        const unsigned abar = smem_u32(&acc_full);
+        asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+                     ::"r"(abar) : "memory");
+      }
+      if (tr) P.trace[(size_t)oi * ST_TRACE + 8] = clock64();
+      ++gi;
     }
   } else {
     // =============================== workers: barrier, prologue (B operand), epilogue ===============================
@@ -267,13 +327,28 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
     const int wq = warp & 3;                  // TMEM lane quadrant this warp may read
     const int ww = warp - 2;
     unsigned gi = 0, bar_target = 0;
+    // stage descriptors are copied into shared memory ONE STAGE AHEAD (cp.async): read straight from global memory, each first touch of a
+    // descriptor field was an L2/DRAM round trip on the critical path (~1 us per stage, profiles/r02_stream_trace_2.txt)
+    constexpr int OPCH = (int)(sizeof(SOp) / 16);
+    if (wt < OPCH) cp_async16(s_opbuf[0] + wt * 16, reinterpret_cast<const unsigned char*>(P.ops) + wt * 16, 16);
+    cp_async_commit();
+    cp_async_wait<0>();
+    worker_sync();
     for (int oi = 0; oi < P.n_ops; ++oi) {
-      const SOp& op = P.ops[oi];
+      const SOp& op = *reinterpret_cast<const SOp*>(s_opbuf[oi & 1]);
+      if (oi + 1 < P.n_ops && wt < OPCH)
+        cp_async16(s_opbuf[(oi + 1) & 1] + wt * 16, reinterpret_cast<const unsigned char*>(P.ops + oi + 1) + wt * 16, 16);
+      cp_async_commit();
+      const bool tr = P.trace && (int)blockIdx.x == P.trace_cta && wt == 0;
+      if (tr) P.trace[(size_t)oi * ST_TRACE + 0] = clock64();
+      do {
       if (op.sync_before) {
-        bar_target += G;
-        worker_sync();                         // every worker's global writes of the previous stage are issued ...
+        bar_target += G;                       // (every worker's global writes of the previous stage were issued before the sync that ended it)
         if (wt == 0) {
-          __threadfence();                     // ... and ordered before this CTA's arrival (cumulativity through bar.sync)
+          if (P.trace2) P.trace2[((size_t)oi * G + blockIdx.x) * 2] = gtime_ns();
+          // arrival = one fire-and-forget release reduction, then poll the counter.  (Tried, profiles/r02_stream_trace_7.txt: a returning
+          // atomic + release words replicated over 16 lines for the pollers -- 2.6 us from last arrival to last release against 1.5 us for
+          // this form: under the weight stream every dependent L2 round trip costs ~0.7 us, so the form with the fewest of them wins.)
           red_add_release_u32(P.bar_count, 1u);
           long long t0 = 0;
           for (unsigned spins = 0; ld_acquire_u32(P.bar_count) < bar_target; ++spins) {
@@ -283,52 +358,157 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
               else if (t - t0 > 6000000000ll) st_die(P.diag, 4u, (unsigned)oi, bar_target, ld_acquire_u32(P.bar_count));
             }
           }
+          if (P.trace2) P.trace2[((size_t)oi * G + blockIdx.x) * 2 + 1] = gtime_ns();
         }
         worker_sync();
       }
+      if (tr) P.trace[(size_t)oi * ST_TRACE + 1] = clock64();
       if (op.init_dst) {
         for (long long i = (long long)blockIdx.x * ST_WORKERS + wt; i < op.init_n; i += (long long)G * ST_WORKERS) op.init_dst[i] = 0.f;
       }
-      if (op.kind != SK_GEMV) continue;
-      long long u0, u1; int KB;
+      if (op.init2_dst) {
+        for (long long i = (long long)blockIdx.x * ST_WORKERS + wt; i < op.init2_n; i += (long long)G * ST_WORKERS) op.init2_dst[i] = 0.f;
+      }
+      if (op.kind != SK_GEMV) break;
+      unsigned u0, u1; int KB;
       st_part(op, u0, u1, KB);
-      if (u0 == u1) continue;
+      if (u0 == u1) break;
       const int M = op.M, K = op.K, N = op.N, nB = op.nB, half = nB >> 1;
       const int units = (int)(u1 - u0);
       const int count = units < KB ? units : KB;          // k-blocks of activations this CTA needs (contiguous mod KB from kb_first)
-      const int kb_first = (int)(u0 % KB), rt_first = (int)(u0 / KB);
+      const int rt_first = (int)(u0 / (unsigned)KB), kb_first = (int)(u0 - (unsigned)rt_first * (unsigned)KB);
       const int pro = op.pro;
-      // ---------------- row statistics (full rows) ----------------
-      if (pro == SP_RMSNORM || pro == SP_ADALN) {
-        for (int m0 = 0; m0 < M; m0 += 8) {
-          float ss[8];
+      // ---------------- prologue: ONE batch of L2 loads (row statistics + the first activation chunks), then compute ----------------
+      // (measured, profiles/r02_stream_trace_1.txt: a statistics loop followed by a staging loop costs one L2 round trip per loop
+      //  iteration, 4.4 us per AdaLN stage; every load below is issued before the first value is consumed)
+      const int total = M * count * 8;                     // 16-byte chunks (8 consecutive k of one activation row) to stage
+      const bool norm = (pro == SP_RMSNORM || pro == SP_ADALN);
+      auto chunk_coord = [&](int c, int& m, int& jloc, int& ch, int& k) {
+        m = c / (count * 8);
+        const int r = c - m * (count * 8);
+        jloc = r >> 3; ch = r & 7;
+        int kb = kb_first + jloc; if (kb >= KB) kb -= KB;
+        k = kb * 64 + ch * 8;
+      };
+      auto chunk_load = [&](int c, float4 (&in)[8]) {       // raw operands of one chunk (nothing is consumed here)
+        int m, jloc, ch, k;
+        chunk_coord(c, m, jloc, ch, k);
+        if (c >= total || k >= K || pro == SP_DPM) return;
+        if (pro == SP_SWIGLU) {
+          const float* xr = op.x + (long long)m * op.ldx + 2 * k;
+          in[0] = ldcg4(xr); in[1] = ldcg4(xr + 4); in[2] = ldcg4(xr + 8); in[3] = ldcg4(xr + 12);
+          return;
+        }
+        const float* xr = op.x + (long long)m * op.ldx + k;
+        in[0] = ldcg4(xr); in[1] = ldcg4(xr + 4);
+        if (norm) {
+          if (op.pro_w) { in[2] = *reinterpret_cast<const float4*>(op.pro_w + k); in[3] = *reinterpret_cast<const float4*>(op.pro_w + k + 4); }
+          else { in[2] = make_float4(1.f, 1.f, 1.f, 1.f); in[3] = in[2]; }
+        }
+        if (pro == SP_ADALN) {
+          const long long o = (long long)m * op.pro_ld + k;
+          in[4] = ldcg4(op.pro_scale + o); in[5] = ldcg4(op.pro_scale + o + 4);
+          in[6] = ldcg4(op.pro_shift + o); in[7] = ldcg4(op.pro_shift + o + 4);
+        }
+      };
+      auto chunk_store = [&](int c, const float4 (&in)[8]) {
+        if (c >= total) return;
+        int m, jloc, ch, k;
+        chunk_coord(c, m, jloc, ch, k);
+        float v[8];
+        if (k >= K) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) ss[j] = 0.f;
-          for (int q = wt; q < (K >> 2); q += ST_WORKERS) {
+          for (int j = 0; j < 8; ++j) v[j] = 0.f;          // k >= K: the weight tile is zero there, keep 0 * x finite
+        } else if (pro == SP_SWIGLU) {
+          v[0] = silu_f(in[0].x) * in[0].y; v[1] = silu_f(in[0].z) * in[0].w; v[2] = silu_f(in[1].x) * in[1].y; v[3] = silu_f(in[1].z) * in[1].w;
+          v[4] = silu_f(in[2].x) * in[2].y; v[5] = silu_f(in[2].z) * in[2].w; v[6] = silu_f(in[3].x) * in[3].y; v[7] = silu_f(in[3].z) * in[3].w;
+        } else if (pro == SP_DPM) {
+          const float* zr = s_z + (m % op.dpm.B) * 64 + k;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (m0 + j < M) {
-                const float4 v = ldcg4(op.x + (long long)(m0 + j) * op.ldx + 4 * q);
-                ss[j] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-              }
+          for (int j = 0; j < 8; ++j) v[j] = zr[j];
+        } else {
+          v[0] = in[0].x; v[1] = in[0].y; v[2] = in[0].z; v[3] = in[0].w; v[4] = in[1].x; v[5] = in[1].y; v[6] = in[1].z; v[7] = in[1].w;
+          if (norm) {
+            const float inv = s_inv[m];
+            const float w[8] = {in[2].x, in[2].y, in[2].z, in[2].w, in[3].x, in[3].y, in[3].z, in[3].w};
+            if (pro == SP_RMSNORM) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] *= inv * w[j];
+            } else {
+              const float sc[8] = {in[4].x, in[4].y, in[4].z, in[4].w, in[5].x, in[5].y, in[5].z, in[5].w};
+              const float sh[8] = {in[6].x, in[6].y, in[6].z, in[6].w, in[7].x, in[7].y, in[7].z, in[7].w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = v[j] * inv * w[j] * (1.f + sc[j]) + sh[j];
             }
-          }
+          } else if (pro == SP_GELU) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { ss[j] = warp_sum(ss[j]); if (lane == 0) s_red[ww][j] = ss[j]; }
-          worker_sync();
-          if (wt < 8 && m0 + wt < M) s_inv[m0 + wt] = rsqrtf((s_red[0][wt] + s_red[1][wt] + s_red[2][wt] + s_red[3][wt]) / (float)K + op.pro_eps);
-          worker_sync();
+            for (int j = 0; j < 8; ++j) v[j] = gelu_erf_f(v[j]);
+          } else if (pro == SP_SILU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+          }
+        }
+        float h[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+        const uint4 hv = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+        const uint4 lv = make_uint4(pack_bf16(v[0] - h[0], v[1] - h[1]), pack_bf16(v[2] - h[2], v[3] - h[3]),
+                                    pack_bf16(v[4] - h[4], v[5] - h[5]), pack_bf16(v[6] - h[6], v[7] - h[7]));
+        unsigned char* blk = breg + (size_t)jloc * (size_t)(nB * 128);
+        const int rl = half + m;
+        *reinterpret_cast<uint4*>(blk + (m >> 3) * 1024 + (m & 7) * 128 + ((ch ^ (m & 7)) << 4)) = hv;
+        *reinterpret_cast<uint4*>(blk + (rl >> 3) * 1024 + (rl & 7) * 128 + ((ch ^ (rl & 7)) << 4)) = lv;
+      };
+      float4 in0[8], in1[8];
+      chunk_load(wt, in0);                                  // first two chunks of this thread: in flight during the statistics
+      chunk_load(wt + ST_WORKERS, in1);
+      if (tr) P.trace[(size_t)oi * ST_TRACE + 10] = clock64();
+      if (norm) {
+        // sum of squares of every full row: rows in pairs, <= 16 float4 per thread in flight (K <= 4096), further columns looped
+        const int K4 = K >> 2;
+        const int rot = (int)((blockIdx.x * 67u) % (unsigned)K4);      // every CTA starts at a different column: the 148 SMs read the same
+        for (int m0 = 0; m0 < M; m0 += 2) {                              // rows at the same moment, in phase they queue on the same L2 lines
+          float4 sv[2][8];
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int q = wt + i * ST_WORKERS;
+              int qr = q + rot; if (qr >= K4) qr -= K4;
+              sv[r][i] = (m0 + r < M && q < K4) ? ldcg4(op.x + (long long)(m0 + r) * op.ldx + 4 * qr) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          float ss[2] = {0.f, 0.f};
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ss[r] += sv[r][i].x * sv[r][i].x + sv[r][i].y * sv[r][i].y + sv[r][i].z * sv[r][i].z + sv[r][i].w * sv[r][i].w;
+            if (m0 + r < M)
+              for (int q = wt + 8 * ST_WORKERS; q < K4; q += ST_WORKERS) {
+                int qr = q + rot; if (qr >= K4) qr -= K4;
+                const float4 v = ldcg4(op.x + (long long)(m0 + r) * op.ldx + 4 * qr);
+                ss[r] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+              }
+            ss[r] = warp_sum(ss[r]);
+            if (lane == 0) s_red[ww][(m0 & 6) + r] = ss[r];
+          }
+          if (tr && m0 == 0) P.trace[(size_t)oi * ST_TRACE + 11] = clock64();
+          if (((m0 & 6) == 6) || m0 + 2 >= M) {             // flush every 8 rows (s_red holds 8 rows)
+            worker_sync();
+            const int base = m0 & ~7;
+            if (wt < 8 && base + wt < M) s_inv[base + wt] = rsqrtf((s_red[0][wt] + s_red[1][wt] + s_red[2][wt] + s_red[3][wt]) / (float)K + op.pro_eps);
+            worker_sync();
+          }
         }
       } else if (pro == SP_DPM) {
-        // z' for every sample (same arithmetic as dpm_update_proj_kernel); CTA 0... every CTA recomputes, the first unit owner publishes
-        const SDpm d = *op.dpm;
+        // z' for every sample (same arithmetic as dpm_update_proj_kernel); every CTA with work recomputes it, the owner of unit 0 publishes
+        const SDpm& d = op.dpm;
         for (int i = wt; i < d.B * 64; i += ST_WORKERS) {
           const int b = i >> 6, e = i & 63;
           float zn, x0 = 0.f;
           if (d.step < 0) {
             zn = ldcg1(d.noise + i);
           } else {
-            const DpmCoef c = d.coef[d.step];
+            const DpmCoef c = d.c;
             const float cfg = *d.cfg_p;
             const float vc = ldcg1(d.v + (size_t)b * 64 + e), vu = ldcg1(d.v + (size_t)(d.B + b) * 64 + e);
             const float vv_ = vu + cfg * (vc - vu);
@@ -346,82 +526,40 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         }
         worker_sync();
       }
-      // ---------------- B operand: 16-byte chunks of 8 consecutive k for one activation row ----------------
-      {
-        const int total = M * count * 8;
-        for (int c = wt; c < total; c += ST_WORKERS) {
-          const int m = c / (count * 8), r = c - m * (count * 8);
-          const int jloc = r >> 3, ch = r & 7;
-          int kb = kb_first + jloc; if (kb >= KB) kb -= KB;
-          const int k = kb * 64 + ch * 8;
-          float v[8];
-          if (k < K) {
-            if (pro == SP_SWIGLU) {
-              const float* xr = op.x + (long long)m * op.ldx + 2 * k;
-              const float4 a0 = ldcg4(xr), a1 = ldcg4(xr + 4), a2 = ldcg4(xr + 8), a3 = ldcg4(xr + 12);
-              v[0] = silu_f(a0.x) * a0.y; v[1] = silu_f(a0.z) * a0.w; v[2] = silu_f(a1.x) * a1.y; v[3] = silu_f(a1.z) * a1.w;
-              v[4] = silu_f(a2.x) * a2.y; v[5] = silu_f(a2.z) * a2.w; v[6] = silu_f(a3.x) * a3.y; v[7] = silu_f(a3.z) * a3.w;
-            } else if (pro == SP_DPM) {
-              const float* zr = s_z + (m % op.dpm->B) * 64 + k;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = zr[j];
-            } else {
-              const float* xr = op.x + (long long)m * op.ldx + k;
-              const float4 a0 = ldcg4(xr), a1 = ldcg4(xr + 4);
-              v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
-              if (pro == SP_RMSNORM) {
-                const float inv = s_inv[m];
-                const float4 w0 = *reinterpret_cast<const float4*>(op.pro_w + k), w1 = *reinterpret_cast<const float4*>(op.pro_w + k + 4);
-                v[0] *= inv * w0.x; v[1] *= inv * w0.y; v[2] *= inv * w0.z; v[3] *= inv * w0.w;
-                v[4] *= inv * w1.x; v[5] *= inv * w1.y; v[6] *= inv * w1.z; v[7] *= inv * w1.w;
-              } else if (pro == SP_ADALN) {
-                const float inv = s_inv[m];
-                float w[8];
-                if (op.pro_w) {
-                  const float4 w0 = *reinterpret_cast<const float4*>(op.pro_w + k), w1 = *reinterpret_cast<const float4*>(op.pro_w + k + 4);
-                  w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) w[j] = 1.f;
-                }
-                const long long o = (long long)m * op.pro_ld + k;
-                const float4 s0 = ldcg4(op.pro_scale + o), s1 = ldcg4(op.pro_scale + o + 4);
-                const float4 h0 = ldcg4(op.pro_shift + o), h1 = ldcg4(op.pro_shift + o + 4);
-                const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = v[j] * inv * w[j] * (1.f + sc[j]) + sh[j];
-              } else if (pro == SP_GELU) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = gelu_erf_f(v[j]);
-              } else if (pro == SP_SILU) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = 0.f;        // k >= K: the weight tile is zero-filled there, keep 0 * x finite
-          }
-          float h[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) h[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
-          const uint4 hv = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
-          const uint4 lv = make_uint4(pack_bf16(v[0] - h[0], v[1] - h[1]), pack_bf16(v[2] - h[2], v[3] - h[3]),
-                                      pack_bf16(v[4] - h[4], v[5] - h[5]), pack_bf16(v[6] - h[6], v[7] - h[7]));
-          unsigned char* blk = breg + (size_t)jloc * (size_t)(nB * 128);
-          const int rl = half + m;
-          *reinterpret_cast<uint4*>(blk + (m >> 3) * 1024 + (m & 7) * 128 + ((ch ^ (m & 7)) << 4)) = hv;
-          *reinterpret_cast<uint4*>(blk + (rl >> 3) * 1024 + (rl & 7) * 128 + ((ch ^ (rl & 7)) << 4)) = lv;
-        }
+      if (tr) P.trace[(size_t)oi * ST_TRACE + 2] = clock64();
+      chunk_store(wt, in0);
+      chunk_store(wt + ST_WORKERS, in1);
+      for (int c = wt + 2 * ST_WORKERS; c < total; c += 2 * ST_WORKERS) {
+        chunk_load(c, in0);
+        chunk_load(c + ST_WORKERS, in1);
+        chunk_store(c, in0);
+        chunk_store(c + ST_WORKERS, in1);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy smem writes -> visible to the tensor core
       worker_sync();
       if (wt == 0) mbar_arrive(&b_ready);
+      if (tr) P.trace[(size_t)oi * ST_TRACE + 3] = clock64();
       // ---------------- epilogue ----------------
+      // bias / gamma / gate values do not depend on the MMA: fetch them while it runs (a gate load per segment AFTER the accumulators were
+      // complete cost one L2 round trip per segment and made the CTAs that straddle a row-tile boundary arrive ~0.9 us late at every barrier)
+      const int rt_last = (int)((u1 - 1u) / (unsigned)KB);
+      constexpr int EPRE = 3;                                 // segments whose operands are prefetched (more: loaded in place)
+      float e_bias[EPRE], e_alpha[EPRE][8];
+#pragma unroll
+      for (int sg = 0; sg < EPRE; ++sg) {
+        const int rt = rt_first + sg;
+        const int n = rt * 128 + wq * 32 + lane;
+        const bool live = rt <= rt_last && n < N;
+        const bool from0 = (sg > 0) || kb_first == 0;
+        e_bias[sg] = (live && from0 && op.bias) ? op.bias[n] : 0.f;
+        const float gam = (live && op.alpha_kind == SA_GAMMA) ? op.alpha[n] : 1.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          e_alpha[sg][j] = (live && op.alpha_kind == SA_GATE && j < M) ? ldcg1(op.alpha + (long long)j * op.lda + n) : gam;
+      }
       mbar_wait_wd(&acc_full, gi & 1u, P.diag, 5u, (unsigned)oi, gi);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int rt_last = (int)((u1 - 1) / KB);
+      if (tr) P.trace[(size_t)oi * ST_TRACE + 4] = clock64();
       for (int rt = rt_first; rt <= rt_last; ++rt) {
         const bool from0 = (rt > rt_first) || kb_first == 0;            // this segment holds k-block 0 of its row tile -> it adds the bias
         const int n = rt * 128 + wq * 32 + lane;
@@ -434,14 +572,19 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
                        : "=r"(rl[0]), "=r"(rl[1]), "=r"(rl[2]), "=r"(rl[3]), "=r"(rl[4]), "=r"(rl[5]), "=r"(rl[6]), "=r"(rl[7]) : "r"(tcol + (unsigned)(half + m0)));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (n < N) {
-            const float bias = (from0 && op.bias) ? op.bias[n] : 0.f;
-            const float gam = (op.alpha_kind == SA_GAMMA) ? op.alpha[n] : 1.f;
+            const int sg = rt - rt_first;
+            const bool pre = sg < EPRE && m0 == 0;
+            float bias, gam = 1.f;
+            if (sg < EPRE) bias = sg == 0 ? e_bias[0] : (sg == 1 ? e_bias[1] : e_bias[2]);
+            else bias = (from0 && op.bias) ? op.bias[n] : 0.f;
+            if (!pre && op.alpha_kind == SA_GAMMA) gam = op.alpha[n];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int m = m0 + j;
               if (m < M) {
                 float val = __uint_as_float(rh[j]) + __uint_as_float(rl[j]) + bias;
-                if (op.alpha_kind == SA_GATE) val *= ldcg1(op.alpha + (long long)m * op.lda + n);
+                if (pre) val *= sg == 0 ? e_alpha[0][j] : (sg == 1 ? e_alpha[1][j] : e_alpha[2][j]);
+                else if (op.alpha_kind == SA_GATE) val *= ldcg1(op.alpha + (long long)m * op.lda + n);
                 else val *= gam;
                 float* yp = op.y + (long long)m * op.ldy + n;
                 if (op.store) *yp = val; else red_add_f32(yp, val);
@@ -451,7 +594,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (tr) P.trace[(size_t)oi * ST_TRACE + 5] = clock64();
       ++gi;
+      } while (0);
+      cp_async_wait<0>();                      // next stage's descriptor has landed ...
+      worker_sync();                           // ... for every worker; also: all workers' global writes of this stage are issued
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -460,6 +607,81 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
     __syncwarp();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// micro-benchmark: issue rate / execution time of tcgen05.mma 128 x nB x 16 from shared memory (operands are whatever the buffer holds)
+//   mode 0: `n` MMAs back to back, one commit at the end; mode 1: commit + mbarrier wait after every 4 MMAs (= one 16 KB weight tile).
+//   `nacc` accumulators are used round-robin (1 = one dependent chain).  out[cta] = SM cycles.
+// ---------------------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n, int nB, int mode, int nacc, long long* out) {
+  extern __shared__ unsigned char mr_raw[];
+  __shared__ unsigned long long bar;
+  __shared__ unsigned tmem_base_s;
+  const unsigned raw_addr = smem_u32(mr_raw);
+  unsigned char* sm = mr_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (8 * ST_TILE + 32768) / 4; i += 128) reinterpret_cast<unsigned*>(sm)[i] = 0x3c003c00u;
+  if (tid == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const unsigned tmem = tmem_base_s;
+  const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(nB >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+  const unsigned long long db = umma_desc_sw128(smem_u32(sm + 8 * ST_TILE));
+  const unsigned long long da0 = umma_desc_sw128(smem_u32(sm));
+  // modes: 0 one thread (tid 0) issues, single commit; 1 commit + wait per 4; 3 whole warp converged, elect.sync inside the asm; 4 like 0 but
+  //        loop-invariant operands (same A tile, same accumulator): pure issue cost
+  if (mode == 3) {
+    if (warp == 1) {
+      const long long t0 = clock64();
+      for (int i = 0; i < n; ++i) {
+        const unsigned long long da = da0 + (unsigned long long)(((i >> 2) & 7) * (ST_TILE >> 4)) + 2 * (i & 3);
+        const unsigned dcol = tmem + (unsigned)((i % nacc) * nB);
+        const unsigned acc = i >= nacc ? 1u : 0u;
+        asm volatile("{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(dcol), "l"(da), "l"(db + 2 * (i & 3)), "r"(idesc), "r"(acc) : "memory");
+      }
+      const long long t1 = clock64();
+      if ((tid & 31) == 0) {
+        tc5_commit(&bar);
+        mbar_wait_wd(&bar, 0, nullptr, 9u, 0u, 0u);
+        out[blockIdx.x] = clock64() - t0;
+        out[gridDim.x + blockIdx.x] = t1 - t0;
+      }
+    }
+  } else if (tid == 0) {
+    unsigned phase = 0;
+    const long long t0 = clock64();
+    if (mode == 4) {
+      for (int i = 0; i < n; ++i) tc5_mma(tmem, da0, db, idesc, 1u);
+    } else {
+      for (int i = 0; i < n; ++i) {
+        const unsigned long long da = da0 + (unsigned long long)(((i >> 2) & 7) * (ST_TILE >> 4)) + 2 * (i & 3);
+        tc5_mma(tmem + (unsigned)((i % nacc) * nB), da, db + 2 * (i & 3), idesc, i >= nacc ? 1u : 0u);   // nacc independent accumulators
+        if (mode == 1 && (i & 3) == 3) {
+          tc5_commit(&bar);
+          mbar_wait_wd(&bar, phase, nullptr, 9u, 0u, 0u);
+          phase ^= 1u;
+        }
+      }
+    }
+    const long long t1 = clock64();
+    if (mode != 1) {
+      tc5_commit(&bar);
+      mbar_wait_wd(&bar, 0, nullptr, 9u, 0u, 0u);
+    }
+    out[blockIdx.x] = clock64() - t0;
+    out[gridDim.x + blockIdx.x] = t1 - t0;       // issue loop only
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
 }  // namespace vv
