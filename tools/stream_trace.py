@@ -21,6 +21,7 @@ ap.add_argument("--model", default="1.5b")
 ap.add_argument("--steps", type=int, default=30)
 ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--prog", default="samp")
+ap.add_argument("--ctx", type=int, default=61440)
 ap.add_argument("--mhz", type=float, default=1965.0)
 a = ap.parse_args()
 os.environ.setdefault("VV_STREAM_TRACE", "5")
@@ -36,8 +37,20 @@ with torch.cuda.stream(eng.stream):
     eng.active.fill_(1)
     eng.noise.normal_()
     eng.hidden.normal_()
-for _ in range(5):
-    eng.diffusion_sample(1.3)
+if a.prog.startswith("lm"):
+    ctx = a.ctx
+    eng.kv_init(B * (ctx + 64) + B * 64)
+    for r in range(B):
+        N.check(eng.lib.vv_kv_reserve(eng.h, r, ctx + 16, eng.s))
+        eng.kv_set_len(r, ctx)
+        eng.kv_set_len(B + r, 0)
+    eng.embed_tokens([tok.speech_start_id] * (2 * B), eng.embeds)
+    for _ in range(5):
+        eng.lm_decode()
+        eng.kv_commit([1] * (2 * B))
+else:
+    for _ in range(5):
+        eng.diffusion_sample(1.3)
 eng.sync()
 MAXO = 4096
 out = np.zeros((MAXO, 12), dtype=np.int64)
@@ -49,6 +62,10 @@ rows = {}
 for i in range(n):
     t = out[i]
     kind, Nn, K, pro = meta[i]
+    if kind == 2 and t[5]:
+        rows.setdefault(("attention", 0, 0), []).append([us(t[1] - t[0]), us(t[2] - t[1]), us(t[3] - t[2]), us(t[4] - t[3]), us(t[5] - t[4]), us(t[5] - t[0]),
+                                                         0, 0, 0, us(t[9] - t[0])])
+        continue
     if kind != 0 or t[5] == 0:
         continue
     key = (int(Nn), int(K), int(pro))
@@ -84,5 +101,6 @@ if G:
     lat = np.array([t2[i, :, 0] - np.median(t2[i, :, 0]) for i in range(1, n) if t2[i, :, 0].min() > 0]) / 1e3
     m = lat.mean(axis=0)
     print("mean lateness (us) by CTA: min %.2f max %.2f; worst CTAs %s" % (m.min(), m.max(), [(int(c), round(float(m[c]), 2)) for c in np.argsort(-m)[:8]]))
-tot = sum(us(out[i][5] - out[i][0]) for i in range(n) if meta[i][0] == 0 and out[i][5])
+print("(attention rows: barrier | Q staged | first segment's pages | merge + partial | remaining segments)")
+tot = sum(us(out[i][5] - out[i][0]) for i in range(n) if meta[i][0] in (0, 2) and out[i][5])
 print("sum of traced stage totals: %.1f us; first->last stamp: %.1f us" % (tot, us(out[:n, 5].max() - out[:n, 0][out[:n, 0] > 0].min())))

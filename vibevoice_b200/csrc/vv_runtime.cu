@@ -139,7 +139,10 @@ struct vv_ctx {
   unsigned* st_bar = nullptr;            // grid-barrier counter of the stream kernel
   unsigned* st_diag_host = nullptr; unsigned* st_diag_dev = nullptr;   // host-mapped watchdog record
   int st_inflight = 4;                   // VV_STREAM_INFLIGHT: TMA tiles (16 KB) a CTA keeps in flight
-  int use_stream = 3;                    // VV_STREAM bit 0: sampler, bit 1: LM linears through the weight-stream kernel; 0 -> kernel-per-stage everywhere
+  int use_stream = 7;                    // VV_STREAM bit 0: sampler, bit 1: LM linears, bit 2: + LM attention (whole decoder stack as one launch)
+                                         // through the weight-stream kernel; 0 -> kernel-per-stage everywhere
+  float* s_rope = nullptr;                        // [2B][64][2] cos / sin of the current positions
+  float *s_pacc2 = nullptr, *s_pml2 = nullptr;   // attention partials of the stream path: [2B][kv_heads][SMs][8][128] / [..][8][2]
   std::map<const bf16*, bf16*> tiled; size_t tiled_bytes = 0;   // tile-major copies of the weights the stream kernel reads
   long long* st_trace2 = nullptr;
   long long* st_trace = nullptr; int st_trace_ops = 0; int st_trace_cta = 0; int st_trace_last_ops = 0;   // VV_STREAM_TRACE=<cta>: per-stage clock stamps of one CTA
@@ -349,6 +352,48 @@ struct StreamBuilder {
   // y[m][n] (+)= alpha * (W x'[m] + bias); x' = pro(x)
   bool fresh_weights = false;
   std::vector<bf16*> owned;         // tile-major copies made with fresh_weights (freed by the caller)
+  int kv_tmap = -1;                 // index of the K-pool tensor map (V-pool map follows) for SK_ATTN stages
+  std::vector<int> needs_kv;        // ops whose att.tmap_k / tmap_v must be patched
+  int use_kv_pool() {
+    if (kv_tmap >= 0) return 0;
+    const auto& d = c->d;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail(VV_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t rows = (cuuint64_t)d.num_layers * c->n_pages * d.num_kv_heads * KV_PAGE;
+    const cuuint64_t dims[2] = {(cuuint64_t)HD, rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)HD * 2};
+    const cuuint32_t box[2] = {64, KV_PAGE};
+    const cuuint32_t estr[2] = {1, 1};
+    for (bf16* pool : {c->kpool, c->vpool}) {
+      CUtensorMap tm;
+      CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)pool, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail(VV_ERR_CUDA, "cuTensorMapEncodeTiled(KV pool) failed with %d", (int)r);
+      tmaps.push_back(tm);
+    }
+    kv_tmap = (int)tmaps.size() - 2;
+    return 0;
+  }
+  void fill_att(SAtt* a, int layer) {
+    const auto& d = c->d;
+    const size_t per_layer = (size_t)c->n_pages * d.num_kv_heads * KV_PAGE * HD;
+    memset(a, 0, sizeof *a);
+    a->qkv = c->s_qkv;
+    a->kv.kpool = c->kpool + per_layer * layer; a->kv.vpool = c->vpool + per_layer * layer;
+    a->kv.page_table = c->page_table_dev; a->kv.max_pages = c->max_pages; a->kv.kv_len = c->kv_len_dev; a->kv.row_mode = c->row_mode_dev;
+    a->kv.kv_heads = d.num_kv_heads; a->kv.q_heads = d.num_q_heads;
+    a->part_acc = c->s_pacc2; a->part_ml = c->s_pml2; a->inv_freq = c->inv_freq; a->scale = 1.0f / sqrtf((float)HD);
+    a->row_base = (unsigned)((size_t)layer * c->n_pages * d.num_kv_heads * KV_PAGE);
+    a->rope_cs = c->s_rope;
+  }
+  int attn(int layer, int M) {
+    RET(use_kv_pool());
+    SOp& o = push(SK_ATTN, true);
+    o.M = M;
+    fill_att(&o.att, layer);
+    needs_kv.push_back((int)ops.size() - 1);
+    return 0;
+  }
   int gemv(const bf16* W, const float* bias, const float* x, long long ldx, float* y, long long ldy, int M, int N, int K, bool sync, SOp** out) {
     if (M < 1 || M > 32) return fail(VV_ERR_INVALID, "stream gemv: M=%d outside [1,32]", M);
     CUtensorMap tm;
@@ -375,6 +420,7 @@ static int finish_stream(StreamBuilder& b, vv_ctx::StreamProg* pr) {
   const int G = c->sm_count;
   int b_bytes = 2048;
   for (const SOp& o : b.ops) {
+    if (o.kind == SK_ATTN) b_bytes = std::max(b_bytes, 32768);        // Q tile, new K/V row and the warp-merge buffers live in the operand region
     if (o.kind != SK_GEMV) continue;
     const long long KB = (o.K + 63) / 64, R = (o.N + 127) / 128, U = R * KB;
     const long long per = (U + G - 1) / G;
@@ -383,6 +429,12 @@ static int finish_stream(StreamBuilder& b, vv_ctx::StreamProg* pr) {
     const long long segs = (per + KB - 1) / KB + 1;
     if (segs > ST_MAXSEG || segs * o.nB > 512) return fail(VV_ERR_INVALID, "stream: stage [%d x %d] needs %lld accumulators per CTA", o.N, o.K, segs);
     if (o.store && KB != 1) return fail(VV_ERR_INVALID, "stream: store epilogue needs K <= 64");
+    if (o.pro == SP_COMBINE) {
+      const long long nh = count / 2 + 2;
+      if (count * o.nB * 128 > 16384 || (long long)o.M * nh > 32 || KB != 2 * c->d.num_q_heads)
+        return fail(VV_ERR_INVALID, "stream: attention-merge prologue does not fit (M=%d, %lld k-blocks per CTA)", o.M, count);
+      b_bytes = std::max<long long>(b_bytes, 16384 + o.M * nh * G * 4 + 16 + 2048 + o.M * count * 256);
+    }
     if (U * (G + 1) >= (1ll << 32)) return fail(VV_ERR_INVALID, "stream: stage [%d x %d] has too many tiles for 32-bit scheduling", o.N, o.K);
   }
   cudaFuncAttributes fa;
@@ -396,6 +448,10 @@ static int finish_stream(StreamBuilder& b, vv_ctx::StreamProg* pr) {
   pr->n_ops = (int)b.ops.size();
   RET(dmalloc(c, &pr->tmaps, std::max<size_t>(b.tmaps.size(), 1), false));
   RET(dmalloc(c, &pr->ops, b.ops.size(), false));
+  for (int i : b.needs_kv) {
+    b.ops[i].att.tmap_k = (unsigned long long)(uintptr_t)(pr->tmaps + b.kv_tmap);
+    b.ops[i].att.tmap_v = (unsigned long long)(uintptr_t)(pr->tmaps + b.kv_tmap + 1);
+  }
   for (size_t i = 0; i < b.ops.size(); ++i) {
     if (b.tmap_of[i] >= 0) b.ops[i].tmap = (unsigned long long)(uintptr_t)(pr->tmaps + b.tmap_of[i]);
     pr->gemv_ops += b.ops[i].kind == SK_GEMV;
@@ -420,6 +476,7 @@ static int launch_stream(const L& l, const vv_ctx::StreamProg& pr, int op_begin 
   SParams P;
   P.ops = pr.ops + op_begin; P.n_ops = op_count; P.bar_count = c->st_bar; P.diag = c->st_diag_dev; P.n_stages = pr.n_stages; P.b_bytes = pr.b_bytes;
   P.max_inflight = std::max(1, std::min(pr.n_stages, c->st_inflight));
+  P.kv_len = c->kv_len_dev; P.row_mode = c->row_mode_dev; P.n_seq = 2 * c->d.max_batch; P.kv_heads = c->d.num_kv_heads;
   P.trace = (c->st_trace && op_count == pr.n_ops && pr.n_ops <= c->st_trace_ops) ? c->st_trace : nullptr; P.trace_cta = c->st_trace_cta;
   P.trace2 = P.trace ? c->st_trace2 : nullptr;
   if (P.trace) c->st_trace_last_ops = pr.n_ops;
@@ -969,6 +1026,9 @@ extern "C" int vv_finalize_weights(vv_ctx* c) {
   RET(dmalloc(c, &c->s_attn, (size_t)M2 * nq));
   RET(dmalloc(c, &c->s_act, (size_t)M2 * I));
   RET(dmalloc(c, &c->s_lgu, (size_t)M2 * 2 * I));
+  RET(dmalloc(c, &c->s_rope, (size_t)M2 * HD));
+  RET(dmalloc(c, &c->s_pacc2, (size_t)M2 * d.num_kv_heads * c->sm_count * 8 * HD));
+  RET(dmalloc(c, &c->s_pml2, (size_t)M2 * d.num_kv_heads * c->sm_count * 8 * 2));
   RET(dmalloc(c, &c->s_pacc, (size_t)M2 * d.num_q_heads * c->nsplit * HD));
   RET(dmalloc(c, &c->s_pml, (size_t)M2 * d.num_q_heads * c->nsplit * 2));
   RET(dmalloc(c, &c->s_tok, 64));
@@ -1049,6 +1109,10 @@ extern "C" int vv_kv_init(vv_ctx* c, int64_t n_pages) {
     CK(cudaDeviceSynchronize());
     dfree(c, &c->kpool); dfree(c, &c->vpool); dfree(c, &c->page_table_dev);
     drop_graphs(c, {"lm:", "lmr:", "frame:"});
+    for (auto it = c->sprogs.begin(); it != c->sprogs.end();) {
+      if (it->first.rfind("lmf:", 0) == 0) { dfree(c, &it->second.ops); dfree(c, &it->second.tmaps); it = c->sprogs.erase(it); }
+      else ++it;
+    }
     std::fill(c->kv_len_host.begin(), c->kv_len_host.end(), 0);
     for (auto& pg : c->seq_pages) pg.clear();
   }
@@ -1205,6 +1269,42 @@ static int lm_stream_prog(vv_ctx* c, int li0, int li1, const vv_ctx::StreamProg*
   return 0;
 }
 
+// All of decoder layers [li0, li1) as ONE weight-stream program: per layer QKV -> attention (K/V pages through the ring) -> O (prologue merges
+// the attention partials) -> gate/up -> down.  5 grid barriers per layer, no kernel boundary inside the stack.
+static int lm_stream_prog_full(vv_ctx* c, int li0, int li1, const vv_ctx::StreamProg** out) {
+  char key[64];
+  snprintf(key, sizeof key, "lmf:%d:%d", li0, li1);
+  auto it = c->sprogs.find(key);
+  if (it != c->sprogs.end()) { *out = &it->second; return 0; }
+  const auto& d = c->d;
+  const int H = d.hidden_size, I = d.intermediate_size, M = 2 * d.max_batch, nq = d.num_q_heads * HD;
+  StreamBuilder b(c);
+  b.nop(false, c->s_qkv, (long long)M * c->Nqkv);
+  for (int li = li0; li < li1; ++li) {
+    const LmLayer& y = c->lm[li];
+    SOp* o;
+    RET(b.gemv(y.wqkv, y.bqkv, c->s_h, H, c->s_qkv, c->Nqkv, M, c->Nqkv, H, true, &o));
+    o->pro = SP_RMSNORM; o->pro_w = y.ln1; o->pro_eps = d.rms_norm_eps;
+    if (li == li0) { b.fill_att(&o->att, li); o->rope_rows = M; }        // positions are the same for every layer of this call
+    RET(b.attn(li, M));
+    RET(b.gemv(y.wo, nullptr, nullptr, 0, c->s_h, H, M, H, nq, true, &o));
+    o->pro = SP_COMBINE;
+    b.fill_att(&o->att, li);
+    b.needs_kv.push_back((int)b.ops.size() - 1);
+    o->init_dst = c->s_qkv; o->init_n = (long long)M * c->Nqkv;
+    o->init2_dst = c->s_lgu; o->init2_n = (long long)M * 2 * I;
+    RET(b.gemv(y.wgu, nullptr, c->s_h, H, c->s_lgu, 2 * I, M, 2 * I, H, true, &o));
+    o->pro = SP_RMSNORM; o->pro_w = y.ln2; o->pro_eps = d.rms_norm_eps;
+    RET(b.gemv(y.wdown, nullptr, c->s_lgu, 2 * I, c->s_h, H, M, H, I, true, &o));
+    o->pro = SP_SWIGLU;
+  }
+  vv_ctx::StreamProg pr;
+  RET(finish_stream(b, &pr));
+  it = c->sprogs.emplace(key, pr).first;
+  *out = &it->second;
+  return 0;
+}
+
 // decoder layers [li0, li1) over the residual stream s_h (rows = 2B sequences; rows with row_mode 0 neither read nor append KV)
 static int enqueue_lm_layers(const L& l, int li0, int li1, const vv_ctx::StreamProg* sprog = nullptr) {
   vv_ctx* c = l.c;
@@ -1212,6 +1312,7 @@ static int enqueue_lm_layers(const L& l, int li0, int li1, const vv_ctx::StreamP
   const int H = d.hidden_size, I = d.intermediate_size, M = 2 * d.max_batch, nq = d.num_q_heads * HD;
   const size_t per_layer = (size_t)c->n_pages * d.num_kv_heads * KV_PAGE * HD;
   const float scale = 1.0f / sqrtf((float)HD);
+  if (sprog && (c->use_stream & 4)) return launch_stream(l, *sprog);      // whole stack, attention included
   if (sprog) RET(launch_stream(l, *sprog, 0, 2));
   for (int li = li0; li < li1; ++li) {
     const LmLayer& y = c->lm[li];
@@ -1290,7 +1391,8 @@ extern "C" int vv_lm_decode(vv_ctx* c, const float* embeds, float* hidden, float
   char key[256];
   snprintf(key, sizeof key, "lm:%p:%p:%p:%p", (const void*)embeds, (void*)hidden, (void*)logits, (void*)tokens);
   const vv_ctx::StreamProg* sprog = nullptr;      // built outside stream capture
-  if (c->use_stream & 2) RET(lm_stream_prog(c, 0, c->d.num_layers, &sprog));
+  if (c->use_stream & 4) RET(lm_stream_prog_full(c, 0, c->d.num_layers, &sprog));
+  else if (c->use_stream & 2) RET(lm_stream_prog(c, 0, c->d.num_layers, &sprog));
   return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_lm_decode(l, embeds, hidden, logits, tokens, sprog); });
 }
 extern "C" int vv_lm_head(vv_ctx* c, const float* hidden, float* logits, int32_t* tokens, void* stream) {
@@ -1321,7 +1423,8 @@ extern "C" int vv_lm_decode_range(vv_ctx* c, const float* embeds, int layer_begi
   char key[256];
   snprintf(key, sizeof key, "lmr:%p:%p:%d:%d:%d", (const void*)embeds, (void*)hidden, layer_begin, layer_end, final_norm);
   const vv_ctx::StreamProg* sprog = nullptr;
-  if (c->use_stream & 2) RET(lm_stream_prog(c, layer_begin, layer_end, &sprog));
+  if (c->use_stream & 4) RET(lm_stream_prog_full(c, layer_begin, layer_end, &sprog));
+  else if (c->use_stream & 2) RET(lm_stream_prog(c, layer_begin, layer_end, &sprog));
   return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_lm_range(l, embeds, layer_begin, layer_end, final_norm, hidden, sprog); });
 }
 

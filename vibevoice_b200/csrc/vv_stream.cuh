@@ -87,8 +87,8 @@ constexpr int ST_MAXSEG = 8;             // (row tile, k range) segments a CTA m
 constexpr int ST_MAX_STAGES = 12;
 constexpr int ST_BAR_REP = 0;
 
-enum SKind { SK_GEMV = 0, SK_NOP = 1 };
-enum SPro { SP_NONE = 0, SP_RMSNORM = 1, SP_ADALN = 2, SP_SWIGLU = 3, SP_GELU = 4, SP_DPM = 5, SP_SILU = 6 };
+enum SKind { SK_GEMV = 0, SK_NOP = 1, SK_ATTN = 2 };
+enum SPro { SP_NONE = 0, SP_RMSNORM = 1, SP_ADALN = 2, SP_SWIGLU = 3, SP_GELU = 4, SP_DPM = 5, SP_SILU = 6, SP_COMBINE = 7 };
 enum SAlpha { SA_ONE = 0, SA_GATE = 1 /* alpha[m][n], row stride lda */, SA_GAMMA = 2 /* alpha[n] */ };
 
 // CFG + DPM-Solver++ update of step `step` (same arithmetic as dpm_update_proj_kernel), evaluated in the prologue of the stage that
@@ -98,6 +98,25 @@ struct SDpm {
   const float* cfg_p; const float* step_noise; float* latent_out;
   int step, B;
   DpmCoef c;                // coefficients of this step, by value (no dependent loads on the critical path)
+};
+
+// Decode attention as a stage of the stream (SK_ATTN), and its split-partial merge as the prologue of the o-projection (SP_COMBINE).
+// Units = (row m, kv head g, 64-token page t) in that order, dealt out to the CTAs as contiguous ranges like the weight tiles; the K and V
+// page of a unit are two 16 KB ring slots filled by TMA (each page is contiguous in the pool: [64 tokens][128] bf16 -> two 64 x 64 boxes,
+// SWIZZLE_128B), so the KV cache streams through the same ring, prefetched across the grid barriers like the weights.
+// A CTA's run of units inside one (m, g) is a segment: one online-softmax partial (max, sum, acc[G heads][128]) written to slot
+// `cta - first_cta(m, g)` of part_acc / part_ml; SP_COMBINE merges the partials of a head while it stages the o-projection's activations.
+struct SAtt {
+  const float* qkv;            // [M][(q_heads + 2 kv_heads) * 128] fp32, bias added, not rotated
+  KvView kv;                   // this layer's pool pointers (new K/V rows are written here), page table, kv_len, row_mode
+  float* part_acc;             // [M][kv_heads][gridDim][8][128]
+  float* part_ml;              // [M][kv_heads][gridDim][8][2]
+  const float* inv_freq;
+  float scale;
+  unsigned long long tmap_k, tmap_v;   // tensor maps over the WHOLE K / V pool: [layers * pages * kv_heads * 64 rows][128] bf16, box 64 x 64
+  unsigned row_base;           // first row of this layer in those maps
+  float* rope_cs;              // [M][64][2] cos / sin of (kv_len[m] * inv_freq[d]): written by the QKV stage, read here (accurate sincosf of
+                               // positions up to 64K costs ~1 us per segment when every CTA recomputes it)
 };
 
 struct alignas(16) SOp {
@@ -112,12 +131,14 @@ struct alignas(16) SOp {
   const float* pro_w; float pro_eps;     // norm weight [K] (may be null for SP_ADALN)
   const float* pro_shift; const float* pro_scale; long long pro_ld;
   SDpm dpm;                              // SP_DPM only
+  SAtt att;                              // SK_ATTN, SP_COMBINE
   float* y; long long ldy;               // y[m][n] += alpha * (acc + bias[n] if the segment starts at k = 0);  store != 0: y = ... (KB == 1 only)
   const float* bias;
   int alpha_kind; const float* alpha; long long lda;
   int store;
   float* init_dst; long long init_n;     // optional: zero-fill jobs (buffers a LATER stage accumulates into), spread over the grid
   float* init2_dst; long long init2_n;
+  int rope_rows;                         // > 0: this stage also fills att.rope_cs for rows [0, rope_rows) (CTA m computes row m)
 };
 
 struct SParams {
@@ -127,6 +148,7 @@ struct SParams {
   int n_stages;             // ring depth
   int b_bytes;              // bytes of the activation-operand region
   int max_inflight;         // TMA tiles a CTA may have in flight (<= n_stages)
+  const int* kv_len; const int* row_mode; int n_seq, kv_heads;   // sequence state for attention stages (null / 0 when the program has none)
   long long* trace;         // optional [n_ops][ST_TRACE] clock64 stamps of CTA `trace_cta` (tools/stream_trace.py), else null
   int trace_cta;
   long long* trace2;        // optional [n_ops][G][2] globaltimer (ns) of every CTA: arrival at / release from the grid barrier
@@ -187,6 +209,48 @@ VV_DEVINL float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const fl
 VV_DEVINL void red_add_f32(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 VV_DEVINL void worker_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
+// attention units of row m: kv_heads * pages(m) (0 for rows that are switched off); returns the total, fills this CTA's range
+// kv_len / row_mode are constant during a launch; the kernel keeps a copy in shared memory (SeqView) -- read from global memory at the start
+// of every attention stage they were 4 dependent L2 round trips, ~2.5 us, on the critical path
+struct SeqView { const int* kv_len; const int* row_mode; int kv_heads; };
+VV_DEVINL unsigned att_tiles(const SeqView& q, int m) { return q.row_mode[m] ? (unsigned)((q.kv_len[m] + 1 + KV_PAGE - 1) / KV_PAGE) : 0u; }
+// Work split of an attention stage.  Every (row m, kv head g) group with pages contributes nt + ST_ATT_SEGW VIRTUAL units: the first
+// ST_ATT_SEGW stand for the fixed cost of a segment (Q staging, warp merge, partial write ~ 3.6 us ~ 4 pages), the rest are its pages in
+// order.  CTAs take contiguous ranges of virtual units, so a CTA that also gets the few pages of a short (CFG-negative) row gets
+// correspondingly fewer pages of the long one (measured before: the CTA owning both short groups arrived 8 us late at every layer's barrier).
+constexpr unsigned ST_ATT_SEGW = 4;
+VV_DEVINL unsigned att_vtotal(const SeqView& q, int M) {
+  unsigned V = 0;
+  for (int m = 0; m < M; ++m) { const unsigned nt = att_tiles(q, m); if (nt) V += (nt + ST_ATT_SEGW) * (unsigned)q.kv_heads; }
+  return V;
+}
+VV_DEVINL unsigned cta_of_unit(unsigned u, unsigned U, unsigned G) { return ((u + 1u) * G - 1u) / U; }     // inverse of u0 = U c / G
+struct AttSeg { int m, g, t0, t1; unsigned nt, vf; };     // pages [t0, t1) of group (m, g); vf = first virtual unit of the group
+struct AttIter { unsigned v0, v1, vf; int gi; };          // this CTA's virtual range, walking the groups in order
+VV_DEVINL void att_begin(const SeqView& q, int M, AttIter& it) {
+  const unsigned V = att_vtotal(q, M);
+  it.v0 = V * blockIdx.x / gridDim.x; it.v1 = V * (blockIdx.x + 1u) / gridDim.x; it.vf = 0; it.gi = 0;
+}
+VV_DEVINL bool att_next(const SeqView& q, int M, AttIter& it, AttSeg& sg) {
+  while (it.gi < M * q.kv_heads && it.vf < it.v1) {
+    const int m = it.gi / q.kv_heads, g = it.gi - m * q.kv_heads;
+    const unsigned nt = att_tiles(q, m);
+    ++it.gi;
+    if (nt == 0) continue;
+    const unsigned vf = it.vf, len = nt + ST_ATT_SEGW;
+    it.vf += len;
+    const unsigned a = it.v0 > vf ? it.v0 : vf, b = it.v1 < vf + len ? it.v1 : vf + len;
+    if (b <= a) continue;
+    const unsigned t0 = a - vf > ST_ATT_SEGW ? a - vf - ST_ATT_SEGW : 0u, t1 = b - vf > ST_ATT_SEGW ? b - vf - ST_ATT_SEGW : 0u;
+    if (t1 <= t0) continue;
+    sg.m = m; sg.g = g; sg.t0 = (int)t0; sg.t1 = (int)t1; sg.nt = nt; sg.vf = vf;
+    return true;
+  }
+  return false;
+}
+// byte offset of element (token row, d) inside a K / V ring slot: two 64-column halves of 8 KB, 128-byte rows, 16-byte chunks XOR-swizzled
+VV_DEVINL unsigned kv_off(int tok, int d) { return (unsigned)(((d >> 6) << 13) + tok * 128 + ((((d & 63) >> 3) ^ (tok & 7)) << 4) + (d & 7) * 2); }
+
 // this CTA's unit range of a stage: units are (row tile, k-block) pairs in row-tile-major order
 // (32-bit arithmetic: U * gridDim < 2^32 is checked on the host; 64-bit divisions here cost ~0.3 us per stage on the critical path)
 VV_DEVINL void st_part(const SOp& op, unsigned& u0, unsigned& u1, int& KB) {
@@ -208,6 +272,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
   __shared__ float s_inv[64];
   __shared__ float s_z[8 * 64];
   __shared__ __align__(16) unsigned char s_opbuf[2][sizeof(SOp)];
+  __shared__ int s_pinfo[32];
   const unsigned raw_addr = smem_u32(st_raw);
   unsigned char* sm = st_raw + ((1024u - (raw_addr & 1023u)) & 1023u);      // 1024 B aligned (swizzle atom)
   unsigned char* ring = sm;
@@ -215,6 +280,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int NS = P.n_stages;
   const unsigned G = gridDim.x;
+  __shared__ int s_kvlen[16], s_rmode[16];
+  if (tid < 16) {
+    s_kvlen[tid] = (P.kv_len && tid < P.n_seq) ? P.kv_len[tid] : 0;
+    s_rmode[tid] = (P.row_mode && tid < P.n_seq) ? P.row_mode[tid] : 0;
+  }
+  SeqView seq; seq.kv_len = s_kvlen; seq.row_mode = s_rmode; seq.kv_heads = P.kv_heads;
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -238,8 +309,40 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
       unsigned it = 0, done = 0;
       const unsigned cap = (unsigned)P.max_inflight;
+      auto acquire_slot = [&](int oi) -> unsigned {            // next ring slot, respecting the in-flight cap; arms its full barrier
+        const unsigned slot = it % (unsigned)NS, ph = (it / (unsigned)NS) & 1u;
+        while (it - done >= cap) {
+          mbar_wait_wd(&full_bar[done % (unsigned)NS], (done / (unsigned)NS) & 1u, P.diag, 6u, (unsigned)oi, done);
+          ++done;
+        }
+        mbar_wait_wd(&empty_bar[slot], ph ^ 1u, P.diag, 1u, (unsigned)oi, it);
+        mbar_expect_tx(&full_bar[slot], (unsigned)ST_TILE);
+        ++it;
+        return slot;
+      };
+      unsigned long long policy_kv;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy_kv));
       for (int oi = 0; oi < P.n_ops; ++oi) {
         const SOp& op = P.ops[oi];
+        if (op.kind == SK_ATTN) {
+          // K page then V page of every unit: two 64 x 64 boxes each (d 0..63, d 64..127) into one 16 KB slot
+          const SAtt& a = op.att;
+          AttIter ai; AttSeg sg;
+          att_begin(seq, op.M, ai);
+          while (att_next(seq, op.M, ai, sg)) {
+            for (int t = sg.t0; t < sg.t1; ++t) {
+              const int page = a.kv.page_table[(size_t)sg.m * a.kv.max_pages + t];
+              const int row0 = (int)(a.row_base + (unsigned)((page * a.kv.kv_heads + sg.g) * KV_PAGE));
+              unsigned slot = acquire_slot(oi);
+              tma_load_2d(ring + (size_t)slot * ST_TILE, a.tmap_k, 0, row0, &full_bar[slot], policy_kv);
+              tma_load_2d(ring + (size_t)slot * ST_TILE + 8192, a.tmap_k, 64, row0, &full_bar[slot], policy_kv);
+              slot = acquire_slot(oi);
+              tma_load_2d(ring + (size_t)slot * ST_TILE, a.tmap_v, 0, row0, &full_bar[slot], policy_kv);
+              tma_load_2d(ring + (size_t)slot * ST_TILE + 8192, a.tmap_v, 64, row0, &full_bar[slot], policy_kv);
+            }
+          }
+          continue;
+        }
         if (op.kind != SK_GEMV) continue;
         unsigned u0, u1; int KB;
         st_part(op, u0, u1, KB);
@@ -269,6 +372,16 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
     unsigned slot = 0, ph = 0, gi = 0;
     for (int oi = 0; oi < P.n_ops; ++oi) {
       const SOp& op = P.ops[oi];
+      if (op.kind == SK_ATTN) {                                  // the workers consume 2 ring slots per attention unit: keep slot / phase in step
+        AttIter ai; AttSeg sg;
+        att_begin(seq, op.M, ai);
+        unsigned pages = 0;
+        while (att_next(seq, op.M, ai, sg)) pages += (unsigned)(sg.t1 - sg.t0);
+        const unsigned adv = 2u * pages + slot;
+        ph ^= (adv / (unsigned)NS) & 1u;
+        slot = adv % (unsigned)NS;
+        continue;
+      }
       if (op.kind != SK_GEMV) continue;
       unsigned u0, u1; int KB;
       st_part(op, u0, u1, KB);
@@ -327,6 +440,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
     const int wq = warp & 3;                  // TMEM lane quadrant this warp may read
     const int ww = warp - 2;
     unsigned gi = 0, bar_target = 0;
+    unsigned wslot = 0, wph = 0;              // ring position (the workers read K/V pages from the ring; weight tiles are only counted)
+    auto ring_advance = [&](unsigned n) { const unsigned adv = wslot + n; wph ^= (adv / (unsigned)NS) & 1u; wslot = adv % (unsigned)NS; };
     // stage descriptors are copied into shared memory ONE STAGE AHEAD (cp.async): read straight from global memory, each first touch of a
     // descriptor field was an L2/DRAM round trip on the critical path (~1 us per stage, profiles/r02_stream_trace_2.txt)
     constexpr int OPCH = (int)(sizeof(SOp) / 16);
@@ -369,9 +484,175 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       if (op.init2_dst) {
         for (long long i = (long long)blockIdx.x * ST_WORKERS + wt; i < op.init2_n; i += (long long)G * ST_WORKERS) op.init2_dst[i] = 0.f;
       }
+      if (op.rope_rows > 0 && (int)blockIdx.x < op.rope_rows && wt < HD / 2) {
+        const int m = blockIdx.x;
+        float sn, cs;
+        sincosf((float)s_kvlen[m] * op.att.inv_freq[wt], &sn, &cs);
+        *reinterpret_cast<float2*>(op.att.rope_cs + ((size_t)m * (HD / 2) + wt) * 2) = make_float2(cs, sn);
+      }
+      if (op.kind == SK_ATTN) {
+        // =========================== decode attention over the ring (see SAtt) ===========================
+        const SAtt& a = op.att;
+        const unsigned U = att_vtotal(seq, op.M);
+        const int Gq = a.kv.q_heads / a.kv.kv_heads, nkv = a.kv.kv_heads;
+        bf16 (*Qs)[AT2_LD] = reinterpret_cast<bf16 (*)[AT2_LD]>(breg);              // [16][136]: rows 0..7 hi, 8..15 lo of the G query heads
+        bf16* knew = reinterpret_cast<bf16*>(breg + 16 * AT2_LD * 2);
+        bf16* vnew = knew + HD;
+        float* mo = reinterpret_cast<float*>(breg + 8192);                          // [4 warps][8 heads][128]
+        float* mlw = mo + 4 * 8 * HD;                                               // [4][8][2]
+        AttIter ai; AttSeg sg;
+        att_begin(seq, op.M, ai);
+        bool first_seg = true;
+        while (att_next(seq, op.M, ai, sg)) {
+          const int m = sg.m, g = sg.g, t = sg.t0, t_end = sg.t1;
+          const unsigned nt = sg.nt;
+          const int pos = s_kvlen[m], L = pos + 1;
+          const bool owner = (t_end == (int)nt);                                    // this CTA holds the page of the newest token
+          const float* row = a.qkv + (size_t)m * (a.kv.q_heads + 2 * nkv) * HD;
+          for (int i = wt; i < 8 * (HD / 2); i += ST_WORKERS) {
+            const int h = i / (HD / 2), d = i % (HD / 2);
+            float o1 = 0.f, o2 = 0.f;
+            if (h < Gq) {
+              const float2 csn = __ldcg(reinterpret_cast<const float2*>(a.rope_cs + ((size_t)m * (HD / 2) + d) * 2));
+              const float cs = csn.x, sn = csn.y;
+              const float x1 = ldcg1(row + (g * Gq + h) * HD + d), x2 = ldcg1(row + (g * Gq + h) * HD + d + HD / 2);
+              o1 = (x1 * cs - x2 * sn) * a.scale;
+              o2 = (x2 * cs + x1 * sn) * a.scale;
+            }
+            const bf16 h1 = __float2bfloat16_rn(o1), h2 = __float2bfloat16_rn(o2);
+            Qs[h][d] = h1; Qs[h][d + HD / 2] = h2;
+            Qs[h + 8][d] = __float2bfloat16_rn(o1 - __bfloat162float(h1));
+            Qs[h + 8][d + HD / 2] = __float2bfloat16_rn(o2 - __bfloat162float(h2));
+          }
+          if (owner) {                                                              // rotate k, round K / V to bf16, append to the pool
+            const int page = a.kv.page_table[(size_t)m * a.kv.max_pages + pos / KV_PAGE];
+            const size_t oo = (((size_t)page * nkv + g) * KV_PAGE + (pos % KV_PAGE)) * HD;
+            if (wt < HD / 2) {
+              const int d = wt;
+              const float2 csn = __ldcg(reinterpret_cast<const float2*>(a.rope_cs + ((size_t)m * (HD / 2) + d) * 2));
+              const float cs = csn.x, sn = csn.y;
+              const float x1 = ldcg1(row + (a.kv.q_heads + g) * HD + d), x2 = ldcg1(row + (a.kv.q_heads + g) * HD + d + HD / 2);
+              const bf16 k1 = __float2bfloat16_rn(x1 * cs - x2 * sn), k2 = __float2bfloat16_rn(x2 * cs + x1 * sn);
+              knew[d] = k1; knew[d + HD / 2] = k2;
+              a.kv.kpool[oo + d] = k1; a.kv.kpool[oo + d + HD / 2] = k2;
+            } else {
+              for (int d = wt - HD / 2; d < HD; d += 64) {
+                const bf16 vv_ = __float2bfloat16_rn(ldcg1(row + (a.kv.q_heads + nkv + g) * HD + d));
+                vnew[d] = vv_;
+                a.kv.vpool[oo + d] = vv_;
+              }
+            }
+          }
+          worker_sync();
+          if (tr && first_seg) P.trace[(size_t)oi * ST_TRACE + 2] = clock64();
+          unsigned qa[8][4];
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) ldmatrix_x4(qa[ks], &Qs[lane & 15][ks * 16 + (lane >> 4) * 8]);
+          float o[16][4];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { o[i][0] = 0.f; o[i][1] = 0.f; o[i][2] = 0.f; o[i][3] = 0.f; }
+          float m_run = -INFINITY, l_run = 0.f;
+          for (int tt = t; tt < t_end; ++tt) {
+            const int tok0 = tt * KV_PAGE;
+            const unsigned slotK = wslot, phK = wph;
+            ring_advance(1);
+            const unsigned slotV = wslot, phV = wph;
+            ring_advance(1);
+            unsigned char* Ks = ring + (size_t)slotK * ST_TILE;
+            unsigned char* Vs = ring + (size_t)slotV * ST_TILE;
+            mbar_wait_wd(&full_bar[slotK], phK, P.diag, 7u, (unsigned)oi, (unsigned)tt);
+            const bool splice = owner && tt == (int)nt - 1;
+            if (splice) {                          // the page was fetched before (or while) the new row was written: patch it in shared memory
+              mbar_wait_wd(&full_bar[slotV], phV, P.diag, 7u, (unsigned)oi, (unsigned)tt);
+              *reinterpret_cast<bf16*>(Ks + kv_off(pos - tok0, wt)) = knew[wt];
+              *reinterpret_cast<bf16*>(Vs + kv_off(pos - tok0, wt)) = vnew[wt];
+              worker_sync();
+            }
+            float sa[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              unsigned kb[4];
+              ldmatrix_x4(kb, Ks + kv_off(ww * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 16 + ((lane >> 3) & 1) * 8));
+              mma_bf16_16816(sa[0], qa[ks], kb[0], kb[1]);
+              mma_bf16_16816(sa[1], qa[ks], kb[2], kb[3]);
+            }
+            const int tb = tok0 + ww * 16 + (lane & 3) * 2;
+            float sv[4] = {sa[0][0] + sa[0][2], sa[0][1] + sa[0][3], sa[1][0] + sa[1][2], sa[1][1] + sa[1][3]};
+            if (tb >= L) sv[0] = -INFINITY;
+            if (tb + 1 >= L) sv[1] = -INFINITY;
+            if (tb + 8 >= L) sv[2] = -INFINITY;
+            if (tb + 9 >= L) sv[3] = -INFINITY;
+            float mt = fmaxf(fmaxf(sv[0], sv[1]), fmaxf(sv[2], sv[3]));
+            mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 1));
+            mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, 2));
+            const float mn = fmaxf(m_run, mt);
+            const float msafe = (mn == -INFINITY) ? 0.f : mn;
+            float pv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pv[i] = __expf(sv[i] - msafe);
+            const float corr = __expf(m_run - msafe);
+            float rs = pv[0] + pv[1] + pv[2] + pv[3];
+            rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+            rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+            l_run = l_run * corr + rs;
+            m_run = mn;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { o[i][0] *= corr; o[i][1] *= corr; o[i][2] *= corr; o[i][3] *= corr; }
+            float ph_[4], pl_[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { ph_[i] = __bfloat162float(__float2bfloat16_rn(pv[i])); pl_[i] = pv[i] - ph_[i]; }
+            unsigned pa[4] = {pack_bf16(ph_[0], ph_[1]), pack_bf16(pl_[0], pl_[1]), pack_bf16(ph_[2], ph_[3]), pack_bf16(pl_[2], pl_[3])};
+            if (!splice) mbar_wait_wd(&full_bar[slotV], phV, P.diag, 7u, (unsigned)oi, (unsigned)tt);
+#pragma unroll
+            for (int np = 0; np < 8; ++np) {
+              unsigned vb[4];
+              ldmatrix_x4_trans(vb, Vs + kv_off(ww * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, np * 16 + (lane >> 4) * 8));
+              mma_bf16_16816(o[2 * np], pa, vb[0], vb[1]);
+              mma_bf16_16816(o[2 * np + 1], pa, vb[2], vb[3]);
+            }
+            if (splice) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            worker_sync();                         // all four warps are done with both pages
+            if (wt == 0) { mbar_arrive(&empty_bar[slotK]); mbar_arrive(&empty_bar[slotV]); }
+          }
+          if (tr && first_seg) P.trace[(size_t)oi * ST_TRACE + 3] = clock64();
+          // merge the 4 warps' (m, l, O) and publish this segment's partial
+          const int h = lane >> 2;
+#pragma unroll
+          for (int ntl = 0; ntl < 16; ++ntl) {
+            const int d = ntl * 8 + (lane & 3) * 2;
+            mo[(ww * 8 + h) * HD + d] = o[ntl][0] + o[ntl][2];
+            mo[(ww * 8 + h) * HD + d + 1] = o[ntl][1] + o[ntl][3];
+          }
+          if ((lane & 3) == 0) { mlw[(ww * 8 + h) * 2] = m_run; mlw[(ww * 8 + h) * 2 + 1] = l_run; }
+          worker_sync();
+          const unsigned pslot = blockIdx.x - cta_of_unit(sg.vf + ST_ATT_SEGW, U, G);      // first CTA that holds pages of this group
+          const size_t pbase = (((size_t)m * nkv + g) * G + pslot) * 8;
+          for (int hh = 0; hh < Gq; ++hh) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) mx = fmaxf(mx, mlw[(w * 8 + hh) * 2]);
+            float num = 0.f, den = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              const float mw = mlw[(w * 8 + hh) * 2];
+              const float wgt = (mw == -INFINITY) ? 0.f : __expf(mw - mx);
+              num = fmaf(wgt, mo[(w * 8 + hh) * HD + wt], num);
+              den = fmaf(wgt, mlw[(w * 8 + hh) * 2 + 1], den);
+            }
+            a.part_acc[(pbase + hh) * HD + wt] = num;
+            if (wt == 0) { a.part_ml[(pbase + hh) * 2] = mx; a.part_ml[(pbase + hh) * 2 + 1] = den; }
+          }
+          worker_sync();
+          if (tr && first_seg) P.trace[(size_t)oi * ST_TRACE + 4] = clock64();
+          first_seg = false;
+        }
+        if (tr) P.trace[(size_t)oi * ST_TRACE + 5] = clock64();
+        break;
+      }
       if (op.kind != SK_GEMV) break;
       unsigned u0, u1; int KB;
       st_part(op, u0, u1, KB);
+      ring_advance(u1 - u0);
       if (u0 == u1) break;
       const int M = op.M, K = op.K, N = op.N, nB = op.nB, half = nB >> 1;
       const int units = (int)(u1 - u0);
@@ -383,6 +664,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       //  iteration, 4.4 us per AdaLN stage; every load below is issued before the first value is consumed)
       const int total = M * count * 8;                     // 16-byte chunks (8 consecutive k of one activation row) to stage
       const bool norm = (pro == SP_RMSNORM || pro == SP_ADALN);
+      float* s_w = reinterpret_cast<float*>(breg + 16384);              // SP_COMBINE: [M][NH][G] merge weights w_p / sum_p w_p l_p
+      const int cmb_nh = (((kb_first & 1) + count - 1) >> 1) + 1;       // distinct heads among this CTA's k-blocks (k-block = half a head)
+      const int cmb_off = 16384 + ((M * cmb_nh * (int)G * 4 + 15) & ~15); // after the weights: 2 KB of group partial sums, then merged[M][count][64]
       auto chunk_coord = [&](int c, int& m, int& jloc, int& ch, int& k) {
         m = c / (count * 8);
         const int r = c - m * (count * 8);
@@ -393,7 +677,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       auto chunk_load = [&](int c, float4 (&in)[8]) {       // raw operands of one chunk (nothing is consumed here)
         int m, jloc, ch, k;
         chunk_coord(c, m, jloc, ch, k);
-        if (c >= total || k >= K || pro == SP_DPM) return;
+        if (c >= total || k >= K || pro == SP_DPM || pro == SP_COMBINE) return;
         if (pro == SP_SWIGLU) {
           const float* xr = op.x + (long long)m * op.ldx + 2 * k;
           in[0] = ldcg4(xr); in[1] = ldcg4(xr + 4); in[2] = ldcg4(xr + 8); in[3] = ldcg4(xr + 12);
@@ -426,6 +710,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
           const float* zr = s_z + (m % op.dpm.B) * 64 + k;
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = zr[j];
+        } else if (pro == SP_COMBINE) {
+          const float* cv = reinterpret_cast<const float*>(breg + cmb_off + 2048) + ((size_t)(m * count + jloc) * 64 + ch * 8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = cv[j];
         } else {
           v[0] = in[0].x; v[1] = in[0].y; v[2] = in[0].z; v[3] = in[0].w; v[4] = in[1].x; v[5] = in[1].y; v[6] = in[1].z; v[7] = in[1].w;
           if (norm) {
@@ -459,6 +747,92 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         *reinterpret_cast<uint4*>(blk + (m >> 3) * 1024 + (m & 7) * 128 + ((ch ^ (m & 7)) << 4)) = hv;
         *reinterpret_cast<uint4*>(blk + (rl >> 3) * 1024 + (rl & 7) * 128 + ((ch ^ (rl & 7)) << 4)) = lv;
       };
+      if (pro == SP_COMBINE) {
+        const SAtt& a = op.att;
+        const unsigned Ua = att_vtotal(seq, M);
+        const int Gq = a.kv.q_heads / a.kv.kv_heads, nkv = a.kv.kv_heads;
+        for (int pi = ww; pi < M * cmb_nh; pi += 4) {                     // one warp per (row, head)
+          const int m = pi / cmb_nh, hid = pi - m * cmb_nh;
+          const int h = ((kb_first >> 1) + hid) % a.kv.q_heads, g = h / Gq, hh = h - g * Gq;
+          unsigned pre = 0;
+          for (int mm = 0; mm < m; ++mm) { const unsigned n2 = att_tiles(seq, mm); if (n2) pre += (n2 + ST_ATT_SEGW) * (unsigned)nkv; }
+          const unsigned nt = att_tiles(seq, m);
+          int Pn = 0;
+          float* wrow = s_w + (size_t)pi * G;
+          if (nt) {
+            const unsigned first = pre + (unsigned)g * (nt + ST_ATT_SEGW) + ST_ATT_SEGW;      // virtual unit of page 0 of this group
+            const unsigned c_first = cta_of_unit(first, Ua, G);
+            Pn = (int)(cta_of_unit(first + nt - 1u, Ua, G) - c_first) + 1;
+            const float* ml = a.part_ml + ((((size_t)m * nkv + g) * G) * 8 + hh) * 2;     // slot stride 16 floats
+            float2 mlv[8];                                                                // (max, sum) of slots lane, lane + 32, ...: ONE round trip
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int pq = lane + 32 * i;
+              // slots of CTAs whose unit range is empty (fewer units than CTAs: short contexts) are never written: skip them
+              const unsigned cc = c_first + (unsigned)pq;
+              const bool live = pq < Pn && (Ua * cc / G != Ua * (cc + 1u) / G);
+              mlv[i] = live ? __ldcg(reinterpret_cast<const float2*>(ml + (size_t)pq * 16)) : make_float2(-INFINITY, 0.f);
+            }
+            float mx = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mx = fmaxf(mx, mlv[i].x);
+            mx = warp_max(mx);
+            float den = 0.f, wv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              wv[i] = (mlv[i].x == -INFINITY) ? 0.f : __expf(mlv[i].x - mx);
+              den = fmaf(wv[i], mlv[i].y, den);
+            }
+            den = warp_sum(den);
+            const float rden = 1.f / den;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const int pq = lane + 32 * i; if (pq < Pn) wrow[pq] = wv[i] * rden; }
+          }
+          if (lane == 0) s_pinfo[pi] = Pn;
+        }
+        worker_sync();
+        // merged[m][jloc][64] = sum_p w_p acc_p: work items (output float4, partial group) over all 128 threads, <= 16 loads in flight each
+        const int out4 = M * count * 16;
+        int npg = 1;
+        while (npg * 2 * out4 <= ST_WORKERS && npg < 8) npg *= 2;
+        float4* s_cpart = reinterpret_cast<float4*>(breg + cmb_off);       // [npg][out4], npg * out4 <= 128
+        for (int w0 = wt; w0 < out4 * npg; w0 += ST_WORKERS) {
+          const int o4 = w0 % out4, pg = w0 / out4;
+          const int m = o4 / (count * 16), r = o4 - m * (count * 16), jloc = r >> 4, q4 = r & 15;
+          int kb = kb_first + jloc; if (kb >= KB) kb -= KB;
+          const int k = kb * 64 + q4 * 4, h = k >> 7, d = k & 127, g = h / Gq, hh = h - g * Gq;
+          const int pi = m * cmb_nh + (((kb_first & 1) + jloc) >> 1);
+          const int Pn = s_pinfo[pi];
+          const float* wrow = s_w + (size_t)pi * G;
+          const float* ap = a.part_acc + ((((size_t)m * nkv + g) * G) * 8 + hh) * HD + d;       // slot stride 8 * 128 floats
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int p0 = pg; p0 < Pn; p0 += 16 * npg) {
+            float4 v[16];
+#pragma unroll
+            float wv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int pq = p0 + i * npg;
+              wv[i] = pq < Pn ? wrow[pq] : 0.f;                 // weight 0 = absent / empty slot: its accumulator is never read
+              v[i] = wv[i] != 0.f ? ldcg4(ap + (size_t)pq * (8 * HD)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float w = wv[i];
+              acc.x = fmaf(w, v[i].x, acc.x); acc.y = fmaf(w, v[i].y, acc.y); acc.z = fmaf(w, v[i].z, acc.z); acc.w = fmaf(w, v[i].w, acc.w);
+            }
+          }
+          s_cpart[pg * out4 + o4] = acc;
+        }
+        worker_sync();
+        float4* s_comb = reinterpret_cast<float4*>(breg + cmb_off + 2048);  // [M][count][16] float4
+        for (int o4 = wt; o4 < out4; o4 += ST_WORKERS) {
+          float4 acc = s_cpart[o4];
+          for (int pg = 1; pg < npg; ++pg) { const float4 t4 = s_cpart[pg * out4 + o4]; acc.x += t4.x; acc.y += t4.y; acc.z += t4.z; acc.w += t4.w; }
+          s_comb[o4] = acc;
+        }
+        worker_sync();
+      }
       float4 in0[8], in1[8];
       chunk_load(wt, in0);                                  // first two chunks of this thread: in flight during the statistics
       chunk_load(wt + ST_WORKERS, in1);
