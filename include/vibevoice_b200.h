@@ -95,6 +95,8 @@ int vv_kv_reserve(vv_ctx* ctx, int seq, int64_t n_tokens, void* stream); /* make
 int vv_kv_set_len(vv_ctx* ctx, int seq, int64_t len, void* stream);      /* e.g. 0 = negative-stream refresh (:549-565) */
 int vv_kv_write(vv_ctx* ctx, int seq, int layer, int64_t pos0, int64_t n_tokens,
                 const void* k_bf16, const void* v_bf16, void* stream);   /* prefill hand-off: [n_tokens, kv_heads, head_dim] */
+int vv_kv_delete_slot(vv_ctx* ctx, int seq, int64_t pos, void* stream);  /* forget ONE older entry: the last entry moves into its place (order is
+                                                                           * irrelevant to attention); refresh_negative=False bookkeeping, :599-624 */
 int64_t vv_kv_pages_free(vv_ctx* ctx);
 int64_t vv_kv_pages_total(vv_ctx* ctx);
 

@@ -90,6 +90,17 @@ class FakeEngine:
         self.kv[seq].k[layer] = k.float().transpose(0, 1).contiguous()
         self.kv[seq].v[layer] = v.float().transpose(0, 1).contiguous()
 
+    def kv_delete(self, seq: int, pos: int):
+        assert not self.spec[seq]
+        kv = self.kv[seq]
+        n = len(kv)
+        assert 0 <= pos < n
+        for l in range(len(kv.k)):
+            if kv.k[l] is not None:
+                k, v = kv.k[l].clone(), kv.v[l].clone()
+                k[:, pos], v[:, pos] = k[:, n - 1], v[:, n - 1]
+                kv.k[l], kv.v[l] = k[:, :n - 1], v[:, :n - 1]
+
     def kv_commit(self, advance):
         assert len(advance) == 2 * self.B
         self.calls["kv_commit"] += 1

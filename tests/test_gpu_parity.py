@@ -461,7 +461,7 @@ def test_sde_sampler_vs_oracle():
         model.engine.close()
 
 
-def test_refresh_negative_false_single_prompt_vs_oracle():
+def test_refresh_negative_false_vs_oracle():
     """`refresh_negative=False` (reference :503-517), one prompt with two speaker turns: the negative stream keeps every step's input
     and is never restarted."""
     from oracle import vv_oracle as O
@@ -487,13 +487,31 @@ def test_refresh_negative_false_single_prompt_vs_oracle():
         moved = rel_l2(ref.speech_outputs[0], refreshed.speech_outputs[0])
         report("refresh_negative_false", audio_rel_l2=e, differs_from_refresh_true=moved)
         assert e < 1e-2 and moved > 10 * e, (e, moved)
-        with pytest.raises(NotImplementedError):
-            m2, _, _, _ = make_model("tiny", 2)
-            try:
-                m2.generate(input_ids=torch.cat([ids, ids]), tokenizer=tok, is_prefill=False, max_new_tokens=2, refresh_negative=False,
-                            show_progress_bar=False)
-            finally:
-                m2.engine.close()
+        # batched: rows that are not diffusing when another one is get their negative step undone by the reference's mask / cache shift,
+        # whose guard hides an OLDER entry and keeps the newest one when the cache holds correct_cnt + 2 entries (:599-624) -- reproduced
+        # with vv_kv_delete_slot; speaker turns at different steps in the two rows exercise both outcomes
+        m2, _, _, _ = make_model("tiny", 2)
+        try:
+            ids2 = torch.randint(0, dc.vocab_size - 20, (2, 12), generator=g)
+            ids2[:, -1] = tok.speech_start_id
+            mask2 = torch.ones(2, 12, dtype=torch.long)
+            mask2[1, :3] = 0
+            ids2[1, :3] = tok.pad_token_id
+            scripts = [_scripted(tok, "ddesdddesddx"), _scripted(tok, "dddddesdddx")]
+            m2.set_ddpm_inference_steps(5)
+            torch.manual_seed(9)
+            out2 = m2.generate(input_ids=ids2, attention_mask=mask2, tokenizer=tok, cfg_scale=1.3, is_prefill=False, max_new_tokens=40,
+                               logits_processor=[ForcedTokenScript(scripts)], refresh_negative=False, show_progress_bar=False)
+            torch.manual_seed(9)
+            ref2 = O.generate(sd, cfg, ids2, mask2, tok, cfg_scale=1.3, num_steps=5, max_new_tokens=40, forced_tokens=scripts, kv_bf16=True,
+                              refresh_negative=False)
+            assert torch.equal(out2.sequences, ref2.sequences)
+            for r in range(2):
+                e2 = rel_l2(out2.speech_outputs[r].cpu(), ref2.speech_outputs[r])
+                report("refresh_negative_false_batched", row=r, audio_rel_l2=e2)
+                assert e2 < 1e-2, (r, e2)
+        finally:
+            m2.engine.close()
     finally:
         model.engine.close()
 

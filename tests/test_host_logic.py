@@ -214,7 +214,7 @@ def test_lora_assets_fold_into_base_weights(tmp_path):
     from vibevoice.modular.lora_loading import load_lora_assets  # noqa: F401  (drop-in import path)
 
 
-@pytest.mark.parametrize("case", ["scripted", "free", "maxlen", "quirk", "norefresh1", "sde"])
+@pytest.mark.parametrize("case", ["scripted", "free", "maxlen", "quirk", "norefresh1", "norefresh", "sde"])
 def test_product_generate_host_logic_against_reference_generate_fixture(golden, case):
     """`modeling.generate` (the product's host state machine, a-1/a-2/a-8: token bookkeeping, which KV entries the negative stream
     keeps, restart on <speech_start>, codec-state zeroing, per-row finishing, noise-row packing) driven through a CPU stand-in of the

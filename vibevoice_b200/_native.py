@@ -52,6 +52,7 @@ SYMBOLS = {
     "vv_kv_reserve": (_I, [_P, _I, _L, _P]),
     "vv_kv_set_len": (_I, [_P, _I, _L, _P]),
     "vv_kv_write": (_I, [_P, _I, _I, _L, _L, _P, _P, _P]),
+    "vv_kv_delete_slot": (_I, [_P, _I, _L, _P]),
     "vv_kv_pages_free": (_L, [_P]),
     "vv_kv_pages_total": (_L, [_P]),
     "vv_set_rope_inv_freq": (_I, [_P, _P, _I]),

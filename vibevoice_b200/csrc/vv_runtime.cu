@@ -139,7 +139,9 @@ struct vv_ctx {
   unsigned* st_bar = nullptr;            // grid-barrier counter of the stream kernel
   unsigned* st_diag_host = nullptr; unsigned* st_diag_dev = nullptr;   // host-mapped watchdog record
   int st_inflight = 4;                   // VV_STREAM_INFLIGHT: TMA tiles (16 KB) a CTA keeps in flight
-  int use_stream = 7;                    // VV_STREAM bit 0: sampler, bit 1: LM linears, bit 2: + LM attention (whole decoder stack as one launch)
+  float* dec_front_x = nullptr;                  // where the streamed decoder front leaves its rows (same for every program: fixed structure)
+  float *s_cx = nullptr, *s_cu = nullptr;        // codec rows / FFN hidden sums of the stream path (two buffers each)
+  int use_stream = 15;                    // VV_STREAM bit 0: sampler, bit 1: LM linears, bit 2: + LM attention (whole decoder stack as one launch)
                                          // through the weight-stream kernel; 0 -> kernel-per-stage everywhere
   float* s_rope = nullptr;                        // [2B][64][2] cos / sin of the current positions
   float *s_pacc2 = nullptr, *s_pml2 = nullptr;   // attention partials of the stream path: [2B][kv_heads][SMs][8][128] / [..][8][2]
@@ -429,11 +431,17 @@ static int finish_stream(StreamBuilder& b, vv_ctx::StreamProg* pr) {
     const long long segs = (per + KB - 1) / KB + 1;
     if (segs > ST_MAXSEG || segs * o.nB > 512) return fail(VV_ERR_INVALID, "stream: stage [%d x %d] needs %lld accumulators per CTA", o.N, o.K, segs);
     if (o.store && KB != 1) return fail(VV_ERR_INVALID, "stream: store epilogue needs K <= 64");
+    if (o.pro == SP_MIXER) {
+      if (o.M > 8 || o.K % 4) return fail(VV_ERR_INVALID, "stream: mixer prologue handles at most 8 rows (got %d)", o.M);
+      b_bytes = std::max<long long>(b_bytes, ((count * o.nB * 128 + 1023) & ~1023ll) + (long long)o.M * o.K * 4);
+    }
+    if (o.pro == SP_WINDOW && (o.cod.cin % 8)) return fail(VV_ERR_INVALID, "stream: window prologue needs a channel count that is a multiple of 8");
     if (o.pro == SP_COMBINE) {
       const long long nh = count / 2 + 2;
-      if (count * o.nB * 128 > 16384 || (long long)o.M * nh > 32 || KB != 2 * c->d.num_q_heads)
+      if ((long long)o.M * nh > 128 || KB != 2 * c->d.num_q_heads)
         return fail(VV_ERR_INVALID, "stream: attention-merge prologue does not fit (M=%d, %lld k-blocks per CTA)", o.M, count);
-      b_bytes = std::max<long long>(b_bytes, 16384 + o.M * nh * G * 4 + 16 + 2048 + o.M * count * 256);
+      b_bytes = std::max<long long>(b_bytes, ((count * o.nB * 128 + 1023) & ~1023ll) + o.M * nh * G * 4 + 16 + std::max<long long>(2048, o.M * count * 256) +
+                                                 o.M * count * 256);
     }
     if (U * (G + 1) >= (1ll << 32)) return fail(VV_ERR_INVALID, "stream: stage [%d x %d] has too many tiles for 32-bit scheduling", o.N, o.K);
   }
@@ -1027,6 +1035,8 @@ extern "C" int vv_finalize_weights(vv_ctx* c) {
   RET(dmalloc(c, &c->s_act, (size_t)M2 * I));
   RET(dmalloc(c, &c->s_lgu, (size_t)M2 * 2 * I));
   RET(dmalloc(c, &c->s_rope, (size_t)M2 * HD));
+  RET(dmalloc(c, &c->s_cx, (size_t)2 * B * 8192));
+  RET(dmalloc(c, &c->s_cu, (size_t)2 * B * 32768));
   RET(dmalloc(c, &c->s_pacc2, (size_t)M2 * d.num_kv_heads * c->sm_count * 8 * HD));
   RET(dmalloc(c, &c->s_pml2, (size_t)M2 * d.num_kv_heads * c->sm_count * 8 * 2));
   RET(dmalloc(c, &c->s_pacc, (size_t)M2 * d.num_q_heads * c->nsplit * HD));
@@ -1190,6 +1200,37 @@ extern "C" int vv_kv_set_len(vv_ctx* c, int seq, int64_t len, void* stream) {
 extern "C" int vv_kv_commit(vv_ctx* c, const int32_t* adv, void* stream) {
   if (!c || !c->kpool) return fail(VV_ERR_STATE, "KV pool not initialised");
   for (int i = 0; i < 2 * c->d.max_batch; ++i) c->kv_len_host[i] += adv[i] ? 1 : 0;
+  return push_lens(c, (cudaStream_t)stream);
+}
+// drop the entry at position `pos` of a sequence: the last committed entry moves into its place (all layers), the length shrinks by one.
+// Attention does not depend on the order of the cached entries (keys are stored rotated), so this is how a sequence forgets an OLDER entry --
+// the reference's cache shifting with refresh_negative=False hides one (modeling_vibevoice_inference.py:599-624).
+__global__ void kv_move_kernel(bf16* kpool, bf16* vpool, const int* page_row, int kv_heads, size_t per_layer, int src, int dst) {
+  const int layer = blockIdx.x;
+  const int sp = page_row[src / KV_PAGE], dp = page_row[dst / KV_PAGE];
+  for (int i = threadIdx.x; i < kv_heads * HD; i += blockDim.x) {
+    const int h = i / HD, d = i % HD;
+    const size_t so = per_layer * layer + (((size_t)sp * kv_heads + h) * KV_PAGE + (src % KV_PAGE)) * HD + d;
+    const size_t dofs = per_layer * layer + (((size_t)dp * kv_heads + h) * KV_PAGE + (dst % KV_PAGE)) * HD + d;
+    kpool[dofs] = kpool[so];
+    vpool[dofs] = vpool[so];
+  }
+}
+extern "C" int vv_kv_delete_slot(vv_ctx* c, int seq, int64_t pos, void* stream) {
+  if (!c || !c->kpool) return fail(VV_ERR_STATE, "KV pool not initialised");
+  if (seq < 0 || seq >= 2 * c->d.max_batch) return fail(VV_ERR_INVALID, "bad seq %d", seq);
+  const int64_t len = c->kv_len_host[seq];
+  if (pos < 0 || pos >= len) return fail(VV_ERR_INVALID, "vv_kv_delete_slot: position %lld outside [0,%lld)", (long long)pos, (long long)len);
+  const auto& d = c->d;
+  if (pos != len - 1) {
+    const size_t per_layer = (size_t)c->n_pages * d.num_kv_heads * KV_PAGE * HD;
+    kv_move_kernel<<<d.num_layers, 256, 0, (cudaStream_t)stream>>>(c->kpool, c->vpool, c->page_table_dev + (size_t)seq * c->max_pages, d.num_kv_heads, per_layer,
+                                                                  (int)(len - 1), (int)pos);
+    CKL();
+    c->launches++;
+  }
+  c->kv_len_host[seq] = len - 1;
+  release_pages(c, seq, len - 1 + 1);     // keep the page of the next speculative entry
   return push_lens(c, (cudaStream_t)stream);
 }
 extern "C" int vv_set_row_mode(vv_ctx* c, const int32_t* rm, void* stream) {
@@ -1700,26 +1741,169 @@ struct ScopedMinRows {     // the codec stages may use a different GEMV/GEMM row
   ~ScopedMinRows() { c->mma_min_rows = saved; }
 };
 
-static int enqueue_decode(const L& l, const float* latent, const int32_t* active, float* audio) {
+// ---- codec stages with B*T <= 8 rows (96 % of the codec's weights: 2048- and 1024-wide blocks, stem / up- / down-sampling convolutions
+// next to them) as weight-stream programs (vv_stream.cuh: SP_WINDOW, SP_MIXER): two stages per Block1D instead of five kernels ------------
+// Buffers: rows ping-pong between X[0] / X[1], FFN hidden sums between U[0] / U[1].  A block reads X[a], its owner CTA stores x1 into X[a^1]
+// and the second linear accumulates there; a convolution accumulates into a ZEROED buffer -- zero-fill jobs ride on the stage after the
+// buffer's last reader.
+static bool codec_stream_stage(const vv_ctx* c, const Codec& k, int i) {
+  const long long rows = (long long)c->d.max_batch * k.T[i];
+  return (c->use_stream & 8) && rows <= 8 && rows * k.C[i] * 4 <= 65536;
+}
+static long long codec_x_floats(const vv_ctx* c) { return (long long)c->d.max_batch * 8192; }
+static long long codec_u_floats(const vv_ctx* c) { return (long long)c->d.max_batch * 32768; }
+static void window_op(SOp* o, const ConvL& cv, const float* src, int T_in, int T_out, int row_stride, float alpha, float beta) {
+  o->pro = SP_WINDOW;
+  SCodec& w = o->cod;
+  memset(&w, 0, sizeof w);
+  w.hist = cv.hist; w.next = cv.next; w.src = src; w.ctx = cv.ctx; w.T_in = T_in; w.T_out = T_out; w.stride = row_stride; w.cin = cv.Cin;
+  w.alpha = alpha; w.beta = beta;
+}
+struct CodecBufs {
+  float* X[2]; float* U[2];
+  int cur = 0, ub = 0;
+  explicit CodecBufs(vv_ctx* c) { X[0] = c->s_cx; X[1] = c->s_cx + codec_x_floats(c); U[0] = c->s_cu; U[1] = c->s_cu + codec_u_floats(c); }
+};
+// all blocks of one stage; rows enter in X[cur] and leave in X[cur]; if `zero_for_next` the buffer the FOLLOWING convolution accumulates
+// into (= the input of the stage's last block) is zero-filled on that block's second linear
+static int stage_ops(StreamBuilder& b, vv_ctx* c, CodecBufs& cb, const std::vector<Block>& blocks, int B, int T, bool zero_for_next, float* extra_zero,
+                     long long extra_n) {
+  for (size_t j = 0; j < blocks.size(); ++j) {
+    const Block& blk = blocks[j];
+    const int C = blk.C, M = B * T;
+    SOp* o;
+    RET(b.gemv(blk.w1, blk.b1, cb.X[cb.cur], C, cb.U[cb.ub], 4 * C, M, 4 * C, C, true, &o));
+    o->pro = SP_MIXER;
+    SCodec& w = o->cod;
+    memset(&w, 0, sizeof w);
+    w.hist = blk.hist; w.next = blk.next; w.T_out = T; w.norm_w = blk.norm_w; w.dw_w = blk.dw_w; w.dw_b = blk.dw_b; w.gamma = blk.gamma;
+    w.ffn_norm_w = blk.ffn_norm_w; w.x1_out = cb.X[cb.cur ^ 1]; w.eps = c->d.codec_eps;
+    o->init_dst = cb.U[cb.ub ^ 1]; o->init_n = codec_u_floats(c);          // hidden-sum buffer of the NEXT block (its reader finished two stages ago)
+    RET(b.gemv(blk.w2, blk.b2, cb.U[cb.ub], 4 * C, cb.X[cb.cur ^ 1], C, M, C, 4 * C, true, &o));
+    o->pro = SP_GELU; o->alpha_kind = SA_GAMMA; o->alpha = blk.ffn_gamma;
+    if (j + 1 == blocks.size()) {
+      if (zero_for_next) { o->init_dst = cb.X[cb.cur]; o->init_n = codec_x_floats(c); }
+      if (extra_zero) { o->init2_dst = extra_zero; o->init2_n = extra_n; }
+    }
+    cb.cur ^= 1; cb.ub ^= 1;
+  }
+  return 0;
+}
+
+// decoder front: stem conv + the leading stages with <= 8 rows; *n_front = stages covered, *out_x = where the last one leaves its rows
+static int dec_front_prog(vv_ctx* c, const float* latent, const vv_ctx::StreamProg** out, int* n_front, float** out_x) {
+  Codec& k = c->dec;
+  const auto& d = c->d;
+  const int B = d.max_batch;
+  int nf = 0;
+  while (nf < d.n_stages - 1 && codec_stream_stage(c, k, nf)) ++nf;
+  *n_front = nf; *out = nullptr; *out_x = nullptr;
+  if (nf == 0) return 0;
+  char key[96];
+  snprintf(key, sizeof key, "decf:%p", (const void*)latent);
+  {
+    auto hit = c->sprogs.find(key);
+    if (hit != c->sprogs.end()) { *out = &hit->second; *out_x = c->dec_front_x; return 0; }
+  }
+  CodecBufs cb(c);
+  StreamBuilder b(c);
+  b.nop(false, cb.X[0], codec_x_floats(c));
+  b.ops.back().init2_dst = cb.U[0]; b.ops.back().init2_n = codec_u_floats(c);
+  SOp* o;
+  RET(b.gemv(k.convs[0].w, k.convs[0].bias, nullptr, 0, cb.X[0], k.convs[0].N, B, k.convs[0].N, k.convs[0].K, true, &o));
+  window_op(o, k.convs[0], latent, 1, 1, 1, 1.0f / c->speech_scale, -c->speech_bias);
+  for (int i = 0; i < nf; ++i) {
+    if (i > 0) {                                  // transposed conv into stage i: row (b, t) = [previous frame | frame t] -> s * Co outputs
+      const ConvL& cv = k.convs[i];
+      const int Tin = k.T[i - 1];
+      RET(b.gemv(cv.w, cv.bias, nullptr, 0, cb.X[cb.cur ^ 1], cv.N, B * Tin, cv.N, cv.K, true, &o));
+      window_op(o, cv, cb.X[cb.cur], Tin, Tin, 1, 1.f, 0.f);
+      cb.cur ^= 1;
+    }
+    RET(stage_ops(b, c, cb, k.stages[i], B, k.T[i], i + 1 < nf, nullptr, 0));
+  }
+  *out_x = c->dec_front_x = cb.X[cb.cur];
+  auto it = c->sprogs.find(key);
+  if (it == c->sprogs.end()) {
+    vv_ctx::StreamProg pr;
+    RET(finish_stream(b, &pr));
+    it = c->sprogs.emplace(key, pr).first;
+  }
+  *out = &it->second;
+  return 0;
+}
+
+// encoder back: the trailing stages with <= 8 rows, each behind its strided conv, + the head conv.  `xin` = rows entering the conv of the
+// first covered stage (produced by the kernel-per-stage path).
+static int enc_back_first(const vv_ctx* c) {
+  const Codec& k = c->enc;
+  int f = c->d.n_stages;
+  while (f > 1 && codec_stream_stage(c, k, f - 1)) --f;
+  return f;
+}
+static int enc_back_prog(vv_ctx* c, const float* xin, float* feat, const vv_ctx::StreamProg** out) {
+  Codec& k = c->enc;
+  const auto& d = c->d;
+  const int B = d.max_batch, ns = d.n_stages, f = enc_back_first(c);
+  *out = nullptr;
+  if (f >= ns) return 0;
+  char key[96];
+  snprintf(key, sizeof key, "encb:%p:%p", (const void*)xin, (void*)feat);
+  auto it = c->sprogs.find(key);
+  if (it != c->sprogs.end()) { *out = &it->second; return 0; }
+  CodecBufs cb(c);
+  StreamBuilder b(c);
+  b.nop(false, cb.X[0], codec_x_floats(c));
+  b.ops.back().init2_dst = cb.U[0]; b.ops.back().init2_n = codec_u_floats(c);
+  SOp* o;
+  for (int i = f; i < ns; ++i) {
+    const ConvL& cv = k.convs[i];
+    const int Tin = k.T[i - 1], Tout = k.T[i];
+    float* dst = (i == f) ? cb.X[0] : cb.X[cb.cur ^ 1];
+    RET(b.gemv(cv.w, cv.bias, nullptr, 0, dst, cv.N, B * Tout, cv.N, cv.K, true, &o));      // strided conv: window rows [t*r, t*r + 2r)
+    window_op(o, cv, i == f ? xin : cb.X[cb.cur], Tin, Tout, cv.stride, 1.f, 0.f);
+    if (i > f) cb.cur ^= 1;
+    const bool last = (i + 1 == ns);
+    RET(stage_ops(b, c, cb, k.stages[i], B, Tout, !last, last ? feat : nullptr, (long long)B * d.semantic_vae_dim));
+  }
+  const ConvL& hd = k.convs[ns];
+  RET(b.gemv(hd.w, hd.bias, nullptr, 0, feat, hd.N, B, hd.N, hd.K, true, &o));
+  window_op(o, hd, cb.X[cb.cur], 1, 1, 1, 1.f, 0.f);
+  vv_ctx::StreamProg pr;
+  RET(finish_stream(b, &pr));
+  it = c->sprogs.emplace(key, pr).first;
+  *out = &it->second;
+  return 0;
+}
+
+static int enqueue_decode(const L& l, const float* latent, const int32_t* active, float* audio, const vv_ctx::StreamProg* front = nullptr,
+                          int n_front = 0, float* front_x = nullptr) {
   vv_ctx* c = l.c;
   ScopedMinRows scoped(c, c->codec_mma_min_rows);
   const auto& d = c->d;
   Codec& k = c->dec;
   const int B = d.max_batch, ns = d.n_stages;
   float *xa = c->s_xa, *xb = c->s_xb;
-  // stem: window over the last 7 (un-scaled) latent frames; un-scaling latent/scale - bias (:636) is folded in
-  RET(assemble(l, latent, k.convs[0].hist, c->s_win, k.convs[0].next, B, 1, 6, 64, nullptr, 0.f, 1.0f / c->speech_scale, -c->speech_bias));
-  RET(conv_apply(l, k.convs[0], c->s_win, xa, B, 1, 1));
-  for (int i = 0; i < ns; ++i) {
+  if (front) {
+    RET(launch_stream(l, *front));              // stem + stages [0, n_front) through the weight-stream kernel
+    xa = front_x;
+  } else {
+    n_front = 0;
+    // stem: window over the last 7 (un-scaled) latent frames; un-scaling latent/scale - bias (:636) is folded in
+    RET(assemble(l, latent, k.convs[0].hist, c->s_win, k.convs[0].next, B, 1, 6, 64, nullptr, 0.f, 1.0f / c->speech_scale, -c->speech_bias));
+    RET(conv_apply(l, k.convs[0], c->s_win, xa, B, 1, 1));
+  }
+  for (int i = n_front; i < ns; ++i) {
     if (i > 0) {
       const ConvL& cv = k.convs[i];
       const int Tin = k.T[i - 1];
       RET(assemble(l, xa, cv.hist, c->s_win, cv.next, B, Tin, 1, cv.Cin, nullptr, 0.f, 1.f, 0.f));
       RowMap xm; xm.T = Tin; xm.bs = (long long)(1 + Tin) * cv.Cin; xm.rs = cv.Cin;
-      GemvP p = mk(cv.w, cv.bias, c->s_win, 0, xb, cv.N, B * Tin, cv.N, cv.K);
+      float* dst = (xa == c->s_xa) ? c->s_xb : c->s_xa;
+      GemvP p = mk(cv.w, cv.bias, c->s_win, 0, dst, cv.N, B * Tin, cv.N, cv.K);
       p.xmap = xm;
       RET(linear(l, p));
-      std::swap(xa, xb);
+      xa = dst; xb = (xa == c->s_xa) ? c->s_xb : c->s_xa;
     }
     for (const Block& b : k.stages[i]) { RET(enqueue_block(l, b, xa, xb, B, k.T[i], d.codec_eps)); std::swap(xa, xb); }
   }
@@ -1731,17 +1915,30 @@ static int enqueue_decode(const L& l, const float* latent, const int32_t* active
   return 0;
 }
 
-static int enqueue_encode(const L& l, const float* audio, const int32_t* active, float* feat) {
+// stages [0, n_stream_first) of the semantic encoder through the kernel-per-stage path; returns where their rows are (the stream program of
+// the remaining stages was built against that pointer)
+static float* encode_front_out(vv_ctx* c, int first) {
+  // the ping-pong below is deterministic: stem -> s_xa, every conv and every block swaps
+  const Codec& k = c->enc;
+  bool in_a = true;
+  for (int i = 0; i < first; ++i) {
+    if (i > 0) in_a = !in_a;
+    if (k.stages[i].size() & 1) in_a = !in_a;
+  }
+  return in_a ? c->s_xa : c->s_xb;
+}
+static int enqueue_encode(const L& l, const float* audio, const int32_t* active, float* feat, const vv_ctx::StreamProg* back = nullptr) {
   vv_ctx* c = l.c;
   ScopedMinRows scoped(c, c->codec_mma_min_rows);
   const auto& d = c->d;
   Codec& k = c->enc;
   const int B = d.max_batch, ns = d.n_stages;
+  const int stop = back ? enc_back_first(c) : ns;
   float *xa = c->s_xa, *xb = c->s_xb;
   int hop = k.T[0];
   RET(assemble(l, audio, k.convs[0].hist, c->s_win, k.convs[0].next, B, hop, 6, 1, nullptr, 0.f, 1.f, 0.f));
   RET(conv_apply(l, k.convs[0], c->s_win, xa, B, hop, hop));
-  for (int i = 0; i < ns; ++i) {
+  for (int i = 0; i < stop; ++i) {
     if (i > 0) {
       const ConvL& cv = k.convs[i];
       const int Tin = k.T[i - 1];
@@ -1751,9 +1948,14 @@ static int enqueue_encode(const L& l, const float* audio, const int32_t* active,
     }
     for (const Block& b : k.stages[i]) { RET(enqueue_block(l, b, xa, xb, B, k.T[i], d.codec_eps)); std::swap(xa, xb); }
   }
-  const ConvL& hd = k.convs[ns];
-  RET(assemble(l, xa, hd.hist, c->s_win, hd.next, B, 1, 6, hd.Cin, nullptr, 0.f, 1.f, 0.f));
-  RET(conv_apply(l, hd, c->s_win, feat, B, 1, 1));
+  if (back) {
+    if (xa != encode_front_out(c, stop)) return fail(VV_ERR_STATE, "encoder hand-off buffer mismatch");
+    RET(launch_stream(l, *back));
+  } else {
+    const ConvL& hd = k.convs[ns];
+    RET(assemble(l, xa, hd.hist, c->s_win, hd.next, B, 1, 6, hd.Cin, nullptr, 0.f, 1.f, 0.f));
+    RET(conv_apply(l, hd, c->s_win, feat, B, 1, 1));
+  }
   CK(launch_k(l, advance_kernel, dim3(k.n_segs, B, ADV_SLICES), dim3(256), 0, k.segs_dev, active));
   return 0;
 }
@@ -1781,14 +1983,18 @@ extern "C" int vv_codec_decode_frame(vv_ctx* c, const float* latent, const int32
   CK(cudaSetDevice(c->device));
   char key[256];
   snprintf(key, sizeof key, "dec:%p:%p:%p", (const void*)latent, (const void*)active, (void*)audio_out);
-  return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_decode(l, latent, active, audio_out); });
+  const vv_ctx::StreamProg* front = nullptr; int nf = 0; float* fx = nullptr;
+  RET(dec_front_prog(c, latent, &front, &nf, &fx));
+  return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_decode(l, latent, active, audio_out, front, nf, fx); });
 }
 extern "C" int vv_semantic_encode_frame(vv_ctx* c, const float* audio, const int32_t* active, float* feat_out, void* stream) {
   if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
   CK(cudaSetDevice(c->device));
   char key[256];
   snprintf(key, sizeof key, "enc:%p:%p:%p", (const void*)audio, (const void*)active, (void*)feat_out);
-  return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_encode(l, audio, active, feat_out); });
+  const vv_ctx::StreamProg* back = nullptr;
+  RET(enc_back_prog(c, encode_front_out(c, enc_back_first(c)), feat_out, &back));
+  return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) { return enqueue_encode(l, audio, active, feat_out, back); });
 }
 extern "C" int vv_connect(vv_ctx* c, const float* latent, const float* sem, const int32_t* active, float* embeds, void* stream) {
   if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
@@ -1806,10 +2012,13 @@ extern "C" int vv_frame_tail(vv_ctx* c, const float* hidden, const float* noise,
            (void*)audio_out, (void*)embeds);
   const vv_ctx::StreamProg* sprog = nullptr;
   if (c->use_stream & 1) RET(sampler_stream_prog(c, noise, latent_out, &sprog));
+  const vv_ctx::StreamProg *front = nullptr, *back = nullptr; int nf = 0; float* fx = nullptr;
+  RET(dec_front_prog(c, latent_out, &front, &nf, &fx));
+  RET(enc_back_prog(c, encode_front_out(c, enc_back_first(c)), c->s_feat, &back));
   return run_cached(c, key, (cudaStream_t)stream, [&](const L& l) {
     RET(enqueue_diffusion(l, hidden, noise, latent_out, sprog));
-    RET(enqueue_decode(l, latent_out, active, audio_out));
-    RET(enqueue_encode(l, audio_out, active, c->s_feat));
+    RET(enqueue_decode(l, latent_out, active, audio_out, front, nf, fx));
+    RET(enqueue_encode(l, audio_out, active, c->s_feat, back));
     return enqueue_connect(l, latent_out, c->s_feat, active, embeds);
   });
 }

@@ -88,7 +88,7 @@ constexpr int ST_MAX_STAGES = 12;
 constexpr int ST_BAR_REP = 0;
 
 enum SKind { SK_GEMV = 0, SK_NOP = 1, SK_ATTN = 2 };
-enum SPro { SP_NONE = 0, SP_RMSNORM = 1, SP_ADALN = 2, SP_SWIGLU = 3, SP_GELU = 4, SP_DPM = 5, SP_SILU = 6, SP_COMBINE = 7 };
+enum SPro { SP_NONE = 0, SP_RMSNORM = 1, SP_ADALN = 2, SP_SWIGLU = 3, SP_GELU = 4, SP_DPM = 5, SP_SILU = 6, SP_COMBINE = 7, SP_WINDOW = 8, SP_MIXER = 9 };
 enum SAlpha { SA_ONE = 0, SA_GATE = 1 /* alpha[m][n], row stride lda */, SA_GAMMA = 2 /* alpha[n] */ };
 
 // CFG + DPM-Solver++ update of step `step` (same arithmetic as dpm_update_proj_kernel), evaluated in the prologue of the stage that
@@ -119,6 +119,24 @@ struct SAtt {
                                // positions up to 64K costs ~1 us per segment when every CTA recomputes it)
 };
 
+// Streaming-codec prologues (modular_vibevoice_tokenizer.py:327-382, 620-684; same arithmetic as assemble_window / dwconv_res / rows_norm):
+//  SP_WINDOW  activation row (b, t) = rows [t*stride, t*stride + k) of the causal window [hist[b] (ctx rows) ; alpha*src[b]+beta (T_in rows)],
+//             each row `cin` wide, flattened (K = k * cin): strided / transposed convolutions as window GEMVs.  The CTA that owns unit 0
+//             writes the next history (the window's last ctx rows) into `next`.
+//  SP_MIXER   the whole first half of a Block1D in the prologue of its first FFN linear, for rows (b, t), t < T, C = K channels:
+//             xn = RMSNorm(x) * norm_w;  x1 = x + gamma * (dw_b + sum_j dw_w[j] * win[t + j]),  win = [hist[b] (6 normalised rows) ; xn];
+//             B operand = RMSNorm(x1) * ffn_norm_w.  Every CTA recomputes it (it needs full-row statistics of x1 anyway; M * C <= 16 K
+//             values), the owner of unit 0 publishes x1 (the residual base the second FFN linear accumulates into) and the next history.
+struct SCodec {
+  const float* hist; float* next;        // [B][ctx][cin] / [B][6][C]
+  const float* src;                      // SP_WINDOW: [B][T_in][cin]
+  int ctx, T_in, T_out, stride, cin;     // SP_WINDOW geometry (T_out rows per sample); SP_MIXER: T_out = T
+  float alpha, beta;
+  const float* norm_w; const float* dw_w; const float* dw_b; const float* gamma; const float* ffn_norm_w;   // SP_MIXER
+  float* x1_out;                         // SP_MIXER: [M][C]
+  float eps;
+};
+
 struct alignas(16) SOp {
   int kind;
   int sync_before;          // wait until every CTA has finished the previous stage (grid barrier) before touching activations
@@ -132,6 +150,7 @@ struct alignas(16) SOp {
   const float* pro_shift; const float* pro_scale; long long pro_ld;
   SDpm dpm;                              // SP_DPM only
   SAtt att;                              // SK_ATTN, SP_COMBINE
+  SCodec cod;                            // SP_WINDOW, SP_MIXER
   float* y; long long ldy;               // y[m][n] += alpha * (acc + bias[n] if the segment starts at k = 0);  store != 0: y = ... (KB == 1 only)
   const float* bias;
   int alpha_kind; const float* alpha; long long lda;
@@ -272,7 +291,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
   __shared__ float s_inv[64];
   __shared__ float s_z[8 * 64];
   __shared__ __align__(16) unsigned char s_opbuf[2][sizeof(SOp)];
-  __shared__ int s_pinfo[32];
+  __shared__ int s_pinfo[128];
   const unsigned raw_addr = smem_u32(st_raw);
   unsigned char* sm = st_raw + ((1024u - (raw_addr & 1023u)) & 1023u);      // 1024 B aligned (swizzle atom)
   unsigned char* ring = sm;
@@ -664,9 +683,13 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       //  iteration, 4.4 us per AdaLN stage; every load below is issued before the first value is consumed)
       const int total = M * count * 8;                     // 16-byte chunks (8 consecutive k of one activation row) to stage
       const bool norm = (pro == SP_RMSNORM || pro == SP_ADALN);
-      float* s_w = reinterpret_cast<float*>(breg + 16384);              // SP_COMBINE: [M][NH][G] merge weights w_p / sum_p w_p l_p
+      float* s_mix = reinterpret_cast<float*>(breg + ((count * nB * 128 + 1023) & ~1023));   // SP_MIXER: x1 [M][C] behind the B operand
+      // SP_COMBINE scratch behind the B operand: [M][NH][G] merge weights w_p / sum_p w_p l_p | group partial sums | merged[M][count][64]
+      const int cmb_base = (count * nB * 128 + 1023) & ~1023;
+      float* s_w = reinterpret_cast<float*>(breg + cmb_base);
       const int cmb_nh = (((kb_first & 1) + count - 1) >> 1) + 1;       // distinct heads among this CTA's k-blocks (k-block = half a head)
-      const int cmb_off = 16384 + ((M * cmb_nh * (int)G * 4 + 15) & ~15); // after the weights: 2 KB of group partial sums, then merged[M][count][64]
+      const int cmb_off = cmb_base + ((M * cmb_nh * (int)G * 4 + 15) & ~15);
+      const int cmb_part = (M * count * 256 > 2048) ? M * count * 256 : 2048;     // bytes of the group partial sums (npg * out4 float4)
       auto chunk_coord = [&](int c, int& m, int& jloc, int& ch, int& k) {
         m = c / (count * 8);
         const int r = c - m * (count * 8);
@@ -677,7 +700,14 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       auto chunk_load = [&](int c, float4 (&in)[8]) {       // raw operands of one chunk (nothing is consumed here)
         int m, jloc, ch, k;
         chunk_coord(c, m, jloc, ch, k);
-        if (c >= total || k >= K || pro == SP_DPM || pro == SP_COMBINE) return;
+        if (c >= total || k >= K || pro == SP_DPM || pro == SP_COMBINE || pro == SP_MIXER) return;
+        if (pro == SP_WINDOW) {
+          const SCodec& w = op.cod;
+          const int b = m / w.T_out, t = m - b * w.T_out, j = k / w.cin, ci = k - j * w.cin, r = t * w.stride + j;
+          const float* xr = r < w.ctx ? w.hist + ((size_t)b * w.ctx + r) * w.cin + ci : w.src + ((size_t)b * w.T_in + (r - w.ctx)) * w.cin + ci;
+          in[0] = ldcg4(xr); in[1] = ldcg4(xr + 4);
+          return;
+        }
         if (pro == SP_SWIGLU) {
           const float* xr = op.x + (long long)m * op.ldx + 2 * k;
           in[0] = ldcg4(xr); in[1] = ldcg4(xr + 4); in[2] = ldcg4(xr + 8); in[3] = ldcg4(xr + 12);
@@ -710,8 +740,23 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
           const float* zr = s_z + (m % op.dpm.B) * 64 + k;
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = zr[j];
+        } else if (pro == SP_WINDOW) {
+          const SCodec& w = op.cod;
+          const int b = m / w.T_out, t = m - b * w.T_out, j = k / w.cin, r = t * w.stride + j;
+          v[0] = in[0].x; v[1] = in[0].y; v[2] = in[0].z; v[3] = in[0].w; v[4] = in[1].x; v[5] = in[1].y; v[6] = in[1].z; v[7] = in[1].w;
+          if (r >= w.ctx) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) v[jj] = v[jj] * w.alpha + w.beta;
+          }
+          (void)b;
+        } else if (pro == SP_MIXER) {
+          const float* xr = s_mix + (size_t)m * K + k;
+          const float inv = s_inv[m];
+          const float4 w0 = *reinterpret_cast<const float4*>(op.cod.ffn_norm_w + k), w1 = *reinterpret_cast<const float4*>(op.cod.ffn_norm_w + k + 4);
+          v[0] = xr[0] * inv * w0.x; v[1] = xr[1] * inv * w0.y; v[2] = xr[2] * inv * w0.z; v[3] = xr[3] * inv * w0.w;
+          v[4] = xr[4] * inv * w1.x; v[5] = xr[5] * inv * w1.y; v[6] = xr[6] * inv * w1.z; v[7] = xr[7] * inv * w1.w;
         } else if (pro == SP_COMBINE) {
-          const float* cv = reinterpret_cast<const float*>(breg + cmb_off + 2048) + ((size_t)(m * count + jloc) * 64 + ch * 8);
+          const float* cv = reinterpret_cast<const float*>(breg + cmb_off + cmb_part) + ((size_t)(m * count + jloc) * 64 + ch * 8);
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = cv[j];
         } else {
@@ -825,12 +870,99 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
           s_cpart[pg * out4 + o4] = acc;
         }
         worker_sync();
-        float4* s_comb = reinterpret_cast<float4*>(breg + cmb_off + 2048);  // [M][count][16] float4
+        float4* s_comb = reinterpret_cast<float4*>(breg + cmb_off + cmb_part);  // [M][count][16] float4
         for (int o4 = wt; o4 < out4; o4 += ST_WORKERS) {
           float4 acc = s_cpart[o4];
           for (int pg = 1; pg < npg; ++pg) { const float4 t4 = s_cpart[pg * out4 + o4]; acc.x += t4.x; acc.y += t4.y; acc.z += t4.z; acc.w += t4.w; }
           s_comb[o4] = acc;
         }
+        worker_sync();
+      }
+      if (pro == SP_WINDOW && u0 == 0) {                               // owner: next history = last ctx rows of every sample's window
+        const SCodec& w = op.cod;
+        const int per = w.ctx * w.cin, nrow = w.ctx + w.T_in;
+        for (int i = wt; i < (M / w.T_out) * per; i += ST_WORKERS) {
+          const int b = i / per, q = i - b * per, rr = q / w.cin, ci = q - rr * w.cin, r = nrow - w.ctx + rr;
+          w.next[i] = r < w.ctx ? ldcg1(w.hist + ((size_t)b * w.ctx + r) * w.cin + ci)
+                                : ldcg1(w.src + ((size_t)b * w.T_in + (r - w.ctx)) * w.cin + ci) * w.alpha + w.beta;
+        }
+      }
+      if (pro == SP_MIXER) {
+        const SCodec& w = op.cod;
+        const int C = K, T = w.T_out;                                  // M = B * T rows, M <= 8 (host-checked)
+        // pass A: raw rows into shared memory + sum of squares -> inv1
+        float ss[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss[j] = 0.f;
+        for (int c4 = wt; c4 < (C >> 2); c4 += ST_WORKERS) {
+          float4 xv[8];
+#pragma unroll
+          for (int mm = 0; mm < 8; ++mm) xv[mm] = mm < M ? ldcg4(op.x + (long long)mm * op.ldx + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int mm = 0; mm < 8; ++mm) {
+            if (mm < M) {
+              *reinterpret_cast<float4*>(s_mix + (size_t)mm * C + 4 * c4) = xv[mm];
+              ss[mm] += xv[mm].x * xv[mm].x + xv[mm].y * xv[mm].y + xv[mm].z * xv[mm].z + xv[mm].w * xv[mm].w;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ss[j] = warp_sum(ss[j]); if (lane == 0) s_red[ww][j] = ss[j]; }
+        worker_sync();
+        if (wt < 8) s_inv[8 + wt] = rsqrtf((s_red[0][wt] + s_red[1][wt] + s_red[2][wt] + s_red[3][wt]) / (float)C + w.eps);   // inv1
+        worker_sync();
+        // pass B: thread-private channels; rows of a sample in DESCENDING time so x1 can overwrite the raw row in place
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss[j] = 0.f;
+        const int Bn = M / T;
+        for (int c = wt; c < C; c += ST_WORKERS) {
+          const float nw = w.norm_w[c], gm = w.gamma[c], db = w.dw_b[c];
+          float tap[7];
+#pragma unroll
+          for (int j = 0; j < 7; ++j) tap[j] = w.dw_w[j * C + c];
+          for (int b = 0; b < Bn; ++b) {
+            float hv[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) hv[j] = ldcg1(w.hist + ((size_t)b * 6 + j) * C + c);
+            auto win = [&](int r) -> float {                             // window row r of sample b, channel c
+              if (r < 6) return hv[r < 0 ? 0 : r];
+              const int mm = b * T + (r - 6);
+              return s_mix[(size_t)mm * C + c] * s_inv[8 + mm] * nw;
+            };
+            if (u0 == 0) {
+#pragma unroll
+              for (int r = 0; r < 6; ++r) {
+                const int rr = T + r;
+                float val;
+                if (rr < 6) { val = hv[0]; for (int q = 1; q < 6; ++q) if (q == rr) val = hv[q]; }
+                else val = s_mix[(size_t)(b * T + rr - 6) * C + c] * s_inv[8 + b * T + rr - 6] * nw;
+                w.next[((size_t)b * 6 + r) * C + c] = val;
+              }
+            }
+            for (int t = T - 1; t >= 0; --t) {
+              float acc = db;
+#pragma unroll
+              for (int j = 0; j < 7; ++j) {
+                const int r = t + j;
+                float wv;
+                if (r < 6) { wv = hv[0]; for (int q = 1; q < 6; ++q) if (q == r) wv = hv[q]; }
+                else wv = s_mix[(size_t)(b * T + r - 6) * C + c] * s_inv[8 + b * T + r - 6] * nw;
+                acc = fmaf(tap[j], wv, acc);
+              }
+              const int mm = b * T + t;
+              const float x1 = s_mix[(size_t)mm * C + c] + gm * acc;
+              s_mix[(size_t)mm * C + c] = x1;
+              if (u0 == 0) w.x1_out[(size_t)mm * C + c] = x1;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) if (j == mm) ss[j] = fmaf(x1, x1, ss[j]);
+            }
+          }
+        }
+        worker_sync();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ss[j] = warp_sum(ss[j]); if (lane == 0) s_red[ww][j] = ss[j]; }
+        worker_sync();
+        if (wt < 8) s_inv[wt] = rsqrtf((s_red[0][wt] + s_red[1][wt] + s_red[2][wt] + s_red[3][wt]) / (float)C + w.eps);        // inv2
         worker_sync();
       }
       float4 in0[8], in1[8];

@@ -154,6 +154,10 @@ class Engine:
     def kv_set_len(self, seq: int, n: int):
         N.check(self.lib.vv_kv_set_len(self.h, seq, n, self.s), "vv_kv_set_len")
 
+    def kv_delete(self, seq: int, pos: int):
+        """forget the committed entry at `pos` (the last entry takes its place)."""
+        N.check(self.lib.vv_kv_delete_slot(self.h, seq, pos, self.s), "vv_kv_delete_slot")
+
     def kv_commit(self, advance):
         a = N.i32(advance)
         N.check(self.lib.vv_kv_commit(self.h, N.iptr(a), self.s), "vv_kv_commit")

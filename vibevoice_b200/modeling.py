@@ -65,6 +65,40 @@ def sample_valid_tokens(logits_valid, valid_ids, generator=None) -> np.ndarray:
     return np.asarray(valid_ids, dtype=np.int64)[idx.numpy()]
 
 
+class _NegativeSlots:
+    """Integer bookkeeping of ONE row of the CFG-negative stream when `refresh_negative=False`, exactly as the reference keeps it
+    (modeling_vibevoice_inference.py:503-517, 594-624): a cache that only grows, an attention mask with one extra column for the incoming
+    token, and an "undo" of non-diffusing rows done by shifting mask and cache one slot to the right from `correct_cnt`.  The two shift
+    guards differ by one (:603 uses the mask length, :613 the cache length), so when the cache holds exactly correct_cnt + 2 entries the
+    mask moves and the cache does not: the entry at `correct_cnt` is hidden for good and the NEWEST entry stays.  The paged pool holds the
+    visible entries only (attention does not care about their order), so that case is one `vv_kv_delete_slot`."""
+
+    def __init__(self):
+        self.slots: List[int] = []          # physical slot -> entry id
+        self.mask: List[int] = [1]          # len(slots) + 1 columns
+        self.correct_cnt = 0
+        self.n = 0
+
+    def append(self) -> int:
+        e = self.n
+        self.n += 1
+        self.slots.append(e)
+        self.mask.append(1)
+        return e
+
+    def correct(self):
+        s, n, L = self.correct_cnt, len(self.slots), len(self.mask)
+        if s + 1 < L - 1:
+            self.mask[s + 1:] = self.mask[s:-1]
+        self.mask[s] = 0
+        if s + 1 < n - 1:
+            self.slots[s + 1:] = self.slots[s:-1]
+        self.correct_cnt += 1
+
+    def visible(self) -> List[int]:
+        return [self.slots[i] for i in range(len(self.slots)) if self.mask[i]]
+
+
 class WeightModule:
     """Stand-in for an `nn.Module` of the reference's module tree whose parameters live, packed, inside the engine:
     `model.model.prediction_head`, `.acoustic_connector`, `.semantic_connector`.  The reference's fine-tuning loader only ever calls
@@ -361,13 +395,6 @@ class VibeVoiceForConditionalGenerationInference:
         B = eng.B
         if b > B:
             raise ValueError("batch %d exceeds the engine's max_batch %d" % (b, B))
-        if not refresh_negative and b > 1:
-            # :503-517 + :590-624: with refresh_negative=False the reference forwards the negative stream on every step and undoes the
-            # step of non-diffusing rows only when ANOTHER row diffuses, through a cache shift whose guard keeps the newest entry and
-            # hides an older one in the common kv_len == correct_cnt + 2 case (oracle: NegativeStream).  A paged KV stream can drop its
-            # newest entry but not hide an older one, so only the single-prompt case -- where no correction ever happens -- is exact.
-            raise NotImplementedError("refresh_negative=False is supported for one prompt per call (the reference's batched behaviour "
-                                      "depends on its cache-shift guard; see DESIGN section 4)")
         tok = tokenizer
         start_id, end_id, diff_id, eos_id = tok.speech_start_id, tok.speech_end_id, tok.speech_diffusion_id, tok.eos_token_id
         if self._valid_ids(tok) != list(eng.valid_ids):
@@ -390,6 +417,8 @@ class VibeVoiceForConditionalGenerationInference:
         for s in range(2 * B):
             eng.kv_set_len(s, 0)
 
+        neg_state = [_NegativeSlots() for _ in range(B)]        # refresh_negative=False only
+        neg_pos: List[Dict[int, int]] = [dict() for _ in range(B)]   # entry id -> position in the pool
         finished = np.zeros(B, dtype=bool); finished[b:] = True
         reach_max = np.zeros(B, dtype=bool)
         seqs = [input_ids[i].tolist() for i in range(b)]
@@ -511,7 +540,34 @@ class VibeVoiceForConditionalGenerationInference:
                 for r in start_rows.tolist():
                     eng.kv_set_len(B + r, 0)                                                  # negative stream restarts at [<speech_start>]
             else:
-                eng.kv_commit(list(adv_pos) + [1] * B)       # :503-517: every step's input stays in the negative stream, no restart
+                # :503-517, 594-624: every step's input enters the negative stream; when some row diffuses, the rows that do not get
+                # their step undone by the reference's mask / cache shift.  Mirror its bookkeeping and bring the pool to the same set.
+                neg_adv = [0] * B
+                deletes = []
+                for r in range(b):
+                    if finished[r]:
+                        continue                                   # its stream is never read again
+                    st = neg_state[r]
+                    e_new = st.append()
+                    if diff_rows.size and not diff_mask[r]:
+                        st.correct()
+                    vis = st.visible()
+                    if len(set(vis)) != len(vis):
+                        raise NotImplementedError("the reference's cache shift left a duplicated visible entry; not representable")
+                    vis = set(vis)
+                    neg_adv[r] = 1 if e_new in vis else 0
+                    deletes += [(r, e) for e in neg_pos[r] if e not in vis]
+                    if neg_adv[r]:
+                        neg_pos[r][e_new] = len(neg_pos[r])
+                eng.kv_commit(list(adv_pos) + neg_adv)
+                for r, e_old in deletes:                           # an OLDER entry was hidden: the last entry takes its place in the pool
+                    p_old = neg_pos[r].pop(e_old)
+                    n_after = len(neg_pos[r])
+                    for e, ppos in neg_pos[r].items():
+                        if ppos == n_after:
+                            neg_pos[r][e] = p_old
+                            break
+                    eng.kv_delete(B + r, p_old)
             tl = [int(t) for t in next_tokens]
             eng.embed_tokens(tl + tl, eng.embeds)                                             # :569 (negative rows see the same input, :579-581)
             if diff_rows.size:
