@@ -171,6 +171,12 @@ class FakeEngine:
     def read_tokens(self):
         return self.tokens.numpy().copy(), self.logits.numpy().copy()
 
+    def stage_audio(self, rows):
+        return self.audio[list(rows)].clone()
+
+    def fetch_audio(self, ticket) -> torch.Tensor:
+        return ticket
+
     def lm_logits_full(self) -> torch.Tensor:
         return self.hidden[:self.B] @ O.lm_head_weight(self.w, self.config.decoder_config).float().T
 

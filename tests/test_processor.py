@@ -96,3 +96,13 @@ def test_matches_reference_processor():
     a2 = ref(text=SCRIPT, padding=True, return_tensors="pt")
     b2 = mine(text=SCRIPT, padding=True, return_tensors="pt")
     assert torch.equal(a2["input_ids"], b2["input_ids"]) and b2["speech_tensors"] is None
+
+
+def test_convert_to_16_bit_wav_matches_the_gradio_helper():
+    """`demo/gradio_demo.py:1058-1072`: int16 PCM, peak-normalised only when the signal leaves [-1, 1]."""
+    from vibevoice_b200.processor import convert_to_16_bit_wav
+    x = torch.tensor([[0.0, 0.5, -1.0, 0.25]])
+    assert convert_to_16_bit_wav(x).tolist() == [[0, 16383, -32767, 8191]]
+    y = np.array([0.0, 2.0, -4.0])
+    assert convert_to_16_bit_wav(y).tolist() == [0, 16383, -32767]
+    assert convert_to_16_bit_wav(x).dtype == np.int16

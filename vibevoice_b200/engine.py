@@ -254,6 +254,30 @@ class Engine:
             self.noise.copy_(self.noise_h, non_blocking=True)
             self.active.copy_(self.active_h, non_blocking=True)
 
+    # ---- zero-sync audio hand-off: frames leave through a pinned ring, one frame behind the loop -------------------
+    AUDIO_RING = 8
+
+    def stage_audio(self, rows):
+        """Enqueue an asynchronous copy of this frame's audio rows into the next slot of a pinned host ring (no synchronisation).
+        Returns a ticket for `fetch_audio`; the data is valid after ANY later synchronisation of the engine stream (the loop's
+        per-step token read-back already is one), so the streamer hand-off costs no sync of its own."""
+        if getattr(self, "_ring_h", None) is None:
+            self._ring_h = torch.zeros(self.AUDIO_RING, self.B, 3200, dtype=torch.float32).pin_memory()
+            self._ring_ev = [torch.cuda.Event() for _ in range(self.AUDIO_RING)]
+            self._ring_n = 0
+        slot = self._ring_n % self.AUDIO_RING
+        self._ring_n += 1
+        with torch.cuda.stream(self.stream):
+            self._ring_h[slot].copy_(self.audio, non_blocking=True)
+            self._ring_ev[slot].record(self.stream)
+        return slot, list(rows)
+
+    def fetch_audio(self, ticket) -> torch.Tensor:
+        """[n, 3200] CPU tensor of a staged frame (waits on that frame's event only -- already complete in the steady-state loop)."""
+        slot, rows = ticket
+        self._ring_ev[slot].synchronize()
+        return self._ring_h[slot][rows].clone()
+
     def frame_tail(self, cfg_scale: float):
         P = lambda t: C.c_void_p(t.data_ptr())
         N.check(self.lib.vv_frame_tail(self.h, P(self.hidden), P(self.noise), P(self.active), float(cfg_scale), P(self.latent),

@@ -479,9 +479,21 @@ class VibeVoiceForConditionalGenerationInference:
             from tqdm import tqdm
             iterator = (tqdm_class or tqdm)(iterator, desc="Generating", leave=False)
         step_done = False
+        pending_audio = None
+
+        def flush_audio():
+            """hand the previous frame's chunk to the streamer: its copy into the pinned ring was enqueued before the LM step whose
+            tokens the loop has just read back, so no extra synchronisation happens here"""
+            nonlocal pending_audio
+            if pending_audio is not None:
+                ticket, rows = pending_audio
+                pending_audio = None
+                audio_streamer.put(eng.fetch_audio(ticket).unsqueeze(1), torch.as_tensor(rows))
+
         for step in iterator:
             if stop_check_fn is not None and stop_check_fn():                               # :434-440
                 if audio_streamer is not None:
+                    flush_audio()
                     audio_streamer.end()
                 break
             if audio_streamer is not None and hasattr(audio_streamer, "finished_flags") and any(audio_streamer.finished_flags):
@@ -494,6 +506,8 @@ class VibeVoiceForConditionalGenerationInference:
             if step > 0:
                 eng.lm_decode()                                                             # :480-482 (+ speculative negative rows)
             toks_dev, logits_valid = eng.read_tokens()
+            if audio_streamer is not None:
+                flush_audio()
             next_tokens = toks_dev.astype(np.int64).copy()
             if full_vocab_procs:                                                              # :488-498 on full-vocabulary scores
                 scores = eng.lm_logits_full()[:b].clone()
@@ -583,10 +597,10 @@ class VibeVoiceForConditionalGenerationInference:
                     chunk = eng.audio[diff_rows.tolist()].clone()                              # [n, 3200]
                 for i, r in enumerate(diff_rows.tolist()):
                     audio_chunks[r].append(chunk[i:i + 1])                                    # :646-650
-                if audio_streamer is not None:
-                    eng.sync()
-                    audio_streamer.put(chunk.unsqueeze(1), torch.as_tensor(diff_rows))         # :653-655
+                if audio_streamer is not None:                                                 # :653-655, one frame behind (no sync here):
+                    pending_audio = (eng.stage_audio(diff_rows.tolist()), diff_rows.copy())   # pinned ring, delivered after the next read-back
         if audio_streamer is not None:
+            flush_audio()
             audio_streamer.end()                                                              # :677-678
         eng.sync()
         outs: List[Optional[torch.Tensor]] = []

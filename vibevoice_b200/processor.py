@@ -73,6 +73,17 @@ def load_wav_24k(path: str, target_sr: int = 24000) -> np.ndarray:
     return x
 
 
+def convert_to_16_bit_wav(data) -> np.ndarray:
+    """`demo/gradio_demo.py:1058-1072`: tensor / array -> int16 PCM, peak-normalised only when the signal exceeds [-1, 1]."""
+    if torch.is_tensor(data):
+        data = data.detach().float().cpu().numpy()
+    data = np.array(data)
+    peak = np.max(np.abs(data)) if data.size else 0.0
+    if peak > 1.0:
+        data = data / peak
+    return (data * 32767).astype(np.int16)
+
+
 class VibeVoiceProcessor:
     def __init__(self, tokenizer=None, audio_processor=None, speech_tok_compress_ratio: int = 3200, db_normalize: bool = True, **kwargs):
         self.tokenizer = tokenizer
