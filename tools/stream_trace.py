@@ -48,6 +48,12 @@ if a.prog.startswith("lm"):
     for _ in range(5):
         eng.lm_decode()
         eng.kv_commit([1] * (2 * B))
+elif a.prog.startswith("decf"):
+    for _ in range(5):
+        eng.codec_decode()
+elif a.prog.startswith("encb"):
+    for _ in range(5):
+        eng.semantic_encode()
 else:
     for _ in range(5):
         eng.diffusion_sample(1.3)

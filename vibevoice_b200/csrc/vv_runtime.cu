@@ -422,6 +422,7 @@ static int finish_stream(StreamBuilder& b, vv_ctx::StreamProg* pr) {
   const int G = c->sm_count;
   int b_bytes = 2048;
   for (const SOp& o : b.ops) {
+    if (o.kind == SK_MIX && (o.cod.T_out > 8 || o.K % 4 || o.K > 4096)) return fail(VV_ERR_INVALID, "stream: mixer stage handles T <= 8, C <= 4096");
     if (o.kind == SK_ATTN) b_bytes = std::max(b_bytes, 32768);        // Q tile, new K/V row and the warp-merge buffers live in the operand region
     if (o.kind != SK_GEMV) continue;
     const long long KB = (o.K + 63) / 64, R = (o.N + 127) / 128, U = R * KB;
@@ -431,10 +432,6 @@ static int finish_stream(StreamBuilder& b, vv_ctx::StreamProg* pr) {
     const long long segs = (per + KB - 1) / KB + 1;
     if (segs > ST_MAXSEG || segs * o.nB > 512) return fail(VV_ERR_INVALID, "stream: stage [%d x %d] needs %lld accumulators per CTA", o.N, o.K, segs);
     if (o.store && KB != 1) return fail(VV_ERR_INVALID, "stream: store epilogue needs K <= 64");
-    if (o.pro == SP_MIXER) {
-      if (o.M > 8 || o.K % 4) return fail(VV_ERR_INVALID, "stream: mixer prologue handles at most 8 rows (got %d)", o.M);
-      b_bytes = std::max<long long>(b_bytes, ((count * o.nB * 128 + 1023) & ~1023ll) + (long long)o.M * o.K * 4);
-    }
     if (o.pro == SP_WINDOW && (o.cod.cin % 8)) return fail(VV_ERR_INVALID, "stream: window prologue needs a channel count that is a multiple of 8");
     if (o.pro == SP_COMBINE) {
       const long long nh = count / 2 + 2;
@@ -1748,7 +1745,7 @@ struct ScopedMinRows {     // the codec stages may use a different GEMV/GEMM row
 // buffer's last reader.
 static bool codec_stream_stage(const vv_ctx* c, const Codec& k, int i) {
   const long long rows = (long long)c->d.max_batch * k.T[i];
-  return (c->use_stream & 8) && rows <= 8 && rows * k.C[i] * 4 <= 65536;
+  return (c->use_stream & 8) && k.T[i] <= 8 && rows <= 32;
 }
 static long long codec_x_floats(const vv_ctx* c) { return (long long)c->d.max_batch * 8192; }
 static long long codec_u_floats(const vv_ctx* c) { return (long long)c->d.max_batch * 32768; }
@@ -1772,12 +1769,16 @@ static int stage_ops(StreamBuilder& b, vv_ctx* c, CodecBufs& cb, const std::vect
     const Block& blk = blocks[j];
     const int C = blk.C, M = B * T;
     SOp* o;
-    RET(b.gemv(blk.w1, blk.b1, cb.X[cb.cur], C, cb.U[cb.ub], 4 * C, M, 4 * C, C, true, &o));
-    o->pro = SP_MIXER;
-    SCodec& w = o->cod;
-    memset(&w, 0, sizeof w);
-    w.hist = blk.hist; w.next = blk.next; w.T_out = T; w.norm_w = blk.norm_w; w.dw_w = blk.dw_w; w.dw_b = blk.dw_b; w.gamma = blk.gamma;
-    w.ffn_norm_w = blk.ffn_norm_w; w.x1_out = cb.X[cb.cur ^ 1]; w.eps = c->d.codec_eps;
+    {                                                          // mixer stage: x (X[cur]) -> x1 (X[cur^1]) + next history, channels over CTAs
+      SOp& mx = b.push(SK_MIX, true);
+      mx.M = M; mx.K = C; mx.x = cb.X[cb.cur]; mx.ldx = C;
+      SCodec& w = mx.cod;
+      memset(&w, 0, sizeof w);
+      w.hist = blk.hist; w.next = blk.next; w.T_out = T; w.norm_w = blk.norm_w; w.dw_w = blk.dw_w; w.dw_b = blk.dw_b; w.gamma = blk.gamma;
+      w.x1_out = cb.X[cb.cur ^ 1]; w.eps = c->d.codec_eps;
+    }
+    RET(b.gemv(blk.w1, blk.b1, cb.X[cb.cur ^ 1], C, cb.U[cb.ub], 4 * C, M, 4 * C, C, true, &o));
+    o->pro = SP_RMSNORM; o->pro_w = blk.ffn_norm_w; o->pro_eps = c->d.codec_eps;
     o->init_dst = cb.U[cb.ub ^ 1]; o->init_n = codec_u_floats(c);          // hidden-sum buffer of the NEXT block (its reader finished two stages ago)
     RET(b.gemv(blk.w2, blk.b2, cb.U[cb.ub], 4 * C, cb.X[cb.cur ^ 1], C, M, C, 4 * C, true, &o));
     o->pro = SP_GELU; o->alpha_kind = SA_GAMMA; o->alpha = blk.ffn_gamma;

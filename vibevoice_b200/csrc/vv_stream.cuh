@@ -87,7 +87,7 @@ constexpr int ST_MAXSEG = 8;             // (row tile, k range) segments a CTA m
 constexpr int ST_MAX_STAGES = 12;
 constexpr int ST_BAR_REP = 0;
 
-enum SKind { SK_GEMV = 0, SK_NOP = 1, SK_ATTN = 2 };
+enum SKind { SK_GEMV = 0, SK_NOP = 1, SK_ATTN = 2, SK_MIX = 3 };
 enum SPro { SP_NONE = 0, SP_RMSNORM = 1, SP_ADALN = 2, SP_SWIGLU = 3, SP_GELU = 4, SP_DPM = 5, SP_SILU = 6, SP_COMBINE = 7, SP_WINDOW = 8, SP_MIXER = 9 };
 enum SAlpha { SA_ONE = 0, SA_GATE = 1 /* alpha[m][n], row stride lda */, SA_GAMMA = 2 /* alpha[n] */ };
 
@@ -123,10 +123,10 @@ struct SAtt {
 //  SP_WINDOW  activation row (b, t) = rows [t*stride, t*stride + k) of the causal window [hist[b] (ctx rows) ; alpha*src[b]+beta (T_in rows)],
 //             each row `cin` wide, flattened (K = k * cin): strided / transposed convolutions as window GEMVs.  The CTA that owns unit 0
 //             writes the next history (the window's last ctx rows) into `next`.
-//  SP_MIXER   the whole first half of a Block1D in the prologue of its first FFN linear, for rows (b, t), t < T, C = K channels:
+//  SK_MIX     (a stage of its own, no linear) the first half of a Block1D for rows (b, t), t < T, C = K channels, channels dealt out to CTAs:
 //             xn = RMSNorm(x) * norm_w;  x1 = x + gamma * (dw_b + sum_j dw_w[j] * win[t + j]),  win = [hist[b] (6 normalised rows) ; xn];
-//             B operand = RMSNorm(x1) * ffn_norm_w.  Every CTA recomputes it (it needs full-row statistics of x1 anyway; M * C <= 16 K
-//             values), the owner of unit 0 publishes x1 (the residual base the second FFN linear accumulates into) and the next history.
+//             writes x1 (the residual base both FFN linears work on) and the next history (last 6 rows of the window).
+//             (Tried first as the prologue of the FFN linear, recomputed by every CTA: 14-30 us per block, profiles/r02_stream_trace_codec_1.txt.)
 struct SCodec {
   const float* hist; float* next;        // [B][ctx][cin] / [B][6][C]
   const float* src;                      // SP_WINDOW: [B][T_in][cin]
@@ -509,6 +509,71 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         sincosf((float)s_kvlen[m] * op.att.inv_freq[wt], &sn, &cs);
         *reinterpret_cast<float2*>(op.att.rope_cs + ((size_t)m * (HD / 2) + wt) * 2) = make_float2(cs, sn);
       }
+      if (op.kind == SK_MIX) {
+        const SCodec& w = op.cod;
+        const int C = op.K, M = op.M, T = w.T_out, Bn = M / T;
+        // full-row statistics of x: rows in pairs, <= 16 float4 per thread in flight
+        const int K4 = C >> 2;
+        for (int m0 = 0; m0 < M; m0 += 2) {
+          float4 sv[2][8];
+#pragma unroll
+          for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int q = wt + i * ST_WORKERS;
+              sv[r][i] = (m0 + r < M && q < K4) ? ldcg4(op.x + (long long)(m0 + r) * op.ldx + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          float ss[2] = {0.f, 0.f};
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ss[r] += sv[r][i].x * sv[r][i].x + sv[r][i].y * sv[r][i].y + sv[r][i].z * sv[r][i].z + sv[r][i].w * sv[r][i].w;
+            ss[r] = warp_sum(ss[r]);
+            if (lane == 0) s_red[ww][(m0 & 6) + r] = ss[r];
+          }
+          if (((m0 & 6) == 6) || m0 + 2 >= M) {
+            worker_sync();
+            const int base = m0 & ~7;
+            if (wt < 8 && base + wt < M) s_inv[base + wt] = rsqrtf((s_red[0][wt] + s_red[1][wt] + s_red[2][wt] + s_red[3][wt]) / (float)C + w.eps);
+            worker_sync();
+          }
+        }
+        // this CTA's channels, one (sample, channel) item per thread: every operand requested before the first is used
+        const int c0 = (int)((unsigned)C * blockIdx.x / G), c1 = (int)((unsigned)C * (blockIdx.x + 1u) / G), nc = c1 - c0;
+        for (int it = wt; it < nc * Bn; it += ST_WORKERS) {
+          const int b = it / nc, c = c0 + (it - b * nc);
+          float hv[6], tap[7], xr[8];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) hv[j] = ldcg1(w.hist + ((size_t)b * 6 + j) * C + c);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) xr[t] = t < T ? ldcg1(op.x + (long long)(b * T + t) * op.ldx + c) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 7; ++j) tap[j] = w.dw_w[(size_t)j * C + c];
+          const float nw = w.norm_w[c], gm = w.gamma[c], db = w.dw_b[c];
+          float win[14];                                   // [hist (6) ; xn (T <= 8)]
+#pragma unroll
+          for (int j = 0; j < 6; ++j) win[j] = hv[j];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) win[6 + t] = t < T ? xr[t] * s_inv[b * T + t] * nw : 0.f;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {                      // next history = window rows T .. T+5
+            float val = 0.f;
+#pragma unroll
+            for (int q = 0; q < 14; ++q) if (q == T + r) val = win[q];
+            w.next[((size_t)b * 6 + r) * C + c] = val;
+          }
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            if (t < T) {
+              float acc = db;
+#pragma unroll
+              for (int j = 0; j < 7; ++j) acc = fmaf(tap[j], win[t + j], acc);
+              w.x1_out[(size_t)(b * T + t) * C + c] = xr[t] + gm * acc;
+            }
+          }
+        }
+        break;
+      }
       if (op.kind == SK_ATTN) {
         // =========================== decode attention over the ring (see SAtt) ===========================
         const SAtt& a = op.att;
@@ -683,7 +748,6 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       //  iteration, 4.4 us per AdaLN stage; every load below is issued before the first value is consumed)
       const int total = M * count * 8;                     // 16-byte chunks (8 consecutive k of one activation row) to stage
       const bool norm = (pro == SP_RMSNORM || pro == SP_ADALN);
-      float* s_mix = reinterpret_cast<float*>(breg + ((count * nB * 128 + 1023) & ~1023));   // SP_MIXER: x1 [M][C] behind the B operand
       // SP_COMBINE scratch behind the B operand: [M][NH][G] merge weights w_p / sum_p w_p l_p | group partial sums | merged[M][count][64]
       const int cmb_base = (count * nB * 128 + 1023) & ~1023;
       float* s_w = reinterpret_cast<float*>(breg + cmb_base);
@@ -700,7 +764,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       auto chunk_load = [&](int c, float4 (&in)[8]) {       // raw operands of one chunk (nothing is consumed here)
         int m, jloc, ch, k;
         chunk_coord(c, m, jloc, ch, k);
-        if (c >= total || k >= K || pro == SP_DPM || pro == SP_COMBINE || pro == SP_MIXER) return;
+        if (c >= total || k >= K || pro == SP_DPM || pro == SP_COMBINE) return;
         if (pro == SP_WINDOW) {
           const SCodec& w = op.cod;
           const int b = m / w.T_out, t = m - b * w.T_out, j = k / w.cin, ci = k - j * w.cin, r = t * w.stride + j;
@@ -749,12 +813,6 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
             for (int jj = 0; jj < 8; ++jj) v[jj] = v[jj] * w.alpha + w.beta;
           }
           (void)b;
-        } else if (pro == SP_MIXER) {
-          const float* xr = s_mix + (size_t)m * K + k;
-          const float inv = s_inv[m];
-          const float4 w0 = *reinterpret_cast<const float4*>(op.cod.ffn_norm_w + k), w1 = *reinterpret_cast<const float4*>(op.cod.ffn_norm_w + k + 4);
-          v[0] = xr[0] * inv * w0.x; v[1] = xr[1] * inv * w0.y; v[2] = xr[2] * inv * w0.z; v[3] = xr[3] * inv * w0.w;
-          v[4] = xr[4] * inv * w1.x; v[5] = xr[5] * inv * w1.y; v[6] = xr[6] * inv * w1.z; v[7] = xr[7] * inv * w1.w;
         } else if (pro == SP_COMBINE) {
           const float* cv = reinterpret_cast<const float*>(breg + cmb_off + cmb_part) + ((size_t)(m * count + jloc) * 64 + ch * 8);
 #pragma unroll
@@ -886,84 +944,6 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
           w.next[i] = r < w.ctx ? ldcg1(w.hist + ((size_t)b * w.ctx + r) * w.cin + ci)
                                 : ldcg1(w.src + ((size_t)b * w.T_in + (r - w.ctx)) * w.cin + ci) * w.alpha + w.beta;
         }
-      }
-      if (pro == SP_MIXER) {
-        const SCodec& w = op.cod;
-        const int C = K, T = w.T_out;                                  // M = B * T rows, M <= 8 (host-checked)
-        // pass A: raw rows into shared memory + sum of squares -> inv1
-        float ss[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ss[j] = 0.f;
-        for (int c4 = wt; c4 < (C >> 2); c4 += ST_WORKERS) {
-          float4 xv[8];
-#pragma unroll
-          for (int mm = 0; mm < 8; ++mm) xv[mm] = mm < M ? ldcg4(op.x + (long long)mm * op.ldx + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int mm = 0; mm < 8; ++mm) {
-            if (mm < M) {
-              *reinterpret_cast<float4*>(s_mix + (size_t)mm * C + 4 * c4) = xv[mm];
-              ss[mm] += xv[mm].x * xv[mm].x + xv[mm].y * xv[mm].y + xv[mm].z * xv[mm].z + xv[mm].w * xv[mm].w;
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { ss[j] = warp_sum(ss[j]); if (lane == 0) s_red[ww][j] = ss[j]; }
-        worker_sync();
-        if (wt < 8) s_inv[8 + wt] = rsqrtf((s_red[0][wt] + s_red[1][wt] + s_red[2][wt] + s_red[3][wt]) / (float)C + w.eps);   // inv1
-        worker_sync();
-        // pass B: thread-private channels; rows of a sample in DESCENDING time so x1 can overwrite the raw row in place
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ss[j] = 0.f;
-        const int Bn = M / T;
-        for (int c = wt; c < C; c += ST_WORKERS) {
-          const float nw = w.norm_w[c], gm = w.gamma[c], db = w.dw_b[c];
-          float tap[7];
-#pragma unroll
-          for (int j = 0; j < 7; ++j) tap[j] = w.dw_w[j * C + c];
-          for (int b = 0; b < Bn; ++b) {
-            float hv[6];
-#pragma unroll
-            for (int j = 0; j < 6; ++j) hv[j] = ldcg1(w.hist + ((size_t)b * 6 + j) * C + c);
-            auto win = [&](int r) -> float {                             // window row r of sample b, channel c
-              if (r < 6) return hv[r < 0 ? 0 : r];
-              const int mm = b * T + (r - 6);
-              return s_mix[(size_t)mm * C + c] * s_inv[8 + mm] * nw;
-            };
-            if (u0 == 0) {
-#pragma unroll
-              for (int r = 0; r < 6; ++r) {
-                const int rr = T + r;
-                float val;
-                if (rr < 6) { val = hv[0]; for (int q = 1; q < 6; ++q) if (q == rr) val = hv[q]; }
-                else val = s_mix[(size_t)(b * T + rr - 6) * C + c] * s_inv[8 + b * T + rr - 6] * nw;
-                w.next[((size_t)b * 6 + r) * C + c] = val;
-              }
-            }
-            for (int t = T - 1; t >= 0; --t) {
-              float acc = db;
-#pragma unroll
-              for (int j = 0; j < 7; ++j) {
-                const int r = t + j;
-                float wv;
-                if (r < 6) { wv = hv[0]; for (int q = 1; q < 6; ++q) if (q == r) wv = hv[q]; }
-                else wv = s_mix[(size_t)(b * T + r - 6) * C + c] * s_inv[8 + b * T + r - 6] * nw;
-                acc = fmaf(tap[j], wv, acc);
-              }
-              const int mm = b * T + t;
-              const float x1 = s_mix[(size_t)mm * C + c] + gm * acc;
-              s_mix[(size_t)mm * C + c] = x1;
-              if (u0 == 0) w.x1_out[(size_t)mm * C + c] = x1;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) if (j == mm) ss[j] = fmaf(x1, x1, ss[j]);
-            }
-          }
-        }
-        worker_sync();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { ss[j] = warp_sum(ss[j]); if (lane == 0) s_red[ww][j] = ss[j]; }
-        worker_sync();
-        if (wt < 8) s_inv[wt] = rsqrtf((s_red[0][wt] + s_red[1][wt] + s_red[2][wt] + s_red[3][wt]) / (float)C + w.eps);        // inv2
-        worker_sync();
       }
       float4 in0[8], in1[8];
       chunk_load(wt, in0);                                  // first two chunks of this thread: in flight during the statistics
