@@ -35,6 +35,9 @@ import numpy as np
 import torch
 
 AUDIO_S_PER_FRAME = 3200.0 / 24000.0
+# DRAM traffic of one frame / one LM step from an ncu pass (dram__bytes_read.sum + dram__bytes_write.sum over every kernel of the frame),
+# see profiles/ (filled in by the profiling run of this round; None = not captured for that model)
+TRAFFIC_NOTE = {}
 
 
 def parse():
@@ -52,6 +55,7 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=None, help="frames in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-7b", action="store_true", help="skip the VibeVoice-7B sub-configs appended to the 1.5B line")
     return ap.parse_args()
 
 
@@ -227,6 +231,77 @@ def config_dict(args, cfg, L0, F):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+def run_extra_config(tag, preset, B, L0, F, args, rank, world, local, dev, peak):
+    """Steady-state loop of another BASELINE configuration (same method as `value`): 1 warm-up + 2 timed steps of F frames."""
+    import torch.distributed as dist
+    from vibevoice_b200.configuration import preset_config
+    from vibevoice_b200.modeling import VibeVoiceForConditionalGenerationInference
+    from vibevoice_b200.synth import SynthTokenizer, iter_synth_state_dict_fast
+    cfg = preset_config(preset)
+    tok = SynthTokenizer(cfg.decoder_config.vocab_size)
+    model = VibeVoiceForConditionalGenerationInference(cfg, tok, max_batch=B, device=local, torch_prefill=True)
+    parts = ("lm", "head", "acoustic_decoder", "semantic", "connectors", "lm_head")
+    model.load_state_dict(iter_synth_state_dict_fast(cfg, 4321 + rank, device=dev, parts=parts), tok)
+    model.set_ddpm_inference_steps(args.diffusion_steps)
+    eng = model.engine
+    wb = eng.weight_bytes()
+    eng.kv_init(B * (L0 + F + 8) + B * (F + 8))
+    eng.set_diffusion_steps(args.diffusion_steps)
+    g = torch.Generator().manual_seed(200 + rank)
+    ids = torch.randint(0, 151643, (B, L0), generator=g)
+    ids[:, -1] = tok.speech_start_id
+    embw = model._lm_sd["model.language_model.embed_tokens.weight"]
+    with torch.cuda.stream(eng.stream):
+        for r in range(B):
+            model._prefill.run(eng, r, embw[ids[r].to(dev)])
+    eng.sync()
+    noise_tab = torch.randn(F, B, 64, device=dev)
+    ones = [1] * (2 * B)
+
+    def step():
+        eng.codec_state_reset()
+        for r in range(B):
+            eng.kv_set_len(r, L0); eng.kv_set_len(B + r, 0)
+        eng.embed_tokens([tok.speech_start_id] * (2 * B), eng.embeds)
+        with torch.cuda.stream(eng.stream):
+            eng.active.fill_(1)
+        for f in range(F):
+            eng.lm_decode()
+            eng.kv_commit(ones)
+            with torch.cuda.stream(eng.stream):
+                eng.noise.copy_(noise_tab[f])
+            eng.frame_tail(args.cfg_scale)
+    step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    K = 2
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(eng.stream)
+    for _ in range(K):
+        step()
+    e1.record(eng.stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_frame = ms / (K * F)
+    abytes = algorithmic_bytes_per_frame(wb, cfg, L0 + (F - 1) / 2.0 + 1, (F - 1) / 2.0 + 1, args.diffusion_steps, B)
+    ach = abytes / (ms_frame * 1e-3) / 1e9
+    out = {"config": tag, "model": preset, "batch_per_gpu": B, "prompt_len": L0, "frames_per_step": F, "steps": K, "warmup": 1,
+           "value": round(K * F * B * world * AUDIO_S_PER_FRAME / (ms / 1e3), 3), "unit": "audio-s/s", "n_gpus": world,
+           "ms_per_frame": round(ms_frame, 4), "algorithmic_bytes_per_frame": int(abytes),
+           "roofline": {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4)}}
+    eng.close()
+    del model, eng
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args):
     rank, world, local = dist_env()
     import torch.distributed as dist
@@ -322,40 +397,51 @@ def run_b200(args):
                 "unit_of_work": "one speech frame = lm_decode graph + frame_tail graph",
                 "algorithmic_bytes_per_frame": int(abytes), "ms_per_frame": round(ms_frame, 4)}
 
-    # ---------------- dominant kernel alone (gemv_kernel<MB>: ~55% of kernel time, profiles/): algorithmic bytes / event time ----
-    def kernel_roofline():
-        import ctypes as C
-        from vibevoice_b200 import _native as NV
+    # ---------------- per-segment rooflines at this context (each C-ABI entry point alone, CUDA events on the engine stream) ----------------
+    def segment_rooflines():
         dc = cfg.decoder_config
-        N_, K_ = 2 * dc.intermediate_size, dc.hidden_size           # LM gate/up projection, the largest single weight stream per layer
-        M_ = 2 * B
-        ncopy = max(2, int(300e6 // (N_ * K_ * 2)) + 1)               # rotate through > L2-size of weights
-        Wt = torch.empty(ncopy, N_, K_, device=dev, dtype=torch.bfloat16).normal_(0, 0.02)
-        xt = torch.randn(M_, K_, device=dev)
-        nw = torch.rand(K_, device=dev) + 0.5
-        yt = torch.zeros(M_, N_ // 2, device=dev)
-        P = lambda t: C.c_void_p(t.data_ptr())
+        kvB = dc.num_hidden_layers * 2 * dc.num_key_value_heads * dc.head_dim * 2
+        for r in range(B):
+            eng.kv_set_len(r, L0); eng.kv_set_len(B + r, 0)
+        eng.embed_tokens([tok.speech_start_id] * (2 * B), eng.embeds)
 
-        def run(n):
-            for i in range(n):
-                NV.check(eng.lib.vv_debug_gemv(eng.h, P(Wt[i % ncopy]), None, P(xt), P(yt), M_, N_, K_, NV.PRO_RMSNORM, P(nw), 1e-6,
-                                               NV.EPI_SWIGLU, eng.s))
-        run(20)
-        eng.sync()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(eng.stream)
-        run(200)
-        e1.record(eng.stream)
-        eng.sync()
-        us = e0.elapsed_time(e1) * 1e3 / 200
-        ach = N_ * K_ * 2 / us / 1e3
-        return {"kernel": "gemv_kernel<%d> (LM gate/up, N=%d K=%d, fused RMSNorm + SwiGLU)" % (2 if M_ <= 2 else (4 if M_ <= 4 else 8), N_, K_),
-                "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                "algorithmic_bytes_per_launch": N_ * K_ * 2, "us_per_launch": round(us, 2),
-                "traffic": "55.11 MB dram read for 55.05 MB algorithmic (ncu --set full, profiles/r01_prof_gemv_raw.csv)" if args.model == "1.5b" else None,
-                "note": "back-to-back launches, weights rotated through >300 MB so L2 cannot serve them"}
-    roofline["dominant_kernel"] = kernel_roofline()
-    log("dominant-kernel roofline done")
+        def lm():
+            eng.lm_decode()
+            eng.kv_commit(ones)
+        segs = [("lm_decode", lm, wb["lm"] + B * kvB * (L0 + 8)),
+                ("diffusion_sample", lambda: eng.diffusion_sample(args.cfg_scale), args.diffusion_steps * wb["head_step"] + wb["cond_proj"]),
+                ("codec_decode", eng.codec_decode, wb["decoder"]),
+                ("semantic_encode", eng.semantic_encode, wb["semantic"]),
+                ("connect", eng.connect, wb["connectors"])]
+        out = {}
+        for name, fn, nbytes in segs:
+            for _ in range(3):
+                fn()
+            eng.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 16
+            e0.record(eng.stream)
+            for _ in range(n):
+                fn()
+            e1.record(eng.stream)
+            eng.sync()
+            us = e0.elapsed_time(e1) * 1e3 / n
+            out[name] = {"us": round(us, 1), "algorithmic_bytes": int(nbytes), "achieved_GBps": round(nbytes / us / 1e3, 1),
+                         "frac": round(nbytes / us / 1e3 / peak, 4)}
+        return out
+    segs = segment_rooflines()
+    roofline["segments"] = segs
+    roofline["traffic"] = TRAFFIC_NOTE.get(args.model)
+    lm_seg = segs["lm_decode"]
+    roofline["dominant_kernel"] = {
+        "kernel": "stream_kernel (vv_stream.cuh): the whole %d-layer decoder stack of one step as ONE persistent launch -- tcgen05.mma + TMEM, "
+                  "weight tiles and K/V pages by TMA through one ring" % cfg.decoder_config.num_hidden_layers,
+        "bound": "hbm", "achieved": lm_seg["achieved_GBps"], "peak": peak, "unit": "GB/s", "frac": lm_seg["frac"],
+        "algorithmic_bytes_per_launch": lm_seg["algorithmic_bytes"], "us_per_launch": lm_seg["us"],
+        "traffic": TRAFFIC_NOTE.get(args.model + ":lm"),
+        "note": "vv_lm_decode timed alone (copy-in, the stream launch, final norm, 4-row lm_head); weights + KV of one step >> L2"}
+    head_step_us = segs["diffusion_sample"]["us"] / args.diffusion_steps
+    log("segment rooflines done")
 
     # ---------------- e2e: public generate() with host buffers ----------------
     e2e = None
@@ -412,11 +498,27 @@ def run_b200(args):
         log("cpu sample done")
         cpu = {"value": round(cpu["value"], 4), "unit": "audio-s/s", "cores": cpu["cores"], "kind": "port", "sample": cpu["sample"]}
 
+    # ---------------- BASELINE configs #3 / #4 on the same clock: VibeVoice-7B, short frame counts (the headline stays on config #2) ----
+    extra_configs = []
+    if args.model == "1.5b" and not args.no_7b:
+        model.engine.close()
+        del model, eng
+        torch.cuda.empty_cache()
+        for (tag, b7, L7, F7) in (("7b ctx 30720, 1 prompt/GPU (BASELINE config #3 shape)", 1, 30720, 48),
+                                  ("7b 4 prompts/GPU, 256-token prompts (BASELINE config #4 per-GPU share)", 4, 256, 48)):
+            try:
+                extra_configs.append(run_extra_config(tag, "7b", b7, L7, F7, args, rank, world, local, dev, peak))
+                log("extra config done: %s" % tag)
+            except Exception as e:  # a sub-config must never take the headline line down with it
+                extra_configs.append({"config": tag, "error": "%s: %s" % (type(e).__name__, str(e)[:300])})
+
     if rank == 0:
         line = {"metric": "audio_seconds_per_second", "value": round(value, 3), "unit": "audio-s/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": round(ms_value / K, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic", "config": config_dict(args, cfg, L0, F), "rtf": round(1.0 / (value / world), 5),
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk,
+                "roofline": roofline, "diffusion_head_step_us": round(head_step_us, 2),
+                "diffusion_head_step_floor_us": round(wb["head_step"] / peak / 1e3, 2),
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "configs": extra_configs,
                 "weight_bytes": wb, "setup_s": round(time.time() - t_setup, 1)}
         print(json.dumps(line), flush=True)
     if world > 1:
