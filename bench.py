@@ -46,7 +46,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="1.5b", choices=["1.5b", "7b", "1.5b-l2", "tiny", "small"])
+    ap.add_argument("--model", default="1.5b", choices=["1.5b", "7b", "1.5b-l2", "tiny", "small", "streaming-0.5b"])
+    ap.add_argument("--runs", type=int, default=100, help="streaming-0.5b: generate() calls the latency percentiles are taken over")
     ap.add_argument("--prompt-len", type=int, default=None)
     ap.add_argument("--frames", type=int, default=None, help="speech frames generated per step")
     ap.add_argument("--diffusion-steps", type=int, default=30)
@@ -525,8 +526,88 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------------------------
+def run_streaming_latency(args):
+    """BASELINE config #5: VibeVoice-Streaming-0.5B, 8K-token cached prompt, 5 diffusion steps, cfg 1.5, text / speech windows 5 / 6 --
+    p50 of the time from generate() entry to the first [1, 3200] chunk handed to AudioStreamer.put, over `--runs` calls
+    (demo/streaming_inference_from_file.py:170, 291: the prompt state comes from a cached `all_prefilled_outputs`, as here)."""
+    from types import SimpleNamespace
+    from vibevoice_b200 import streaming as S
+    from vibevoice_b200.configuration import preset_config
+    from vibevoice_b200.streamer import AudioStreamer
+    from vibevoice_b200.synth import iter_synth_state_dict_fast
+    dev = torch.device("cuda", 0)
+    cfg = preset_config("streaming-0.5b")
+    dc = cfg.decoder_config
+    H, tts_layers = dc.hidden_size, 20
+    low = dc.num_hidden_layers - tts_layers
+    L0 = args.prompt_len or 8192
+    steps = 5 if args.diffusion_steps == 30 else args.diffusion_steps
+    g = torch.Generator(device=dev).manual_seed(7)
+
+    def items():
+        yield from iter_synth_state_dict_fast(cfg, 1234, device=dev, parts=("lm", "head", "acoustic_decoder", "connectors"))
+        yield "model.tts_input_types.weight", torch.randn(2, H, device=dev, generator=g) * 0.05
+        yield "tts_eos_classifier.fc1.weight", torch.randn(H, H, device=dev, generator=g) * 0.05
+        yield "tts_eos_classifier.fc1.bias", torch.zeros(H, device=dev)
+        yield "tts_eos_classifier.fc2.weight", torch.randn(1, H, device=dev, generator=g) * 0.05
+        yield "tts_eos_classifier.fc2.bias", torch.full((1,), -8.0, device=dev)       # never stops inside the measured window
+    t_setup = time.time()
+    m = S.VibeVoiceStreamingForConditionalGenerationInference(cfg, tts_backbone_num_hidden_layers=tts_layers)
+    m.load_state_dict(items())
+    m.set_ddpm_inference_steps(steps)
+    eng = m.engine
+
+    def cache(n_layers, L):          # the reference's cached-prompt format: per-layer (key, value) [1, kv_heads, L, head_dim], bf16, rotated keys
+        return tuple((torch.randn(1, dc.num_key_value_heads, L, dc.head_dim, device=dev, generator=g).to(torch.bfloat16) * 0.5,
+                      torch.randn(1, dc.num_key_value_heads, L, dc.head_dim, device=dev, generator=g).to(torch.bfloat16) * 0.5) for _ in range(n_layers))
+    out = lambda n, L: SimpleNamespace(past_key_values=cache(n, L), last_hidden_state=torch.randn(1, L, H, device=dev, generator=g) * 0.1)
+    prefilled = {"lm": out(low, L0), "tts_lm": out(tts_layers, L0), "neg_lm": out(low, 1), "neg_tts_lm": out(tts_layers, 1)}
+    prompt = torch.randint(0, 150000, (L0,))
+    text = torch.randint(0, 150000, (40,))
+    log("streaming model ready (%d-token cached prompt)" % L0)
+
+    class FirstChunk(AudioStreamer):
+        def __init__(self):
+            super().__init__(batch_size=1)
+            self.t_first = None
+
+        def put(self, audio_chunks, sample_indices):
+            if self.t_first is None:
+                self.t_first = time.perf_counter()
+            super().put(audio_chunks, sample_indices)
+    lat = []
+    clocks = ClockSampler(0)
+    for it in range(args.warmup + args.runs):
+        if it == args.warmup:
+            clocks.start()
+        st = FirstChunk()
+        torch.manual_seed(it)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        res = m.generate(input_ids=prompt[None], tts_lm_input_ids=prompt[None], tts_text_ids=text[None], neg_text_input_id=151655,
+                         cfg_scale=1.5 if args.cfg_scale == 1.3 else args.cfg_scale, max_new_tokens=5 + 6, all_prefilled_outputs=prefilled,
+                         audio_streamer=st)
+        if it >= args.warmup:
+            lat.append((st.t_first - t0) * 1e3)
+        assert res.speech_outputs[0] is not None and res.speech_outputs[0].shape[-1] >= 3200
+    clk = clocks.stop()
+    lat = np.asarray(lat)
+    line = {"metric": "first_audio_latency_ms_p50", "value": round(float(np.percentile(lat, 50)), 3), "unit": "ms", "n_gpus": 1, "steps": args.runs,
+            "warmup": args.warmup, "ms_per_step": round(float(lat.mean()), 3), "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "VibeVoice-Streaming-0.5B random-init (24 layers = 4 text + 20 TTS, H 896, 14/2 heads of 64), %d-token cached prompt "
+                                   "imported through vv_kv_write, first text window of 5 tokens, %d diffusion steps, cfg 1.5: generate() entry -> "
+                                   "first [1,3200] chunk at AudioStreamer.put" % (L0, steps), "prompt_len": L0, "diffusion_steps": steps},
+            "p90_ms": round(float(np.percentile(lat, 90)), 3), "min_ms": round(float(lat.min()), 3), "clocks": clk,
+            "gpu_launches": int(eng.launch_count()), "setup_s": round(time.time() - t_setup, 1)}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse()
+    if args.model == "streaming-0.5b":
+        return run_streaming_latency(args)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -190,3 +190,44 @@ def test_batch4_closed_loop_vs_oracle():
             assert e < 1e-2, (r, e)
     finally:
         model.engine.close()
+
+
+def test_head_dim_64_lm_decode_vs_oracle():
+    """head_dim 64 (the streaming-0.5B attention geometry) through the weight-stream path: K / V pages are one 64-column TMA box, the
+    o-projection merges one head per k-block.  Crosses a page boundary; both rows long enough to have several partials."""
+    from test_gpu_parity import _lm_roundtrip
+    model, cfg, tok, sd = _model("tiny64", 2)
+    try:
+        assert cfg.decoder_config.head_dim == 64
+        errs = _lm_roundtrip(model, cfg, tok, sd, n_prompt=70, n_steps=6)
+        report("lm_decode_head_dim_64", max_rel_l2=max(errs))
+        assert max(errs) < 2e-3, errs
+    finally:
+        model.engine.close()
+
+
+def test_streaming_variant_real_05b_shapes_vs_oracle():
+    """SURVEY 8f-1 at the real VibeVoice-Streaming-0.5B layer shapes (H = 896, 14 / 2 heads of 64, I = 4864; 1 text + 3 TTS layers here):
+    the split-stack loop against `oracle/vv_streaming.py` (pinned to the reference's own streaming generate())."""
+    from oracle import vv_streaming as VS
+    from vibevoice_b200 import streaming as S
+    cfg = preset_config("streaming-0.5b-l4")
+    base = synth_state_dict(cfg, SEED, torch.bfloat16, parts=("lm", "head", "acoustic_decoder", "connectors", "lm_head"))
+    sd = VS.streaming_state_dict(base, cfg, 3, eos_bias=-6.0)
+    m = S.VibeVoiceStreamingForConditionalGenerationInference(cfg, tts_backbone_num_hidden_layers=3)
+    m.load_state_dict(sd)
+    try:
+        m.set_ddpm_inference_steps(5)
+        g = torch.Generator().manual_seed(7)
+        prompt = torch.randint(0, 2000, (40,), generator=g)
+        text = torch.randint(0, 2000, (12,), generator=g)
+        torch.manual_seed(0)
+        out = m.generate(input_ids=prompt[None], tts_text_ids=text[None], neg_text_input_id=2047, cfg_scale=1.5, max_new_tokens=24)
+        torch.manual_seed(0)
+        ref = VS.generate_streaming(sd, cfg, 3, prompt, text, 2047, cfg_scale=1.5, num_steps=5, max_new_tokens=24, kv_bf16=True)
+        assert torch.equal(out.sequences, ref.sequences), (out.sequences, ref.sequences)
+        e = rel_l2(out.speech_outputs[0].cpu(), ref.speech_outputs[0])
+        report("streaming_generate_0.5b_shapes", audio_rel_l2=e)
+        assert e < 1e-2, e
+    finally:
+        m.engine.close()

@@ -187,4 +187,22 @@ def preset_config(name: str) -> VibeVoiceConfig:
             d[k]["encoder_depths"] = "2-1-1-1-1-1-2" if big else "1-1-1-1-1-1-2"
         d["acoustic_tokenizer_config"]["decoder_n_filters"] = 16 if big else 8
         return VibeVoiceConfig.from_dict(d)
+    if name == "tiny64":
+        # head_dim 64 (the streaming-0.5B attention geometry: GQA group 2 here) at toy widths
+        d = _preset(128, 384, 4, 2, 4096, 2048, True)
+        d["decoder_config"]["num_hidden_layers"] = 2
+        d["decoder_config"]["head_dim"] = 64
+        for k in ("acoustic_tokenizer_config", "semantic_tokenizer_config"):
+            d[k]["encoder_n_filters"] = 8
+            d[k]["encoder_depths"] = "1-1-1-1-1-1-2"
+        d["acoustic_tokenizer_config"]["decoder_n_filters"] = 8
+        return VibeVoiceConfig.from_dict(d)
+    if name in ("streaming-0.5b", "streaming-0.5b-l4"):
+        # VibeVoice-Streaming-0.5B language model: Qwen2.5-0.5B geometry (H = 896, 14 query / 2 kv heads of 64, I = 4864, 24 layers = 4 text
+        # + 20 TTS layers; inferred from the cached-prompt tensors demo/voices/streaming_model/*.pt and the public Qwen2.5-0.5B config, the
+        # reference ships no JSON for it -- SURVEY 8d-5).  "-l4" = the same layer shapes with 1 + 3 layers for parity tests.
+        d = _preset(896, 4864, 14, 2, 8192 if name.endswith("l4") else 32768, 4096 if name.endswith("l4") else 151936, True)
+        d["decoder_config"]["num_hidden_layers"] = 4 if name.endswith("l4") else 24
+        d["decoder_config"]["head_dim"] = 64
+        return VibeVoiceConfig.from_dict(d)
     raise ValueError("unknown preset %r" % name)

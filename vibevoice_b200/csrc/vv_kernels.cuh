@@ -1579,17 +1579,17 @@ __global__ void timestep_feat_kernel(const float* __restrict__ t, const float* _
 }
 // KV hand-off from a prefill: src [n_tokens][kv_heads][HD] bf16 -> pages
 __global__ void kv_write_kernel(const bf16* __restrict__ k, const bf16* __restrict__ v, bf16* __restrict__ kpool, bf16* __restrict__ vpool,
-                                const int* __restrict__ page_row, int kv_heads, long long pos0, long long n_tokens) {
+                                const int* __restrict__ page_row, int kv_heads, int hd, long long pos0, long long n_tokens) {
   const long long t = blockIdx.x;
   if (t >= n_tokens) return;
   const long long pos = pos0 + t;
   const int page = page_row[pos / KV_PAGE];
   const int slot = (int)(pos % KV_PAGE);
-  for (int i = threadIdx.x; i < kv_heads * HD; i += blockDim.x) {
-    const int h = i / HD, d = i % HD;
-    const size_t o = (((size_t)page * kv_heads + h) * KV_PAGE + slot) * HD + d;
-    kpool[o] = k[(size_t)t * kv_heads * HD + i];
-    vpool[o] = v[(size_t)t * kv_heads * HD + i];
+  for (int i = threadIdx.x; i < kv_heads * hd; i += blockDim.x) {
+    const int h = i / hd, d = i % hd;
+    const size_t o = (((size_t)page * kv_heads + h) * KV_PAGE + slot) * hd + d;
+    kpool[o] = k[(size_t)t * kv_heads * hd + i];
+    vpool[o] = v[(size_t)t * kv_heads * hd + i];
   }
 }
 

@@ -362,8 +362,8 @@ struct StreamBuilder {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return fail(VV_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     const cuuint64_t rows = (cuuint64_t)d.num_layers * c->n_pages * d.num_kv_heads * KV_PAGE;
-    const cuuint64_t dims[2] = {(cuuint64_t)HD, rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)HD * 2};
+    const cuuint64_t dims[2] = {(cuuint64_t)d.head_dim, rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)d.head_dim * 2};
     const cuuint32_t box[2] = {64, KV_PAGE};
     const cuuint32_t estr[2] = {1, 1};
     for (bf16* pool : {c->kpool, c->vpool}) {
@@ -378,13 +378,14 @@ struct StreamBuilder {
   }
   void fill_att(SAtt* a, int layer) {
     const auto& d = c->d;
-    const size_t per_layer = (size_t)c->n_pages * d.num_kv_heads * KV_PAGE * HD;
+    const size_t per_layer = (size_t)c->n_pages * d.num_kv_heads * KV_PAGE * d.head_dim;
     memset(a, 0, sizeof *a);
+    a->hd = d.head_dim;
     a->qkv = c->s_qkv;
     a->kv.kpool = c->kpool + per_layer * layer; a->kv.vpool = c->vpool + per_layer * layer;
     a->kv.page_table = c->page_table_dev; a->kv.max_pages = c->max_pages; a->kv.kv_len = c->kv_len_dev; a->kv.row_mode = c->row_mode_dev;
     a->kv.kv_heads = d.num_kv_heads; a->kv.q_heads = d.num_q_heads;
-    a->part_acc = c->s_pacc2; a->part_ml = c->s_pml2; a->inv_freq = c->inv_freq; a->scale = 1.0f / sqrtf((float)HD);
+    a->part_acc = c->s_pacc2; a->part_ml = c->s_pml2; a->inv_freq = c->inv_freq; a->scale = 1.0f / sqrtf((float)d.head_dim);
     a->row_base = (unsigned)((size_t)layer * c->n_pages * d.num_kv_heads * KV_PAGE);
     a->rope_cs = c->s_rope;
   }
@@ -435,7 +436,7 @@ static int finish_stream(StreamBuilder& b, vv_ctx::StreamProg* pr) {
     if (o.pro == SP_WINDOW && (o.cod.cin % 8)) return fail(VV_ERR_INVALID, "stream: window prologue needs a channel count that is a multiple of 8");
     if (o.pro == SP_COMBINE) {
       const long long nh = count / 2 + 2;
-      if ((long long)o.M * nh > 128 || KB != 2 * c->d.num_q_heads)
+      if ((long long)o.M * nh > 128 || KB != (c->d.head_dim / 64) * c->d.num_q_heads)
         return fail(VV_ERR_INVALID, "stream: attention-merge prologue does not fit (M=%d, %lld k-blocks per CTA)", o.M, count);
       b_bytes = std::max<long long>(b_bytes, ((count * o.nB * 128 + 1023) & ~1023ll) + o.M * nh * G * 4 + 16 + std::max<long long>(2048, o.M * count * 256) +
                                                  o.M * count * 256);
@@ -547,7 +548,7 @@ extern "C" const char* vv_last_error(void) { return g_err.c_str(); }
 
 extern "C" int vv_create(const vv_model_desc* desc, int device, vv_ctx** out) {
   if (!desc || !out) return fail(VV_ERR_INVALID, "vv_create: null argument");
-  if (desc->head_dim != HD) return fail(VV_ERR_INVALID, "head_dim %d unsupported (kernels are specialised for 128)", desc->head_dim);
+  if (desc->head_dim != 128 && desc->head_dim != 64) return fail(VV_ERR_INVALID, "head_dim %d unsupported (64 or 128)", desc->head_dim);
   if (desc->max_batch < 1 || desc->max_batch > 8) return fail(VV_ERR_INVALID, "max_batch must be in [1,8]");
   if (desc->n_stages < 2 || desc->n_stages > 8) return fail(VV_ERR_INVALID, "n_stages out of range");
   if (desc->num_q_heads % desc->num_kv_heads || desc->num_q_heads / desc->num_kv_heads > ATT_MAXG)
@@ -791,7 +792,7 @@ extern "C" int vv_finalize_weights(vv_ctx* c) {
       return fail(VV_ERR_STATE, "speech_scaling_factor / speech_bias_factor are NaN (random-init checkpoints: call vv_set_speech_factors)");
   }
   const auto& d = c->d;
-  const int H = d.hidden_size, I = d.intermediate_size, nq = d.num_q_heads * HD, nkv = d.num_kv_heads * HD, B = d.max_batch;
+  const int H = d.hidden_size, I = d.intermediate_size, nq = d.num_q_heads * d.head_dim, nkv = d.num_kv_heads * d.head_dim, B = d.max_batch;
   const int M2 = 2 * B;
   // ---------------- LM ----------------
   const std::string lm = "model.language_model";
@@ -847,10 +848,11 @@ extern "C" int vv_finalize_weights(vv_ctx* c) {
     gather_rows_kernel<<<d.n_valid_ids, 256>>>(table, c->valid_ids_dev, c->head_valid, H);
     CKL();
     *wb += (int64_t)d.n_valid_ids * H * 2;
-    RET(dmalloc(c, &c->inv_freq, HD / 2));
-    std::vector<float> f(HD / 2);
-    for (int i = 0; i < HD / 2; ++i) f[i] = 1.0f / powf(d.rope_theta, (float)(2 * i) / (float)HD);
-    CK(cudaMemcpy(c->inv_freq, f.data(), sizeof(float) * (HD / 2), cudaMemcpyHostToDevice));
+    const int hd = d.head_dim;
+    RET(dmalloc(c, &c->inv_freq, hd / 2));
+    std::vector<float> f(hd / 2);
+    for (int i = 0; i < hd / 2; ++i) f[i] = 1.0f / powf(d.rope_theta, (float)(2 * i) / (float)hd);
+    CK(cudaMemcpy(c->inv_freq, f.data(), sizeof(float) * (hd / 2), cudaMemcpyHostToDevice));
   }
   // ---------------- diffusion head ----------------
   {
@@ -1202,13 +1204,13 @@ extern "C" int vv_kv_commit(vv_ctx* c, const int32_t* adv, void* stream) {
 // drop the entry at position `pos` of a sequence: the last committed entry moves into its place (all layers), the length shrinks by one.
 // Attention does not depend on the order of the cached entries (keys are stored rotated), so this is how a sequence forgets an OLDER entry --
 // the reference's cache shifting with refresh_negative=False hides one (modeling_vibevoice_inference.py:599-624).
-__global__ void kv_move_kernel(bf16* kpool, bf16* vpool, const int* page_row, int kv_heads, size_t per_layer, int src, int dst) {
+__global__ void kv_move_kernel(bf16* kpool, bf16* vpool, const int* page_row, int kv_heads, int hd, size_t per_layer, int src, int dst) {
   const int layer = blockIdx.x;
   const int sp = page_row[src / KV_PAGE], dp = page_row[dst / KV_PAGE];
-  for (int i = threadIdx.x; i < kv_heads * HD; i += blockDim.x) {
-    const int h = i / HD, d = i % HD;
-    const size_t so = per_layer * layer + (((size_t)sp * kv_heads + h) * KV_PAGE + (src % KV_PAGE)) * HD + d;
-    const size_t dofs = per_layer * layer + (((size_t)dp * kv_heads + h) * KV_PAGE + (dst % KV_PAGE)) * HD + d;
+  for (int i = threadIdx.x; i < kv_heads * hd; i += blockDim.x) {
+    const int h = i / hd, d = i % hd;
+    const size_t so = per_layer * layer + (((size_t)sp * kv_heads + h) * KV_PAGE + (src % KV_PAGE)) * hd + d;
+    const size_t dofs = per_layer * layer + (((size_t)dp * kv_heads + h) * KV_PAGE + (dst % KV_PAGE)) * hd + d;
     kpool[dofs] = kpool[so];
     vpool[dofs] = vpool[so];
   }
@@ -1220,8 +1222,8 @@ extern "C" int vv_kv_delete_slot(vv_ctx* c, int seq, int64_t pos, void* stream) 
   if (pos < 0 || pos >= len) return fail(VV_ERR_INVALID, "vv_kv_delete_slot: position %lld outside [0,%lld)", (long long)pos, (long long)len);
   const auto& d = c->d;
   if (pos != len - 1) {
-    const size_t per_layer = (size_t)c->n_pages * d.num_kv_heads * KV_PAGE * HD;
-    kv_move_kernel<<<d.num_layers, 256, 0, (cudaStream_t)stream>>>(c->kpool, c->vpool, c->page_table_dev + (size_t)seq * c->max_pages, d.num_kv_heads, per_layer,
+    const size_t per_layer = (size_t)c->n_pages * d.num_kv_heads * KV_PAGE * d.head_dim;
+    kv_move_kernel<<<d.num_layers, 256, 0, (cudaStream_t)stream>>>(c->kpool, c->vpool, c->page_table_dev + (size_t)seq * c->max_pages, d.num_kv_heads, d.head_dim, per_layer,
                                                                   (int)(len - 1), (int)pos);
     CKL();
     c->launches++;
@@ -1241,7 +1243,7 @@ extern "C" int vv_set_row_mode(vv_ctx* c, const int32_t* rm, void* stream) {
 }
 extern "C" int vv_set_rope_inv_freq(vv_ctx* c, const float* f, int n) {
   if (!c || !c->finalized) return fail(VV_ERR_STATE, "not finalized");
-  if (n != HD / 2) return fail(VV_ERR_INVALID, "inv_freq must have %d entries", HD / 2);
+  if (n != c->d.head_dim / 2) return fail(VV_ERR_INVALID, "inv_freq must have %d entries", c->d.head_dim / 2);
   CK(cudaMemcpy(c->inv_freq, f, sizeof(float) * n, cudaMemcpyHostToDevice));
   return 0;
 }
@@ -1249,10 +1251,10 @@ extern "C" int vv_kv_write(vv_ctx* c, int seq, int layer, int64_t pos0, int64_t 
   if (!c || !c->kpool) return fail(VV_ERR_STATE, "KV pool not initialised");
   RET(vv_kv_reserve(c, seq, pos0 + n_tokens, stream));
   const auto& d = c->d;
-  const size_t per_layer = (size_t)c->n_pages * d.num_kv_heads * KV_PAGE * HD;
+  const size_t per_layer = (size_t)c->n_pages * d.num_kv_heads * KV_PAGE * d.head_dim;
   kv_write_kernel<<<(unsigned)n_tokens, 128, 0, (cudaStream_t)stream>>>((const bf16*)k, (const bf16*)v, c->kpool + per_layer * layer,
                                                                       c->vpool + per_layer * layer,
-                                                                      c->page_table_dev + (size_t)seq * c->max_pages, d.num_kv_heads, pos0, n_tokens);
+                                                                      c->page_table_dev + (size_t)seq * c->max_pages, d.num_kv_heads, d.head_dim, pos0, n_tokens);
   CKL();
   c->launches++;
   return 0;
@@ -1277,7 +1279,7 @@ static int lm_stream_prog(vv_ctx* c, int li0, int li1, const vv_ctx::StreamProg*
   auto it = c->sprogs.find(key);
   if (it != c->sprogs.end()) { *out = &it->second; return 0; }
   const auto& d = c->d;
-  const int H = d.hidden_size, I = d.intermediate_size, M = 2 * d.max_batch, nq = d.num_q_heads * HD;
+  const int H = d.hidden_size, I = d.intermediate_size, M = 2 * d.max_batch, nq = d.num_q_heads * d.head_dim;
   StreamBuilder b(c);
   b.nop(false, c->s_qkv, (long long)M * c->Nqkv);
   auto qkv = [&](int li) -> int {
@@ -1315,7 +1317,7 @@ static int lm_stream_prog_full(vv_ctx* c, int li0, int li1, const vv_ctx::Stream
   auto it = c->sprogs.find(key);
   if (it != c->sprogs.end()) { *out = &it->second; return 0; }
   const auto& d = c->d;
-  const int H = d.hidden_size, I = d.intermediate_size, M = 2 * d.max_batch, nq = d.num_q_heads * HD;
+  const int H = d.hidden_size, I = d.intermediate_size, M = 2 * d.max_batch, nq = d.num_q_heads * d.head_dim;
   StreamBuilder b(c);
   b.nop(false, c->s_qkv, (long long)M * c->Nqkv);
   for (int li = li0; li < li1; ++li) {
@@ -1351,6 +1353,7 @@ static int enqueue_lm_layers(const L& l, int li0, int li1, const vv_ctx::StreamP
   const size_t per_layer = (size_t)c->n_pages * d.num_kv_heads * KV_PAGE * HD;
   const float scale = 1.0f / sqrtf((float)HD);
   if (sprog && (c->use_stream & 4)) return launch_stream(l, *sprog);      // whole stack, attention included
+  if (d.head_dim != HD) return fail(VV_ERR_INVALID, "head_dim %d runs through the weight-stream path only (VV_STREAM bit 2)", d.head_dim);
   if (sprog) RET(launch_stream(l, *sprog, 0, 2));
   for (int li = li0; li < li1; ++li) {
     const LmLayer& y = c->lm[li];

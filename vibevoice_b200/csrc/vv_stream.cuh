@@ -115,6 +115,7 @@ struct SAtt {
   float scale;
   unsigned long long tmap_k, tmap_v;   // tensor maps over the WHOLE K / V pool: [layers * pages * kv_heads * 64 rows][128] bf16, box 64 x 64
   unsigned row_base;           // first row of this layer in those maps
+  int hd;                      // head_dim: 128 (a K / V page = two 64-column boxes) or 64 (one box, 8 KB of the slot used)
   float* rope_cs;              // [M][64][2] cos / sin of (kv_len[m] * inv_freq[d]): written by the QKV stage, read here (accurate sincosf of
                                // positions up to 64K costs ~1 us per segment when every CTA recomputes it)
 };
@@ -328,14 +329,14 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
       unsigned it = 0, done = 0;
       const unsigned cap = (unsigned)P.max_inflight;
-      auto acquire_slot = [&](int oi) -> unsigned {            // next ring slot, respecting the in-flight cap; arms its full barrier
+      auto acquire_slot = [&](int oi, unsigned bytes) -> unsigned {    // next ring slot, respecting the in-flight cap; arms its full barrier
         const unsigned slot = it % (unsigned)NS, ph = (it / (unsigned)NS) & 1u;
         while (it - done >= cap) {
           mbar_wait_wd(&full_bar[done % (unsigned)NS], (done / (unsigned)NS) & 1u, P.diag, 6u, (unsigned)oi, done);
           ++done;
         }
         mbar_wait_wd(&empty_bar[slot], ph ^ 1u, P.diag, 1u, (unsigned)oi, it);
-        mbar_expect_tx(&full_bar[slot], (unsigned)ST_TILE);
+        mbar_expect_tx(&full_bar[slot], bytes);
         ++it;
         return slot;
       };
@@ -352,12 +353,13 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
             for (int t = sg.t0; t < sg.t1; ++t) {
               const int page = a.kv.page_table[(size_t)sg.m * a.kv.max_pages + t];
               const int row0 = (int)(a.row_base + (unsigned)((page * a.kv.kv_heads + sg.g) * KV_PAGE));
-              unsigned slot = acquire_slot(oi);
+              const unsigned pbytes = (unsigned)(KV_PAGE * a.hd * 2);
+              unsigned slot = acquire_slot(oi, pbytes);
               tma_load_2d(ring + (size_t)slot * ST_TILE, a.tmap_k, 0, row0, &full_bar[slot], policy_kv);
-              tma_load_2d(ring + (size_t)slot * ST_TILE + 8192, a.tmap_k, 64, row0, &full_bar[slot], policy_kv);
-              slot = acquire_slot(oi);
+              if (a.hd > 64) tma_load_2d(ring + (size_t)slot * ST_TILE + 8192, a.tmap_k, 64, row0, &full_bar[slot], policy_kv);
+              slot = acquire_slot(oi, pbytes);
               tma_load_2d(ring + (size_t)slot * ST_TILE, a.tmap_v, 0, row0, &full_bar[slot], policy_kv);
-              tma_load_2d(ring + (size_t)slot * ST_TILE + 8192, a.tmap_v, 64, row0, &full_bar[slot], policy_kv);
+              if (a.hd > 64) tma_load_2d(ring + (size_t)slot * ST_TILE + 8192, a.tmap_v, 64, row0, &full_bar[slot], policy_kv);
             }
           }
           continue;
@@ -503,7 +505,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       if (op.init2_dst) {
         for (long long i = (long long)blockIdx.x * ST_WORKERS + wt; i < op.init2_n; i += (long long)G * ST_WORKERS) op.init2_dst[i] = 0.f;
       }
-      if (op.rope_rows > 0 && (int)blockIdx.x < op.rope_rows && wt < HD / 2) {
+      if (op.rope_rows > 0 && (int)blockIdx.x < op.rope_rows && wt < op.att.hd / 2) {
         const int m = blockIdx.x;
         float sn, cs;
         sincosf((float)s_kvlen[m] * op.att.inv_freq[wt], &sn, &cs);
@@ -579,6 +581,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         const SAtt& a = op.att;
         const unsigned U = att_vtotal(seq, op.M);
         const int Gq = a.kv.q_heads / a.kv.kv_heads, nkv = a.kv.kv_heads;
+        const int hd = a.hd, hh2 = hd >> 1, nks = hd >> 4;                         // head_dim, RoPE half, 16-wide k / d steps
         bf16 (*Qs)[AT2_LD] = reinterpret_cast<bf16 (*)[AT2_LD]>(breg);              // [16][136]: rows 0..7 hi, 8..15 lo of the G query heads
         bf16* knew = reinterpret_cast<bf16*>(breg + 16 * AT2_LD * 2);
         bf16* vnew = knew + HD;
@@ -592,36 +595,36 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
           const unsigned nt = sg.nt;
           const int pos = s_kvlen[m], L = pos + 1;
           const bool owner = (t_end == (int)nt);                                    // this CTA holds the page of the newest token
-          const float* row = a.qkv + (size_t)m * (a.kv.q_heads + 2 * nkv) * HD;
-          for (int i = wt; i < 8 * (HD / 2); i += ST_WORKERS) {
-            const int h = i / (HD / 2), d = i % (HD / 2);
+          const float* row = a.qkv + (size_t)m * (a.kv.q_heads + 2 * nkv) * hd;
+          for (int i = wt; i < 8 * hh2; i += ST_WORKERS) {
+            const int h = i / hh2, d = i - h * hh2;
             float o1 = 0.f, o2 = 0.f;
             if (h < Gq) {
               const float2 csn = __ldcg(reinterpret_cast<const float2*>(a.rope_cs + ((size_t)m * (HD / 2) + d) * 2));
               const float cs = csn.x, sn = csn.y;
-              const float x1 = ldcg1(row + (g * Gq + h) * HD + d), x2 = ldcg1(row + (g * Gq + h) * HD + d + HD / 2);
+              const float x1 = ldcg1(row + (g * Gq + h) * hd + d), x2 = ldcg1(row + (g * Gq + h) * hd + d + hh2);
               o1 = (x1 * cs - x2 * sn) * a.scale;
               o2 = (x2 * cs + x1 * sn) * a.scale;
             }
             const bf16 h1 = __float2bfloat16_rn(o1), h2 = __float2bfloat16_rn(o2);
-            Qs[h][d] = h1; Qs[h][d + HD / 2] = h2;
+            Qs[h][d] = h1; Qs[h][d + hh2] = h2;
             Qs[h + 8][d] = __float2bfloat16_rn(o1 - __bfloat162float(h1));
-            Qs[h + 8][d + HD / 2] = __float2bfloat16_rn(o2 - __bfloat162float(h2));
+            Qs[h + 8][d + hh2] = __float2bfloat16_rn(o2 - __bfloat162float(h2));
           }
           if (owner) {                                                              // rotate k, round K / V to bf16, append to the pool
             const int page = a.kv.page_table[(size_t)m * a.kv.max_pages + pos / KV_PAGE];
-            const size_t oo = (((size_t)page * nkv + g) * KV_PAGE + (pos % KV_PAGE)) * HD;
-            if (wt < HD / 2) {
+            const size_t oo = (((size_t)page * nkv + g) * KV_PAGE + (pos % KV_PAGE)) * hd;
+            if (wt < hh2) {
               const int d = wt;
               const float2 csn = __ldcg(reinterpret_cast<const float2*>(a.rope_cs + ((size_t)m * (HD / 2) + d) * 2));
               const float cs = csn.x, sn = csn.y;
-              const float x1 = ldcg1(row + (a.kv.q_heads + g) * HD + d), x2 = ldcg1(row + (a.kv.q_heads + g) * HD + d + HD / 2);
+              const float x1 = ldcg1(row + (a.kv.q_heads + g) * hd + d), x2 = ldcg1(row + (a.kv.q_heads + g) * hd + d + hh2);
               const bf16 k1 = __float2bfloat16_rn(x1 * cs - x2 * sn), k2 = __float2bfloat16_rn(x2 * cs + x1 * sn);
-              knew[d] = k1; knew[d + HD / 2] = k2;
-              a.kv.kpool[oo + d] = k1; a.kv.kpool[oo + d + HD / 2] = k2;
+              knew[d] = k1; knew[d + hh2] = k2;
+              a.kv.kpool[oo + d] = k1; a.kv.kpool[oo + d + hh2] = k2;
             } else {
-              for (int d = wt - HD / 2; d < HD; d += 64) {
-                const bf16 vv_ = __float2bfloat16_rn(ldcg1(row + (a.kv.q_heads + nkv + g) * HD + d));
+              for (int d = wt - hh2; d < hd; d += ST_WORKERS - hh2) {
+                const bf16 vv_ = __float2bfloat16_rn(ldcg1(row + (a.kv.q_heads + nkv + g) * hd + d));
                 vnew[d] = vv_;
                 a.kv.vpool[oo + d] = vv_;
               }
@@ -631,7 +634,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
           if (tr && first_seg) P.trace[(size_t)oi * ST_TRACE + 2] = clock64();
           unsigned qa[8][4];
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) ldmatrix_x4(qa[ks], &Qs[lane & 15][ks * 16 + (lane >> 4) * 8]);
+          for (int ks = 0; ks < 8; ++ks) if (ks < nks) ldmatrix_x4(qa[ks], &Qs[lane & 15][ks * 16 + (lane >> 4) * 8]);
           float o[16][4];
 #pragma unroll
           for (int i = 0; i < 16; ++i) { o[i][0] = 0.f; o[i][1] = 0.f; o[i][2] = 0.f; o[i][3] = 0.f; }
@@ -648,17 +651,21 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
             const bool splice = owner && tt == (int)nt - 1;
             if (splice) {                          // the page was fetched before (or while) the new row was written: patch it in shared memory
               mbar_wait_wd(&full_bar[slotV], phV, P.diag, 7u, (unsigned)oi, (unsigned)tt);
-              *reinterpret_cast<bf16*>(Ks + kv_off(pos - tok0, wt)) = knew[wt];
-              *reinterpret_cast<bf16*>(Vs + kv_off(pos - tok0, wt)) = vnew[wt];
+              if (wt < hd) {
+                *reinterpret_cast<bf16*>(Ks + kv_off(pos - tok0, wt)) = knew[wt];
+                *reinterpret_cast<bf16*>(Vs + kv_off(pos - tok0, wt)) = vnew[wt];
+              }
               worker_sync();
             }
             float sa[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks) {
-              unsigned kb[4];
-              ldmatrix_x4(kb, Ks + kv_off(ww * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 16 + ((lane >> 3) & 1) * 8));
-              mma_bf16_16816(sa[0], qa[ks], kb[0], kb[1]);
-              mma_bf16_16816(sa[1], qa[ks], kb[2], kb[3]);
+              if (ks < nks) {
+                unsigned kb[4];
+                ldmatrix_x4(kb, Ks + kv_off(ww * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 16 + ((lane >> 3) & 1) * 8));
+                mma_bf16_16816(sa[0], qa[ks], kb[0], kb[1]);
+                mma_bf16_16816(sa[1], qa[ks], kb[2], kb[3]);
+              }
             }
             const int tb = tok0 + ww * 16 + (lane & 3) * 2;
             float sv[4] = {sa[0][0] + sa[0][2], sa[0][1] + sa[0][3], sa[1][0] + sa[1][2], sa[1][1] + sa[1][3]};
@@ -689,10 +696,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
             if (!splice) mbar_wait_wd(&full_bar[slotV], phV, P.diag, 7u, (unsigned)oi, (unsigned)tt);
 #pragma unroll
             for (int np = 0; np < 8; ++np) {
-              unsigned vb[4];
-              ldmatrix_x4_trans(vb, Vs + kv_off(ww * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, np * 16 + (lane >> 4) * 8));
-              mma_bf16_16816(o[2 * np], pa, vb[0], vb[1]);
-              mma_bf16_16816(o[2 * np + 1], pa, vb[2], vb[3]);
+              if (np < nks) {
+                unsigned vb[4];
+                ldmatrix_x4_trans(vb, Vs + kv_off(ww * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, np * 16 + (lane >> 4) * 8));
+                mma_bf16_16816(o[2 * np], pa, vb[0], vb[1]);
+                mma_bf16_16816(o[2 * np + 1], pa, vb[2], vb[3]);
+              }
             }
             if (splice) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             worker_sync();                         // all four warps are done with both pages
@@ -703,9 +712,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
           const int h = lane >> 2;
 #pragma unroll
           for (int ntl = 0; ntl < 16; ++ntl) {
-            const int d = ntl * 8 + (lane & 3) * 2;
-            mo[(ww * 8 + h) * HD + d] = o[ntl][0] + o[ntl][2];
-            mo[(ww * 8 + h) * HD + d + 1] = o[ntl][1] + o[ntl][3];
+            if (ntl < 2 * nks) {
+              const int d = ntl * 8 + (lane & 3) * 2;
+              mo[(ww * 8 + h) * HD + d] = o[ntl][0] + o[ntl][2];
+              mo[(ww * 8 + h) * HD + d + 1] = o[ntl][1] + o[ntl][3];
+            }
           }
           if ((lane & 3) == 0) { mlw[(ww * 8 + h) * 2] = m_run; mlw[(ww * 8 + h) * 2 + 1] = l_run; }
           worker_sync();
@@ -723,7 +734,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
               num = fmaf(wgt, mo[(w * 8 + hh) * HD + wt], num);
               den = fmaf(wgt, mlw[(w * 8 + hh) * 2 + 1], den);
             }
-            a.part_acc[(pbase + hh) * HD + wt] = num;
+            if (wt < hd) a.part_acc[(pbase + hh) * HD + wt] = num;
             if (wt == 0) { a.part_ml[(pbase + hh) * 2] = mx; a.part_ml[(pbase + hh) * 2 + 1] = den; }
           }
           worker_sync();
@@ -751,7 +762,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       // SP_COMBINE scratch behind the B operand: [M][NH][G] merge weights w_p / sum_p w_p l_p | group partial sums | merged[M][count][64]
       const int cmb_base = (count * nB * 128 + 1023) & ~1023;
       float* s_w = reinterpret_cast<float*>(breg + cmb_base);
-      const int cmb_nh = (((kb_first & 1) + count - 1) >> 1) + 1;       // distinct heads among this CTA's k-blocks (k-block = half a head)
+      const int cmb_kbh = (pro == SP_COMBINE ? op.att.hd : 128) >> 6;     // k-blocks per head (head_dim 128: two, 64: one)
+      const int cmb_nh = ((kb_first % cmb_kbh) + count - 1) / cmb_kbh + 1;   // distinct heads among this CTA's k-blocks
       const int cmb_off = cmb_base + ((M * cmb_nh * (int)G * 4 + 15) & ~15);
       const int cmb_part = (M * count * 256 > 2048) ? M * count * 256 : 2048;     // bytes of the group partial sums (npg * out4 float4)
       auto chunk_coord = [&](int c, int& m, int& jloc, int& ch, int& k) {
@@ -856,7 +868,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         const int Gq = a.kv.q_heads / a.kv.kv_heads, nkv = a.kv.kv_heads;
         for (int pi = ww; pi < M * cmb_nh; pi += 4) {                     // one warp per (row, head)
           const int m = pi / cmb_nh, hid = pi - m * cmb_nh;
-          const int h = ((kb_first >> 1) + hid) % a.kv.q_heads, g = h / Gq, hh = h - g * Gq;
+          const int h = ((kb_first / cmb_kbh) + hid) % a.kv.q_heads, g = h / Gq, hh = h - g * Gq;
           unsigned pre = 0;
           for (int mm = 0; mm < m; ++mm) { const unsigned n2 = att_tiles(seq, mm); if (n2) pre += (n2 + ST_ATT_SEGW) * (unsigned)nkv; }
           const unsigned nt = att_tiles(seq, m);
@@ -903,8 +915,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
           const int o4 = w0 % out4, pg = w0 / out4;
           const int m = o4 / (count * 16), r = o4 - m * (count * 16), jloc = r >> 4, q4 = r & 15;
           int kb = kb_first + jloc; if (kb >= KB) kb -= KB;
-          const int k = kb * 64 + q4 * 4, h = k >> 7, d = k & 127, g = h / Gq, hh = h - g * Gq;
-          const int pi = m * cmb_nh + (((kb_first & 1) + jloc) >> 1);
+          const int k = kb * 64 + q4 * 4, h = k / a.hd, d = k - h * a.hd, g = h / Gq, hh = h - g * Gq;
+          const int pi = m * cmb_nh + ((kb_first % cmb_kbh) + jloc) / cmb_kbh;
           const int Pn = s_pinfo[pi];
           const float* wrow = s_w + (size_t)pi * G;
           const float* ap = a.part_acc + ((((size_t)m * nkv + g) * G) * 8 + hh) * HD + d;       // slot stride 8 * 128 floats
