@@ -546,7 +546,9 @@ def run_streaming_latency(args):
     g = torch.Generator(device=dev).manual_seed(7)
 
     def items():
-        yield from iter_synth_state_dict_fast(cfg, 1234, device=dev, parts=("lm", "head", "acoustic_decoder", "connectors"))
+        for name, t in iter_synth_state_dict_fast(cfg, 1234, device=dev, parts=("lm", "head", "acoustic_decoder", "connectors")):
+            if not name.startswith("model.semantic"):          # the streaming model has no semantic branch (zero-filled by the loader)
+                yield name, t
         yield "model.tts_input_types.weight", torch.randn(2, H, device=dev, generator=g) * 0.05
         yield "tts_eos_classifier.fc1.weight", torch.randn(H, H, device=dev, generator=g) * 0.05
         yield "tts_eos_classifier.fc1.bias", torch.zeros(H, device=dev)
