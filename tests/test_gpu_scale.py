@@ -231,3 +231,36 @@ def test_streaming_variant_real_05b_shapes_vs_oracle():
         assert e < 1e-2, e
     finally:
         m.engine.close()
+
+
+def test_batch8_tiny_closed_loop_vs_oracle():
+    """The largest batch the engine accepts (8 prompts -> 16 LM rows: MMA N = 32 in the weight-stream kernel, 16 attention rows, 8-row codec
+    stages): ragged prompts, rows finishing at different steps."""
+    from oracle import vv_oracle as O
+    from vibevoice_b200.modeling import ForcedTokenScript
+    model, cfg, tok, sd = _model("tiny", 8)
+    try:
+        dc = cfg.decoder_config
+        g = torch.Generator().manual_seed(13)
+        L0 = 14
+        ids = torch.randint(0, dc.vocab_size - 20, (8, L0), generator=g)
+        ids[:, -1] = tok.speech_start_id
+        mask = torch.ones(8, L0, dtype=torch.long)
+        for r in range(8):
+            mask[r, :r] = 0
+            ids[r, :r] = tok.pad_token_id
+        plans = ["ddddx", "dddesddx", "dx", "ddddddx", "ddx", "dddx", "desdx", "dddddx"]
+        scripts = [_scripted(tok, p) for p in plans]
+        model.set_ddpm_inference_steps(5)
+        torch.manual_seed(0)
+        out = model.generate(input_ids=ids, attention_mask=mask, tokenizer=tok, cfg_scale=1.3, is_prefill=False,
+                             logits_processor=[ForcedTokenScript(scripts)], max_new_tokens=16, show_progress_bar=False)
+        torch.manual_seed(0)
+        ref = O.generate(sd, cfg, ids, mask, tok, cfg_scale=1.3, num_steps=5, max_new_tokens=16, forced_tokens=scripts, kv_bf16=True)
+        assert torch.equal(out.sequences, ref.sequences)
+        for r in range(8):
+            e = rel_l2(out.speech_outputs[r].cpu(), ref.speech_outputs[r])
+            report("generate_batch8_tiny", row=r, audio_rel_l2=e)
+            assert e < 1e-2, (r, e)
+    finally:
+        model.engine.close()
