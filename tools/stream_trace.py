@@ -107,6 +107,28 @@ if G:
     lat = np.array([t2[i, :, 0] - np.median(t2[i, :, 0]) for i in range(1, n) if t2[i, :, 0].min() > 0]) / 1e3
     m = lat.mean(axis=0)
     print("mean lateness (us) by CTA: min %.2f max %.2f; worst CTAs %s" % (m.min(), m.max(), [(int(c), round(float(m[c]), 2)) for c in np.argsort(-m)[:8]]))
+    # wall-clock span of the kernel's stages (globaltimer, ns) against the SM-cycle stamps -> the SM clock the run really had
+    rel_ok = [i for i in range(1, n) if t2[i, :, 0].min() > 0]
+    if len(rel_ok) > 2:
+        i0, i1 = rel_ok[0], rel_ok[-1]
+        span_ns = float(t2[i1, :, 1].max() - t2[i0, :, 0].min())
+        cyc = float(out[i1][1] - out[i0][0]) if out[i1][1] and out[i0][0] else 0.0
+        print("stages %d..%d: %.1f us by globaltimer, %.0f SM cycles on the traced CTA -> effective SM clock %.0f MHz (stamps above assume %.0f)" % (
+            i0, i1, span_ns / 1e3, cyc, cyc / (span_ns / 1e3) if span_ns else 0.0, a.mhz))
 print("(attention rows: barrier | Q staged | first segment's pages | merge + partial | remaining segments)")
 tot = sum(us(out[i][5] - out[i][0]) for i in range(n) if meta[i][0] in (0, 2) and out[i][5])
 print("sum of traced stage totals: %.1f us; first->last stamp: %.1f us" % (tot, us(out[:n, 5].max() - out[:n, 0][out[:n, 0] > 0].min())))
+
+# the same program by CUDA events, as bench.py times it (graph replays queued back to back)
+fn = {"lm": lambda: (eng.lm_decode(), eng.kv_commit([1] * (2 * B))), "de": eng.codec_decode, "en": eng.semantic_encode}.get(a.prog[:2], lambda: eng.diffusion_sample(1.3))
+for label, f in (("program call", fn),) + ((("lm_decode without kv_commit", eng.lm_decode),) if a.prog.startswith("lm") else ()):
+    for _ in range(3):
+        f()
+    eng.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(eng.stream)
+    for _ in range(16):
+        f()
+    e1.record(eng.stream)
+    eng.sync()
+    print("%s by CUDA events (tracing on): %.1f us" % (label, e0.elapsed_time(e1) * 1e3 / 16))

@@ -134,7 +134,7 @@ struct vv_ctx {
   std::map<std::string, GraphEntry> graphs;
   GridBar* gridbar = nullptr;
   // weight-stream programs (vv_stream.cuh)
-  struct StreamProg { SOp* ops = nullptr; int n_ops = 0; CUtensorMap* tmaps = nullptr; int n_stages = 0; int b_bytes = 0; int smem = 0; int gemv_ops = 0; };
+  struct StreamProg { SOp* ops = nullptr; int n_ops = 0; CUtensorMap* tmaps = nullptr; int n_stages = 0; int b_bytes = 0; int smem = 0; int gemv_ops = 0; int variant = 0; };
   std::map<std::string, StreamProg> sprogs;
   unsigned* st_bar = nullptr;            // grid-barrier counter of the stream kernel
   unsigned* st_diag_host = nullptr; unsigned* st_diag_dev = nullptr;   // host-mapped watchdog record
@@ -418,6 +418,25 @@ struct StreamBuilder {
   }
 };
 
+// stream_kernel instantiations: one per program family, each compiled with only the stage kinds / prologues / scalings the family uses
+// (instruction-cache footprint, see the template's comment); a program runs on the first variant whose feature set covers it.
+constexpr unsigned sfeat(std::initializer_list<int> pros, std::initializer_list<int> kinds, std::initializer_list<int> alphas) {
+  unsigned f = 0;
+  for (int x : pros) f |= 1u << x;
+  for (int x : kinds) f |= 1u << (16 + x);
+  for (int x : alphas) f |= 1u << (24 + x);
+  return f;
+}
+constexpr unsigned SF_SAMP = sfeat({SP_NONE, SP_ADALN, SP_SWIGLU, SP_DPM}, {SK_GEMV, SK_NOP}, {SA_ONE, SA_GATE});
+constexpr unsigned SF_LM = sfeat({SP_NONE, SP_RMSNORM, SP_SWIGLU, SP_COMBINE}, {SK_GEMV, SK_NOP, SK_ATTN}, {SA_ONE});
+constexpr unsigned SF_CODEC = sfeat({SP_NONE, SP_WINDOW, SP_RMSNORM, SP_GELU}, {SK_GEMV, SK_NOP, SK_MIX}, {SA_ONE, SA_GAMMA});
+constexpr unsigned SF_ALL = 0xffffffffu;
+typedef void (*StreamFn)(SParams);
+static const struct { unsigned feat; StreamFn fn; const char* name; } STREAM_VARIANTS[] = {
+  {SF_SAMP, stream_kernel<SF_SAMP>, "sampler"}, {SF_LM, stream_kernel<SF_LM>, "lm"}, {SF_CODEC, stream_kernel<SF_CODEC>, "codec"},
+  {SF_ALL, stream_kernel<SF_ALL>, "all"}};
+constexpr int N_STREAM_VARIANTS = 4;
+
 static int finish_stream(StreamBuilder& b, vv_ctx::StreamProg* pr) {
   vv_ctx* c = b.c;
   const int G = c->sm_count;
@@ -443,8 +462,15 @@ static int finish_stream(StreamBuilder& b, vv_ctx::StreamProg* pr) {
     }
     if (U * (G + 1) >= (1ll << 32)) return fail(VV_ERR_INVALID, "stream: stage [%d x %d] has too many tiles for 32-bit scheduling", o.N, o.K);
   }
+  unsigned feat = 0;
+  for (const SOp& o : b.ops) feat |= (1u << o.pro) | (1u << (16 + o.kind)) | (1u << (24 + o.alpha_kind));
+  pr->variant = N_STREAM_VARIANTS - 1;
+  if (!getenv("VV_STREAM_GENERIC"))
+    for (int v = 0; v < N_STREAM_VARIANTS; ++v)
+      if ((feat & ~STREAM_VARIANTS[v].feat) == 0) { pr->variant = v; break; }
+  if (getenv("VV_VERBOSE")) fprintf(stderr, "[vv] stream program: %zu stages, features %08x -> kernel variant '%s'\n", b.ops.size(), feat, STREAM_VARIANTS[pr->variant].name);
   cudaFuncAttributes fa;
-  CK(cudaFuncGetAttributes(&fa, stream_kernel));
+  CK(cudaFuncGetAttributes(&fa, STREAM_VARIANTS[pr->variant].fn));
   const int max_dyn = 232448 - (int)fa.sharedSizeBytes - 256;
   int ns = (max_dyn - 1024 - b_bytes) / ST_TILE;
   ns = std::min(ns, ST_MAX_STAGES);
@@ -464,7 +490,7 @@ static int finish_stream(StreamBuilder& b, vv_ctx::StreamProg* pr) {
   }
   if (!b.tmaps.empty()) CK(cudaMemcpy(pr->tmaps, b.tmaps.data(), b.tmaps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(pr->ops, b.ops.data(), b.ops.size() * sizeof(SOp), cudaMemcpyHostToDevice));
-  CK(cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  CK(cudaFuncSetAttribute(STREAM_VARIANTS[pr->variant].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   return 0;
 }
 
@@ -487,7 +513,7 @@ static int launch_stream(const L& l, const vv_ctx::StreamProg& pr, int op_begin 
   P.trace2 = P.trace ? c->st_trace2 : nullptr;
   if (P.trace) c->st_trace_last_ops = pr.n_ops;
   c->launches++;
-  CK(cudaLaunchKernelEx(&cfg, stream_kernel, P));
+  CK(cudaLaunchKernelEx(&cfg, STREAM_VARIANTS[pr.variant].fn, P));
   return 0;
 }
 

@@ -239,6 +239,10 @@ VV_DEVINL unsigned att_tiles(const SeqView& q, int m) { return q.row_mode[m] ? (
 // order.  CTAs take contiguous ranges of virtual units, so a CTA that also gets the few pages of a short (CFG-negative) row gets
 // correspondingly fewer pages of the long one (measured before: the CTA owning both short groups arrived 8 us late at every layer's barrier).
 constexpr unsigned ST_ATT_SEGW = 4;
+#ifndef ST_WIDE
+#define ST_WIDE 0      // 1: 4 activation chunks per thread in one L2 round trip. Measured on one box (tools/ab_run.sh): the LM gains 0.5 %, but the extra
+                       // 1 900 instructions cost the sampler 4.7 % (instruction cache) -> off
+#endif
 VV_DEVINL unsigned att_vtotal(const SeqView& q, int M) {
   unsigned V = 0;
   for (int m = 0; m < M; ++m) { const unsigned nt = att_tiles(q, m); if (nt) V += (nt + ST_ATT_SEGW) * (unsigned)q.kv_heads; }
@@ -283,7 +287,14 @@ VV_DEVINL void st_part(const SOp& op, unsigned& u0, unsigned& u1, int& KB) {
 // ---------------------------------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------------------------------
+// FEAT = the stage kinds / prologues / epilogue scalings a program may use (bit SP_x, bit 16 + SK_x, bit 24 + SA_x).  One instantiation per
+// program family: the all-features kernel is 224 KB of SASS and every stage runs its path exactly once, so the instruction cache misses
+// on most of it -- measured on one box (tools/ab_run.sh): +1 900 instructions of code a program never executes cost the sampler 4.7 %.
+template <unsigned FEAT>
 __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
+#define PRO_IS(x) (((FEAT >> (x)) & 1u) != 0u && pro == (x))
+#define KIND_IS(x) (((FEAT >> (16 + (x))) & 1u) != 0u && op.kind == (x))
+#define ALPHA_IS(x) (((FEAT >> (24 + (x))) & 1u) != 0u && op.alpha_kind == (x))
   extern __shared__ unsigned char st_raw[];
   __shared__ unsigned long long full_bar[ST_MAX_STAGES], empty_bar[ST_MAX_STAGES];
   __shared__ unsigned long long b_ready, acc_full;
@@ -344,7 +355,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy_kv));
       for (int oi = 0; oi < P.n_ops; ++oi) {
         const SOp& op = P.ops[oi];
-        if (op.kind == SK_ATTN) {
+        if (KIND_IS(SK_ATTN)) {
           // K page then V page of every unit: two 64 x 64 boxes each (d 0..63, d 64..127) into one 16 KB slot
           const SAtt& a = op.att;
           AttIter ai; AttSeg sg;
@@ -393,7 +404,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
     unsigned slot = 0, ph = 0, gi = 0;
     for (int oi = 0; oi < P.n_ops; ++oi) {
       const SOp& op = P.ops[oi];
-      if (op.kind == SK_ATTN) {                                  // the workers consume 2 ring slots per attention unit: keep slot / phase in step
+      if (KIND_IS(SK_ATTN)) {                                  // the workers consume 2 ring slots per attention unit: keep slot / phase in step
         AttIter ai; AttSeg sg;
         att_begin(seq, op.M, ai);
         unsigned pages = 0;
@@ -477,41 +488,54 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       cp_async_commit();
       const bool tr = P.trace && (int)blockIdx.x == P.trace_cta && wt == 0;
       if (tr) P.trace[(size_t)oi * ST_TRACE + 0] = clock64();
-      do {
+      // the grid barrier sits as LATE as possible inside every stage: everything that only depends on the descriptor (unit range, chunk
+      // coordinates and addresses: a dozen integer divisions, ~0.6 us) is computed by the waiting workers BEFORE it
+      // (arrival first: every worker's global writes of the previous stage were issued before the sync that ended it)
       if (op.sync_before) {
-        bar_target += G;                       // (every worker's global writes of the previous stage were issued before the sync that ended it)
+        bar_target += G;
         if (wt == 0) {
           if (P.trace2) P.trace2[((size_t)oi * G + blockIdx.x) * 2] = gtime_ns();
-          // arrival = one fire-and-forget release reduction, then poll the counter.  (Tried, profiles/r02_stream_trace_7.txt: a returning
-          // atomic + release words replicated over 16 lines for the pollers -- 2.6 us from last arrival to last release against 1.5 us for
-          // this form: under the weight stream every dependent L2 round trip costs ~0.7 us, so the form with the fewest of them wins.)
           red_add_release_u32(P.bar_count, 1u);
-          long long t0 = 0;
-          for (unsigned spins = 0; ld_acquire_u32(P.bar_count) < bar_target; ++spins) {
-            if ((spins & 255u) == 255u) {
-              const long long t = clock64();
-              if (t0 == 0) t0 = t;
-              else if (t - t0 > 6000000000ll) st_die(P.diag, 4u, (unsigned)oi, bar_target, ld_acquire_u32(P.bar_count));
-            }
-          }
-          if (P.trace2) P.trace2[((size_t)oi * G + blockIdx.x) * 2 + 1] = gtime_ns();
         }
-        worker_sync();
       }
-      if (tr) P.trace[(size_t)oi * ST_TRACE + 1] = clock64();
-      if (op.init_dst) {
-        for (long long i = (long long)blockIdx.x * ST_WORKERS + wt; i < op.init_n; i += (long long)G * ST_WORKERS) op.init_dst[i] = 0.f;
-      }
-      if (op.init2_dst) {
-        for (long long i = (long long)blockIdx.x * ST_WORKERS + wt; i < op.init2_n; i += (long long)G * ST_WORKERS) op.init2_dst[i] = 0.f;
-      }
-      if (op.rope_rows > 0 && (int)blockIdx.x < op.rope_rows && wt < op.att.hd / 2) {
-        const int m = blockIdx.x;
-        float sn, cs;
-        sincosf((float)s_kvlen[m] * op.att.inv_freq[wt], &sn, &cs);
-        *reinterpret_cast<float2*>(op.att.rope_cs + ((size_t)m * (HD / 2) + wt) * 2) = make_float2(cs, sn);
-      }
-      if (op.kind == SK_MIX) {
+      auto grid_barrier = [&]() {
+        if (op.sync_before) {
+          if (wt == 0) {
+            // arrival = one fire-and-forget release reduction, then poll the counter.  (Tried, profiles/r02_stream_trace_7.txt: a returning
+            // atomic + release words replicated over 16 lines for the pollers -- 2.6 us from last arrival to last release against 1.5 us for
+            // this form: under the weight stream every dependent L2 round trip costs ~0.7 us, so the form with the fewest of them wins.)
+            long long t0 = 0;
+            for (unsigned spins = 0; ld_acquire_u32(P.bar_count) < bar_target; ++spins) {
+              if ((spins & 255u) == 255u) {
+                const long long t = clock64();
+                if (t0 == 0) t0 = t;
+                else if (t - t0 > 6000000000ll) st_die(P.diag, 4u, (unsigned)oi, bar_target, ld_acquire_u32(P.bar_count));
+              }
+            }
+            if (P.trace2) P.trace2[((size_t)oi * G + blockIdx.x) * 2 + 1] = gtime_ns();
+          }
+          worker_sync();
+        }
+        if (tr) P.trace[(size_t)oi * ST_TRACE + 1] = clock64();
+      };
+      // zero-fill jobs for later stages and the RoPE table: anywhere between this stage's barrier and the next one
+      auto side_jobs = [&]() {
+        if (op.init_dst) {
+          for (long long i = (long long)blockIdx.x * ST_WORKERS + wt; i < op.init_n; i += (long long)G * ST_WORKERS) op.init_dst[i] = 0.f;
+        }
+        if (op.init2_dst) {
+          for (long long i = (long long)blockIdx.x * ST_WORKERS + wt; i < op.init2_n; i += (long long)G * ST_WORKERS) op.init2_dst[i] = 0.f;
+        }
+        if (op.rope_rows > 0 && (int)blockIdx.x < op.rope_rows && wt < op.att.hd / 2) {
+          const int m = blockIdx.x;
+          float sn, cs;
+          sincosf((float)s_kvlen[m] * op.att.inv_freq[wt], &sn, &cs);
+          *reinterpret_cast<float2*>(op.att.rope_cs + ((size_t)m * (HD / 2) + wt) * 2) = make_float2(cs, sn);
+        }
+      };
+      do {
+      if (op.kind != SK_GEMV && !KIND_IS(SK_ATTN)) { grid_barrier(); side_jobs(); }
+      if (KIND_IS(SK_MIX)) {
         const SCodec& w = op.cod;
         const int C = op.K, M = op.M, T = w.T_out, Bn = M / T;
         // full-row statistics of x: rows in pairs, <= 16 float4 per thread in flight
@@ -576,7 +600,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         }
         break;
       }
-      if (op.kind == SK_ATTN) {
+      if (KIND_IS(SK_ATTN)) {
         // =========================== decode attention over the ring (see SAtt) ===========================
         const SAtt& a = op.att;
         const unsigned U = att_vtotal(seq, op.M);
@@ -589,8 +613,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         float* mlw = mo + 4 * 8 * HD;                                               // [4][8][2]
         AttIter ai; AttSeg sg;
         att_begin(seq, op.M, ai);
+        bool have = att_next(seq, op.M, ai, sg);                                    // partition arithmetic: ahead of the barrier
+        { int hv_ = have; asm volatile("" : "+r"(hv_), "+r"(sg.m), "+r"(sg.g), "+r"(sg.t0), "+r"(sg.t1), "+r"(sg.nt), "+r"(sg.vf)); have = hv_ != 0; }
+        grid_barrier();
+        side_jobs();
         bool first_seg = true;
-        while (att_next(seq, op.M, ai, sg)) {
+        for (; have; have = att_next(seq, op.M, ai, sg)) {
           const int m = sg.m, g = sg.g, t = sg.t0, t_end = sg.t1;
           const unsigned nt = sg.nt;
           const int pos = s_kvlen[m], L = pos + 1;
@@ -748,7 +776,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       unsigned u0, u1; int KB;
       st_part(op, u0, u1, KB);
       ring_advance(u1 - u0);
-      if (u0 == u1) break;
+      if (u0 == u1) { grid_barrier(); side_jobs(); break; }
       const int M = op.M, K = op.K, N = op.N, nB = op.nB, half = nB >> 1;
       const int units = (int)(u1 - u0);
       const int count = units < KB ? units : KB;          // k-blocks of activations this CTA needs (contiguous mod KB from kb_first)
@@ -758,74 +786,84 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       // (measured, profiles/r02_stream_trace_1.txt: a statistics loop followed by a staging loop costs one L2 round trip per loop
       //  iteration, 4.4 us per AdaLN stage; every load below is issued before the first value is consumed)
       const int total = M * count * 8;                     // 16-byte chunks (8 consecutive k of one activation row) to stage
-      const bool norm = (pro == SP_RMSNORM || pro == SP_ADALN);
+      const bool norm = (PRO_IS(SP_RMSNORM) || PRO_IS(SP_ADALN));
       // SP_COMBINE scratch behind the B operand: [M][NH][G] merge weights w_p / sum_p w_p l_p | group partial sums | merged[M][count][64]
       const int cmb_base = (count * nB * 128 + 1023) & ~1023;
       float* s_w = reinterpret_cast<float*>(breg + cmb_base);
-      const int cmb_kbh = (pro == SP_COMBINE ? op.att.hd : 128) >> 6;     // k-blocks per head (head_dim 128: two, 64: one)
+      const int cmb_kbh = (PRO_IS(SP_COMBINE) ? op.att.hd : 128) >> 6;     // k-blocks per head (head_dim 128: two, 64: one)
       const int cmb_nh = ((kb_first % cmb_kbh) + count - 1) / cmb_kbh + 1;   // distinct heads among this CTA's k-blocks
       const int cmb_off = cmb_base + ((M * cmb_nh * (int)G * 4 + 15) & ~15);
       const int cmb_part = (M * count * 256 > 2048) ? M * count * 256 : 2048;     // bytes of the group partial sums (npg * out4 float4)
-      auto chunk_coord = [&](int c, int& m, int& jloc, int& ch, int& k) {
-        m = c / (count * 8);
-        const int r = c - m * (count * 8);
-        jloc = r >> 3; ch = r & 7;
-        int kb = kb_first + jloc; if (kb >= KB) kb -= KB;
-        k = kb * 64 + ch * 8;
-      };
-      auto chunk_load = [&](int c, float4 (&in)[8]) {       // raw operands of one chunk (nothing is consumed here)
-        int m, jloc, ch, k;
-        chunk_coord(c, m, jloc, ch, k);
-        if (c >= total || k >= K || pro == SP_DPM || pro == SP_COMBINE) return;
-        if (pro == SP_WINDOW) {
+      struct ChunkRef { const float* xr; int m, jloc, ch, k; bool valid, live, fresh; };
+      auto chunk_ref = [&](int c) -> ChunkRef {             // coordinates + source address of chunk c: descriptor-only arithmetic
+        ChunkRef r;
+        r.m = c / (count * 8);
+        const int q = c - r.m * (count * 8);
+        r.jloc = q >> 3; r.ch = q & 7;
+        int kb = kb_first + r.jloc; if (kb >= KB) kb -= KB;
+        r.k = kb * 64 + r.ch * 8;
+        r.valid = c < total;
+        r.live = r.valid && r.k < K && !PRO_IS(SP_DPM) && !PRO_IS(SP_COMBINE);
+        r.fresh = false;
+        r.xr = op.x;
+        if (!r.live) return r;
+        if (PRO_IS(SP_WINDOW)) {
           const SCodec& w = op.cod;
-          const int b = m / w.T_out, t = m - b * w.T_out, j = k / w.cin, ci = k - j * w.cin, r = t * w.stride + j;
-          const float* xr = r < w.ctx ? w.hist + ((size_t)b * w.ctx + r) * w.cin + ci : w.src + ((size_t)b * w.T_in + (r - w.ctx)) * w.cin + ci;
+          const int b = r.m / w.T_out, t = r.m - b * w.T_out, j = r.k / w.cin, ci = r.k - j * w.cin, rr = t * w.stride + j;
+          r.fresh = rr >= w.ctx;
+          r.xr = rr < w.ctx ? w.hist + ((size_t)b * w.ctx + rr) * w.cin + ci : w.src + ((size_t)b * w.T_in + (rr - w.ctx)) * w.cin + ci;
+        } else if (PRO_IS(SP_SWIGLU)) {
+          r.xr = op.x + (long long)r.m * op.ldx + 2 * r.k;
+        } else {
+          r.xr = op.x + (long long)r.m * op.ldx + r.k;
+        }
+        return r;
+      };
+      auto chunk_load = [&](const ChunkRef& r, float4* in) {            // raw operands of one chunk (nothing is consumed here)
+        if (!r.live) return;
+        const float* xr = r.xr;
+        const int m = r.m, k = r.k;
+        if (PRO_IS(SP_WINDOW)) {
           in[0] = ldcg4(xr); in[1] = ldcg4(xr + 4);
           return;
         }
-        if (pro == SP_SWIGLU) {
-          const float* xr = op.x + (long long)m * op.ldx + 2 * k;
+        if (PRO_IS(SP_SWIGLU)) {
           in[0] = ldcg4(xr); in[1] = ldcg4(xr + 4); in[2] = ldcg4(xr + 8); in[3] = ldcg4(xr + 12);
           return;
         }
-        const float* xr = op.x + (long long)m * op.ldx + k;
         in[0] = ldcg4(xr); in[1] = ldcg4(xr + 4);
         if (norm) {
           if (op.pro_w) { in[2] = *reinterpret_cast<const float4*>(op.pro_w + k); in[3] = *reinterpret_cast<const float4*>(op.pro_w + k + 4); }
           else { in[2] = make_float4(1.f, 1.f, 1.f, 1.f); in[3] = in[2]; }
         }
-        if (pro == SP_ADALN) {
+        if (PRO_IS(SP_ADALN)) {
           const long long o = (long long)m * op.pro_ld + k;
           in[4] = ldcg4(op.pro_scale + o); in[5] = ldcg4(op.pro_scale + o + 4);
           in[6] = ldcg4(op.pro_shift + o); in[7] = ldcg4(op.pro_shift + o + 4);
         }
       };
-      auto chunk_store = [&](int c, const float4 (&in)[8]) {
-        if (c >= total) return;
-        int m, jloc, ch, k;
-        chunk_coord(c, m, jloc, ch, k);
+      auto chunk_store = [&](const ChunkRef& r, const float4* in) {
+        if (!r.valid) return;
+        const int m = r.m, jloc = r.jloc, ch = r.ch, k = r.k;
         float v[8];
         if (k >= K) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = 0.f;          // k >= K: the weight tile is zero there, keep 0 * x finite
-        } else if (pro == SP_SWIGLU) {
+        } else if (PRO_IS(SP_SWIGLU)) {
           v[0] = silu_f(in[0].x) * in[0].y; v[1] = silu_f(in[0].z) * in[0].w; v[2] = silu_f(in[1].x) * in[1].y; v[3] = silu_f(in[1].z) * in[1].w;
           v[4] = silu_f(in[2].x) * in[2].y; v[5] = silu_f(in[2].z) * in[2].w; v[6] = silu_f(in[3].x) * in[3].y; v[7] = silu_f(in[3].z) * in[3].w;
-        } else if (pro == SP_DPM) {
+        } else if (PRO_IS(SP_DPM)) {
           const float* zr = s_z + (m % op.dpm.B) * 64 + k;
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = zr[j];
-        } else if (pro == SP_WINDOW) {
+        } else if (PRO_IS(SP_WINDOW)) {
           const SCodec& w = op.cod;
-          const int b = m / w.T_out, t = m - b * w.T_out, j = k / w.cin, r = t * w.stride + j;
           v[0] = in[0].x; v[1] = in[0].y; v[2] = in[0].z; v[3] = in[0].w; v[4] = in[1].x; v[5] = in[1].y; v[6] = in[1].z; v[7] = in[1].w;
-          if (r >= w.ctx) {
+          if (r.fresh) {
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) v[jj] = v[jj] * w.alpha + w.beta;
           }
-          (void)b;
-        } else if (pro == SP_COMBINE) {
+        } else if (PRO_IS(SP_COMBINE)) {
           const float* cv = reinterpret_cast<const float*>(breg + cmb_off + cmb_part) + ((size_t)(m * count + jloc) * 64 + ch * 8);
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = cv[j];
@@ -834,7 +872,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
           if (norm) {
             const float inv = s_inv[m];
             const float w[8] = {in[2].x, in[2].y, in[2].z, in[2].w, in[3].x, in[3].y, in[3].z, in[3].w};
-            if (pro == SP_RMSNORM) {
+            if (PRO_IS(SP_RMSNORM)) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] *= inv * w[j];
             } else {
@@ -843,10 +881,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] = v[j] * inv * w[j] * (1.f + sc[j]) + sh[j];
             }
-          } else if (pro == SP_GELU) {
+          } else if (PRO_IS(SP_GELU)) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = gelu_erf_f(v[j]);
-          } else if (pro == SP_SILU) {
+          } else if (PRO_IS(SP_SILU)) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
           }
@@ -862,30 +900,76 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         *reinterpret_cast<uint4*>(blk + (m >> 3) * 1024 + (m & 7) * 128 + ((ch ^ (m & 7)) << 4)) = hv;
         *reinterpret_cast<uint4*>(blk + (rl >> 3) * 1024 + (rl & 7) * 128 + ((ch ^ (rl & 7)) << 4)) = lv;
       };
-      if (pro == SP_COMBINE) {
+      ChunkRef r0 = chunk_ref(wt), r1 = chunk_ref(wt + ST_WORKERS);
+      // every prologue but AdaLN needs <= 4 float4 per chunk: the upper halves of the two register batches take a third and a fourth chunk,
+      // so stages with up to 512 chunks (the LM's gate/up: 2 rows x 23 k-blocks) still stage their B operand with ONE L2 round trip
+      const bool wide = ST_WIDE && !PRO_IS(SP_ADALN) && total > 2 * ST_WORKERS;
+      ChunkRef r2 = chunk_ref(wide ? wt + 2 * ST_WORKERS : total), r3 = chunk_ref(wide ? wt + 3 * ST_WORKERS : total);
+      if (wide) asm volatile("" : "+l"(r2.xr), "+r"(r2.m), "+r"(r2.k), "+r"(r2.jloc), "+l"(r3.xr), "+r"(r3.m), "+r"(r3.k), "+r"(r3.jloc));
+      const int K4 = K >> 2;
+      int rot = (int)((blockIdx.x * 67u) % (unsigned)(K4 > 0 ? K4 : 1));     // statistics loads: every CTA starts at a different column
+      // materialise the descriptor-only values HERE, ahead of the barrier (the compiler would otherwise sink them to their first use)
+      asm volatile("" : "+l"(r0.xr), "+r"(r0.m), "+r"(r0.k), "+r"(r0.jloc), "+l"(r1.xr), "+r"(r1.m), "+r"(r1.k), "+r"(r1.jloc), "+r"(rot));
+      // attention merge: the (row, head) a warp merges first and the first accumulator item of every thread, again descriptor-only
+      const bool cmb = PRO_IS(SP_COMBINE);
+      const unsigned Ua = cmb ? att_vtotal(seq, M) : 1u;
+      const int cmb_Gq = cmb ? op.att.kv.q_heads / op.att.kv.kv_heads : 1, cmb_nkv = cmb ? op.att.kv.kv_heads : 1;
+      struct CmbPrep { const float* ml; unsigned c_first; int Pn; };
+      auto cmb_prep = [&](int pi) -> CmbPrep {
         const SAtt& a = op.att;
-        const unsigned Ua = att_vtotal(seq, M);
-        const int Gq = a.kv.q_heads / a.kv.kv_heads, nkv = a.kv.kv_heads;
+        const int m = pi / cmb_nh, hid = pi - m * cmb_nh;
+        const int h = ((kb_first / cmb_kbh) + hid) % a.kv.q_heads, g = h / cmb_Gq, hh = h - g * cmb_Gq;
+        unsigned pre = 0;
+        for (int mm = 0; mm < m; ++mm) { const unsigned n2 = att_tiles(seq, mm); if (n2) pre += (n2 + ST_ATT_SEGW) * (unsigned)cmb_nkv; }
+        const unsigned nt = att_tiles(seq, m);
+        CmbPrep r; r.ml = a.part_ml; r.c_first = 0; r.Pn = 0;
+        if (nt) {
+          const unsigned first = pre + (unsigned)g * (nt + ST_ATT_SEGW) + ST_ATT_SEGW;      // virtual unit of page 0 of this group
+          r.c_first = cta_of_unit(first, Ua, G);
+          r.Pn = (int)(cta_of_unit(first + nt - 1u, Ua, G) - r.c_first) + 1;
+          r.ml = a.part_ml + ((((size_t)m * cmb_nkv + g) * G) * 8 + hh) * 2;                 // slot stride 16 floats
+        }
+        return r;
+      };
+      struct CmbItem { const float* ap; int o4, pg, pi; };
+      const int out4 = M * count * 16;
+      int npg = 1;
+      while (npg * 2 * out4 <= ST_WORKERS && npg < 8) npg *= 2;
+      auto cmb_item = [&](int w0) -> CmbItem {
+        const SAtt& a = op.att;
+        CmbItem r;
+        r.o4 = w0 % out4; r.pg = w0 / out4;
+        const int m = r.o4 / (count * 16), q = r.o4 - m * (count * 16), jloc = q >> 4, q4 = q & 15;
+        int kb = kb_first + jloc; if (kb >= KB) kb -= KB;
+        const int k = kb * 64 + q4 * 4, h = k / a.hd, d = k - h * a.hd, g = h / cmb_Gq, hh = h - g * cmb_Gq;
+        r.pi = m * cmb_nh + ((kb_first % cmb_kbh) + jloc) / cmb_kbh;
+        r.ap = a.part_acc + ((((size_t)m * cmb_nkv + g) * G) * 8 + hh) * HD + d;             // slot stride 8 * 128 floats
+        return r;
+      };
+      CmbPrep cp0; cp0.ml = nullptr; cp0.c_first = 0; cp0.Pn = 0;
+      CmbItem ci0; ci0.ap = nullptr; ci0.o4 = 0; ci0.pg = 0; ci0.pi = 0;
+      if (cmb) {
+        if (ww < M * cmb_nh) cp0 = cmb_prep(ww);
+        if (wt < out4 * npg) ci0 = cmb_item(wt);
+        asm volatile("" : "+l"(cp0.ml), "+r"(cp0.c_first), "+r"(cp0.Pn), "+l"(ci0.ap), "+r"(ci0.o4), "+r"(ci0.pg), "+r"(ci0.pi));
+      }
+      grid_barrier();
+      if (cmb) {
+        const bool all_live = Ua >= G;                                        // every CTA owns at least one attention unit (long contexts)
         for (int pi = ww; pi < M * cmb_nh; pi += 4) {                     // one warp per (row, head)
-          const int m = pi / cmb_nh, hid = pi - m * cmb_nh;
-          const int h = ((kb_first / cmb_kbh) + hid) % a.kv.q_heads, g = h / Gq, hh = h - g * Gq;
-          unsigned pre = 0;
-          for (int mm = 0; mm < m; ++mm) { const unsigned n2 = att_tiles(seq, mm); if (n2) pre += (n2 + ST_ATT_SEGW) * (unsigned)nkv; }
-          const unsigned nt = att_tiles(seq, m);
-          int Pn = 0;
+          const CmbPrep cp = (pi == ww) ? cp0 : cmb_prep(pi);
+          const int Pn = cp.Pn;
           float* wrow = s_w + (size_t)pi * G;
-          if (nt) {
-            const unsigned first = pre + (unsigned)g * (nt + ST_ATT_SEGW) + ST_ATT_SEGW;      // virtual unit of page 0 of this group
-            const unsigned c_first = cta_of_unit(first, Ua, G);
-            Pn = (int)(cta_of_unit(first + nt - 1u, Ua, G) - c_first) + 1;
-            const float* ml = a.part_ml + ((((size_t)m * nkv + g) * G) * 8 + hh) * 2;     // slot stride 16 floats
+          if (Pn) {
+            const unsigned c_first = cp.c_first;
+            const float* ml = cp.ml;
             float2 mlv[8];                                                                // (max, sum) of slots lane, lane + 32, ...: ONE round trip
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int pq = lane + 32 * i;
               // slots of CTAs whose unit range is empty (fewer units than CTAs: short contexts) are never written: skip them
               const unsigned cc = c_first + (unsigned)pq;
-              const bool live = pq < Pn && (Ua * cc / G != Ua * (cc + 1u) / G);
+              const bool live = pq < Pn && (all_live || (Ua * cc / G != Ua * (cc + 1u) / G));
               mlv[i] = live ? __ldcg(reinterpret_cast<const float2*>(ml + (size_t)pq * 16)) : make_float2(-INFINITY, 0.f);
             }
             float mx = -INFINITY;
@@ -907,23 +991,16 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         }
         worker_sync();
         // merged[m][jloc][64] = sum_p w_p acc_p: work items (output float4, partial group) over all 128 threads, <= 16 loads in flight each
-        const int out4 = M * count * 16;
-        int npg = 1;
-        while (npg * 2 * out4 <= ST_WORKERS && npg < 8) npg *= 2;
         float4* s_cpart = reinterpret_cast<float4*>(breg + cmb_off);       // [npg][out4], npg * out4 <= 128
         for (int w0 = wt; w0 < out4 * npg; w0 += ST_WORKERS) {
-          const int o4 = w0 % out4, pg = w0 / out4;
-          const int m = o4 / (count * 16), r = o4 - m * (count * 16), jloc = r >> 4, q4 = r & 15;
-          int kb = kb_first + jloc; if (kb >= KB) kb -= KB;
-          const int k = kb * 64 + q4 * 4, h = k / a.hd, d = k - h * a.hd, g = h / Gq, hh = h - g * Gq;
-          const int pi = m * cmb_nh + ((kb_first % cmb_kbh) + jloc) / cmb_kbh;
+          const CmbItem ci = (w0 == wt) ? ci0 : cmb_item(w0);
+          const int o4 = ci.o4, pg = ci.pg, pi = ci.pi;
           const int Pn = s_pinfo[pi];
           const float* wrow = s_w + (size_t)pi * G;
-          const float* ap = a.part_acc + ((((size_t)m * nkv + g) * G) * 8 + hh) * HD + d;       // slot stride 8 * 128 floats
+          const float* ap = ci.ap;
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
           for (int p0 = pg; p0 < Pn; p0 += 16 * npg) {
             float4 v[16];
-#pragma unroll
             float wv[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -948,7 +1025,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         }
         worker_sync();
       }
-      if (pro == SP_WINDOW && u0 == 0) {                               // owner: next history = last ctx rows of every sample's window
+      if (PRO_IS(SP_WINDOW) && u0 == 0) {                               // owner: next history = last ctx rows of every sample's window
         const SCodec& w = op.cod;
         const int per = w.ctx * w.cin, nrow = w.ctx + w.T_in;
         for (int i = wt; i < (M / w.T_out) * per; i += ST_WORKERS) {
@@ -958,14 +1035,15 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         }
       }
       float4 in0[8], in1[8];
-      chunk_load(wt, in0);                                  // first two chunks of this thread: in flight during the statistics
-      chunk_load(wt + ST_WORKERS, in1);
+      chunk_load(r0, in0);                                  // first chunks of this thread: in flight during the statistics
+      chunk_load(r1, in1);
+      if (wide) { chunk_load(r2, in0 + 4); chunk_load(r3, in1 + 4); }
       if (tr) P.trace[(size_t)oi * ST_TRACE + 10] = clock64();
       if (norm) {
         // sum of squares of every full row: rows in pairs, <= 16 float4 per thread in flight (K <= 4096), further columns looped
-        const int K4 = K >> 2;
-        const int rot = (int)((blockIdx.x * 67u) % (unsigned)K4);      // every CTA starts at a different column: the 148 SMs read the same
-        for (int m0 = 0; m0 < M; m0 += 2) {                              // rows at the same moment, in phase they queue on the same L2 lines
+        // (rot: every CTA starts at a different column -- the 148 SMs read the same rows at the same moment, in phase they queue on the
+        //  same L2 lines)
+        for (int m0 = 0; m0 < M; m0 += 2) {
           float4 sv[2][8];
 #pragma unroll
           for (int r = 0; r < 2; ++r)
@@ -997,7 +1075,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
             worker_sync();
           }
         }
-      } else if (pro == SP_DPM) {
+      } else if (PRO_IS(SP_DPM)) {
         // z' for every sample (same arithmetic as dpm_update_proj_kernel); every CTA with work recomputes it, the owner of unit 0 publishes
         const SDpm& d = op.dpm;
         for (int i = wt; i < d.B * 64; i += ST_WORKERS) {
@@ -1025,18 +1103,22 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         worker_sync();
       }
       if (tr) P.trace[(size_t)oi * ST_TRACE + 2] = clock64();
-      chunk_store(wt, in0);
-      chunk_store(wt + ST_WORKERS, in1);
-      for (int c = wt + 2 * ST_WORKERS; c < total; c += 2 * ST_WORKERS) {
-        chunk_load(c, in0);
-        chunk_load(c + ST_WORKERS, in1);
-        chunk_store(c, in0);
-        chunk_store(c + ST_WORKERS, in1);
+      chunk_store(r0, in0);
+      chunk_store(r1, in1);
+      if (wide) { chunk_store(r2, in0 + 4); chunk_store(r3, in1 + 4); }
+#pragma unroll 1
+      for (int c = wt + (wide ? 4 : 2) * ST_WORKERS; c < total; c += 2 * ST_WORKERS) {
+        r0 = chunk_ref(c); r1 = chunk_ref(c + ST_WORKERS);
+        chunk_load(r0, in0);
+        chunk_load(r1, in1);
+        chunk_store(r0, in0);
+        chunk_store(r1, in1);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy smem writes -> visible to the tensor core
       worker_sync();
       if (wt == 0) mbar_arrive(&b_ready);
       if (tr) P.trace[(size_t)oi * ST_TRACE + 3] = clock64();
+      side_jobs();
       // ---------------- epilogue ----------------
       // bias / gamma / gate values do not depend on the MMA: fetch them while it runs (a gate load per segment AFTER the accumulators were
       // complete cost one L2 round trip per segment and made the CTAs that straddle a row-tile boundary arrive ~0.9 us late at every barrier)
@@ -1050,10 +1132,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         const bool live = rt <= rt_last && n < N;
         const bool from0 = (sg > 0) || kb_first == 0;
         e_bias[sg] = (live && from0 && op.bias) ? op.bias[n] : 0.f;
-        const float gam = (live && op.alpha_kind == SA_GAMMA) ? op.alpha[n] : 1.f;
+        const float gam = (live && ALPHA_IS(SA_GAMMA)) ? op.alpha[n] : 1.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          e_alpha[sg][j] = (live && op.alpha_kind == SA_GATE && j < M) ? ldcg1(op.alpha + (long long)j * op.lda + n) : gam;
+          e_alpha[sg][j] = (live && ALPHA_IS(SA_GATE) && j < M) ? ldcg1(op.alpha + (long long)j * op.lda + n) : gam;
       }
       mbar_wait_wd(&acc_full, gi & 1u, P.diag, 5u, (unsigned)oi, gi);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1075,14 +1157,14 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
             float bias, gam = 1.f;
             if (sg < EPRE) bias = sg == 0 ? e_bias[0] : (sg == 1 ? e_bias[1] : e_bias[2]);
             else bias = (from0 && op.bias) ? op.bias[n] : 0.f;
-            if (!pre && op.alpha_kind == SA_GAMMA) gam = op.alpha[n];
+            if (!pre && ALPHA_IS(SA_GAMMA)) gam = op.alpha[n];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int m = m0 + j;
               if (m < M) {
                 float val = __uint_as_float(rh[j]) + __uint_as_float(rl[j]) + bias;
                 if (pre) val *= sg == 0 ? e_alpha[0][j] : (sg == 1 ? e_alpha[1][j] : e_alpha[2][j]);
-                else if (op.alpha_kind == SA_GATE) val *= ldcg1(op.alpha + (long long)m * op.lda + n);
+                else if (ALPHA_IS(SA_GATE)) val *= ldcg1(op.alpha + (long long)m * op.lda + n);
                 else val *= gam;
                 float* yp = op.y + (long long)m * op.ldy + n;
                 if (op.store) *yp = val; else red_add_f32(yp, val);
@@ -1106,6 +1188,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
 }
+#undef PRO_IS
+#undef KIND_IS
+#undef ALPHA_IS
+
 
 // ---------------------------------------------------------------------------------------------------------------------------------
 // micro-benchmark: issue rate / execution time of tcgen05.mma 128 x nB x 16 from shared memory (operands are whatever the buffer holds)
