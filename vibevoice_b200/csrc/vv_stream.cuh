@@ -794,7 +794,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       const int cmb_nh = ((kb_first % cmb_kbh) + count - 1) / cmb_kbh + 1;   // distinct heads among this CTA's k-blocks
       const int cmb_off = cmb_base + ((M * cmb_nh * (int)G * 4 + 15) & ~15);
       const int cmb_part = (M * count * 256 > 2048) ? M * count * 256 : 2048;     // bytes of the group partial sums (npg * out4 float4)
-      struct ChunkRef { const float* xr; int m, jloc, ch, k; bool valid, live, fresh; };
+      struct ChunkRef { const float* xr; const float* pw; const float* psc; const float* psh; int m, jloc, ch, k; bool valid, live, fresh; };
       auto chunk_ref = [&](int c) -> ChunkRef {             // coordinates + source address of chunk c: descriptor-only arithmetic
         ChunkRef r;
         r.m = c / (count * 8);
@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         r.valid = c < total;
         r.live = r.valid && r.k < K && !PRO_IS(SP_DPM) && !PRO_IS(SP_COMBINE);
         r.fresh = false;
-        r.xr = op.x;
+        r.xr = op.x; r.pw = nullptr; r.psc = nullptr; r.psh = nullptr;
         if (!r.live) return r;
         if (PRO_IS(SP_WINDOW)) {
           const SCodec& w = op.cod;
@@ -816,6 +816,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
           r.xr = op.x + (long long)r.m * op.ldx + 2 * r.k;
         } else {
           r.xr = op.x + (long long)r.m * op.ldx + r.k;
+          if (norm && op.pro_w) r.pw = op.pro_w + r.k;
+          if (PRO_IS(SP_ADALN)) {
+            const long long o = (long long)r.m * op.pro_ld + r.k;
+            r.psc = op.pro_scale + o; r.psh = op.pro_shift + o;
+          }
         }
         return r;
       };
@@ -833,13 +838,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         }
         in[0] = ldcg4(xr); in[1] = ldcg4(xr + 4);
         if (norm) {
-          if (op.pro_w) { in[2] = *reinterpret_cast<const float4*>(op.pro_w + k); in[3] = *reinterpret_cast<const float4*>(op.pro_w + k + 4); }
+          if (r.pw) { in[2] = *reinterpret_cast<const float4*>(r.pw); in[3] = *reinterpret_cast<const float4*>(r.pw + 4); }
           else { in[2] = make_float4(1.f, 1.f, 1.f, 1.f); in[3] = in[2]; }
         }
         if (PRO_IS(SP_ADALN)) {
-          const long long o = (long long)m * op.pro_ld + k;
-          in[4] = ldcg4(op.pro_scale + o); in[5] = ldcg4(op.pro_scale + o + 4);
-          in[6] = ldcg4(op.pro_shift + o); in[7] = ldcg4(op.pro_shift + o + 4);
+          in[4] = ldcg4(r.psc); in[5] = ldcg4(r.psc + 4);
+          in[6] = ldcg4(r.psh); in[7] = ldcg4(r.psh + 4);
         }
       };
       auto chunk_store = [&](const ChunkRef& r, const float4* in) {
@@ -910,6 +914,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       int rot = (int)((blockIdx.x * 67u) % (unsigned)(K4 > 0 ? K4 : 1));     // statistics loads: every CTA starts at a different column
       // materialise the descriptor-only values HERE, ahead of the barrier (the compiler would otherwise sink them to their first use)
       asm volatile("" : "+l"(r0.xr), "+r"(r0.m), "+r"(r0.k), "+r"(r0.jloc), "+l"(r1.xr), "+r"(r1.m), "+r"(r1.k), "+r"(r1.jloc), "+r"(rot));
+      if (norm) asm volatile("" : "+l"(r0.pw), "+l"(r0.psc), "+l"(r0.psh), "+l"(r1.pw), "+l"(r1.psc), "+l"(r1.psh));
       // attention merge: the (row, head) a warp merges first and the first accumulator item of every thread, again descriptor-only
       const bool cmb = PRO_IS(SP_COMBINE);
       const unsigned Ua = cmb ? att_vtotal(seq, M) : 1u;
@@ -1043,6 +1048,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         // sum of squares of every full row: rows in pairs, <= 16 float4 per thread in flight (K <= 4096), further columns looped
         // (rot: every CTA starts at a different column -- the 148 SMs read the same rows at the same moment, in phase they queue on the
         //  same L2 lines)
+        const float* const sx = op.x; const long long sldx = op.ldx;
         for (int m0 = 0; m0 < M; m0 += 2) {
           float4 sv[2][8];
 #pragma unroll
@@ -1051,7 +1057,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
             for (int i = 0; i < 8; ++i) {
               const int q = wt + i * ST_WORKERS;
               int qr = q + rot; if (qr >= K4) qr -= K4;
-              sv[r][i] = (m0 + r < M && q < K4) ? ldcg4(op.x + (long long)(m0 + r) * op.ldx + 4 * qr) : make_float4(0.f, 0.f, 0.f, 0.f);
+              sv[r][i] = (m0 + r < M && q < K4) ? ldcg4(sx + (long long)(m0 + r) * sldx + 4 * qr) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
           float ss[2] = {0.f, 0.f};
 #pragma unroll
@@ -1061,7 +1067,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
             if (m0 + r < M)
               for (int q = wt + 8 * ST_WORKERS; q < K4; q += ST_WORKERS) {
                 int qr = q + rot; if (qr >= K4) qr -= K4;
-                const float4 v = ldcg4(op.x + (long long)(m0 + r) * op.ldx + 4 * qr);
+                const float4 v = ldcg4(sx + (long long)(m0 + r) * sldx + 4 * qr);
                 ss[r] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
               }
             ss[r] = warp_sum(ss[r]);
@@ -1125,17 +1131,29 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       const int rt_last = (int)((u1 - 1u) / (unsigned)KB);
       constexpr int EPRE = 3;                                 // segments whose operands are prefetched (more: loaded in place)
       float e_bias[EPRE], e_alpha[EPRE][8];
+      // (descriptor fields in registers: read through `op` they are re-loaded from shared memory after every asm statement -- this block
+      //  alone was 200 instructions and 12 % of a worker warp's time in the sampler, profiles/r02_prof_stream2_*)
+      const float* const e_al = op.alpha; const float* const e_bs = op.bias; float* const e_y = op.y;
+      const long long e_lda = op.lda, e_ldy = op.ldy;
+      const bool e_gate = ALPHA_IS(SA_GATE), e_gamma = ALPHA_IS(SA_GAMMA), e_store = op.store != 0;
 #pragma unroll
       for (int sg = 0; sg < EPRE; ++sg) {
         const int rt = rt_first + sg;
         const int n = rt * 128 + wq * 32 + lane;
         const bool live = rt <= rt_last && n < N;
         const bool from0 = (sg > 0) || kb_first == 0;
-        e_bias[sg] = (live && from0 && op.bias) ? op.bias[n] : 0.f;
-        const float gam = (live && ALPHA_IS(SA_GAMMA)) ? op.alpha[n] : 1.f;
+        e_bias[sg] = (live && from0 && e_bs) ? e_bs[n] : 0.f;
+        const float gam = (live && e_gamma) ? e_al[n] : 1.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          e_alpha[sg][j] = (live && ALPHA_IS(SA_GATE) && j < M) ? ldcg1(op.alpha + (long long)j * op.lda + n) : gam;
+        for (int j = 0; j < 8; ++j) e_alpha[sg][j] = gam;
+        if (e_gate && live) {
+          const float* gp = e_al + n;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j < M) e_alpha[sg][j] = ldcg1(gp);
+            gp += e_lda;
+          }
+        }
       }
       mbar_wait_wd(&acc_full, gi & 1u, P.diag, 5u, (unsigned)oi, gi);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1156,18 +1174,18 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
             const bool pre = sg < EPRE && m0 == 0;
             float bias, gam = 1.f;
             if (sg < EPRE) bias = sg == 0 ? e_bias[0] : (sg == 1 ? e_bias[1] : e_bias[2]);
-            else bias = (from0 && op.bias) ? op.bias[n] : 0.f;
-            if (!pre && ALPHA_IS(SA_GAMMA)) gam = op.alpha[n];
+            else bias = (from0 && e_bs) ? e_bs[n] : 0.f;
+            if (!pre && e_gamma) gam = e_al[n];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int m = m0 + j;
               if (m < M) {
                 float val = __uint_as_float(rh[j]) + __uint_as_float(rl[j]) + bias;
                 if (pre) val *= sg == 0 ? e_alpha[0][j] : (sg == 1 ? e_alpha[1][j] : e_alpha[2][j]);
-                else if (ALPHA_IS(SA_GATE)) val *= ldcg1(op.alpha + (long long)m * op.lda + n);
+                else if (e_gate) val *= ldcg1(e_al + (long long)m * e_lda + n);
                 else val *= gam;
-                float* yp = op.y + (long long)m * op.ldy + n;
-                if (op.store) *yp = val; else red_add_f32(yp, val);
+                float* yp = e_y + (long long)m * e_ldy + n;
+                if (e_store) *yp = val; else red_add_f32(yp, val);
               }
             }
           }
