@@ -4,4 +4,5 @@
     vibevoice.modular.modeling_vibevoice_inference.VibeVoiceForConditionalGenerationInference
     vibevoice.processor.vibevoice_processor.VibeVoiceProcessor
 and `demo/gradio_demo.py` additionally `vibevoice.modular.streamer.AudioStreamer`; those names resolve here to the B200
-implementations.  Training / conversion / streaming-0.5B modules of the reference are out of scope."""
+implementations; `vibevoice.modular.modeling_vibevoice_streaming_inference` serves the streaming-0.5B variant the same way
+(`demo/streaming_inference_from_file.py`).  Training and conversion modules of the reference are out of scope."""

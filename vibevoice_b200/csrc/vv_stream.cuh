@@ -1049,21 +1049,26 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         // (rot: every CTA starts at a different column -- the 148 SMs read the same rows at the same moment, in phase they queue on the
         //  same L2 lines)
         const float* const sx = op.x; const long long sldx = op.ldx;
+        const int ngrp = (K4 + ST_WORKERS - 1) / ST_WORKERS;           // column groups of 128 float4 that exist (uniform; K = 1536: 3 of 8)
         for (int m0 = 0; m0 < M; m0 += 2) {
           float4 sv[2][8];
 #pragma unroll
-          for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int q = wt + i * ST_WORKERS;
-              int qr = q + rot; if (qr >= K4) qr -= K4;
-              sv[r][i] = (m0 + r < M && q < K4) ? ldcg4(sx + (long long)(m0 + r) * sldx + 4 * qr) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+          for (int i = 0; i < 8; ++i) {
+            if (i >= ngrp) break;
+            const int q = wt + i * ST_WORKERS;
+            int qr = q + rot; if (qr >= K4) qr -= K4;
+            const float* sp = sx + (long long)m0 * sldx + 4 * qr;
+            sv[0][i] = q < K4 ? ldcg4(sp) : make_float4(0.f, 0.f, 0.f, 0.f);
+            sv[1][i] = (m0 + 1 < M && q < K4) ? ldcg4(sp + sldx) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           float ss[2] = {0.f, 0.f};
 #pragma unroll
           for (int r = 0; r < 2; ++r) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) ss[r] += sv[r][i].x * sv[r][i].x + sv[r][i].y * sv[r][i].y + sv[r][i].z * sv[r][i].z + sv[r][i].w * sv[r][i].w;
+            for (int i = 0; i < 8; ++i) {
+              if (i >= ngrp) break;
+              ss[r] += sv[r][i].x * sv[r][i].x + sv[r][i].y * sv[r][i].y + sv[r][i].z * sv[r][i].z + sv[r][i].w * sv[r][i].w;
+            }
             if (m0 + r < M)
               for (int q = wt + 8 * ST_WORKERS; q < K4; q += ST_WORKERS) {
                 int qr = q + rot; if (qr >= K4) qr -= K4;
@@ -1176,17 +1181,17 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
             if (sg < EPRE) bias = sg == 0 ? e_bias[0] : (sg == 1 ? e_bias[1] : e_bias[2]);
             else bias = (from0 && e_bs) ? e_bs[n] : 0.f;
             if (!pre && e_gamma) gam = e_al[n];
+            float* yp = e_y + (long long)m0 * e_ldy + n;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int m = m0 + j;
-              if (m < M) {
-                float val = __uint_as_float(rh[j]) + __uint_as_float(rl[j]) + bias;
-                if (pre) val *= sg == 0 ? e_alpha[0][j] : (sg == 1 ? e_alpha[1][j] : e_alpha[2][j]);
-                else if (e_gate) val *= ldcg1(e_al + (long long)m * e_lda + n);
-                else val *= gam;
-                float* yp = e_y + (long long)m * e_ldy + n;
-                if (e_store) *yp = val; else red_add_f32(yp, val);
-              }
+              if (m >= M) break;                                   // (uniform: rows beyond M cost no instructions)
+              float val = __uint_as_float(rh[j]) + __uint_as_float(rl[j]) + bias;
+              if (pre) val *= sg == 0 ? e_alpha[0][j] : (sg == 1 ? e_alpha[1][j] : e_alpha[2][j]);
+              else if (e_gate) val *= ldcg1(e_al + (long long)m * e_lda + n);
+              else val *= gam;
+              if (e_store) *yp = val; else red_add_f32(yp, val);
+              yp += e_ldy;
             }
           }
         }
