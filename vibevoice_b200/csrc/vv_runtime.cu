@@ -432,9 +432,9 @@ constexpr unsigned SF_LM = sfeat({SP_NONE, SP_RMSNORM, SP_SWIGLU, SP_COMBINE}, {
 constexpr unsigned SF_CODEC = sfeat({SP_NONE, SP_WINDOW, SP_RMSNORM, SP_GELU}, {SK_GEMV, SK_NOP, SK_MIX}, {SA_ONE, SA_GAMMA});
 constexpr unsigned SF_ALL = 0xffffffffu;
 typedef void (*StreamFn)(SParams);
-static const struct { unsigned feat; StreamFn fn; const char* name; } STREAM_VARIANTS[] = {
-  {SF_SAMP, stream_kernel<SF_SAMP>, "sampler"}, {SF_LM, stream_kernel<SF_LM>, "lm"}, {SF_CODEC, stream_kernel<SF_CODEC>, "codec"},
-  {SF_ALL, stream_kernel<SF_ALL>, "all"}};
+static const struct { unsigned feat; StreamFn fn; StreamFn fn_trace; const char* name; } STREAM_VARIANTS[] = {
+  {SF_SAMP, stream_kernel<SF_SAMP, false>, stream_kernel<SF_SAMP, true>, "sampler"}, {SF_LM, stream_kernel<SF_LM, false>, stream_kernel<SF_LM, true>, "lm"},
+  {SF_CODEC, stream_kernel<SF_CODEC, false>, stream_kernel<SF_CODEC, true>, "codec"}, {SF_ALL, stream_kernel<SF_ALL, false>, stream_kernel<SF_ALL, true>, "all"}};
 constexpr int N_STREAM_VARIANTS = 4;
 
 static int finish_stream(StreamBuilder& b, vv_ctx::StreamProg* pr) {
@@ -491,6 +491,7 @@ static int finish_stream(StreamBuilder& b, vv_ctx::StreamProg* pr) {
   if (!b.tmaps.empty()) CK(cudaMemcpy(pr->tmaps, b.tmaps.data(), b.tmaps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(pr->ops, b.ops.data(), b.ops.size() * sizeof(SOp), cudaMemcpyHostToDevice));
   CK(cudaFuncSetAttribute(STREAM_VARIANTS[pr->variant].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+  CK(cudaFuncSetAttribute(STREAM_VARIANTS[pr->variant].fn_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
   return 0;
 }
 
@@ -513,7 +514,7 @@ static int launch_stream(const L& l, const vv_ctx::StreamProg& pr, int op_begin 
   P.trace2 = P.trace ? c->st_trace2 : nullptr;
   if (P.trace) c->st_trace_last_ops = pr.n_ops;
   c->launches++;
-  CK(cudaLaunchKernelEx(&cfg, STREAM_VARIANTS[pr.variant].fn, P));
+  CK(cudaLaunchKernelEx(&cfg, P.trace ? STREAM_VARIANTS[pr.variant].fn_trace : STREAM_VARIANTS[pr.variant].fn, P));
   return 0;
 }
 

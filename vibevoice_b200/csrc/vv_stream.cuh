@@ -239,6 +239,12 @@ VV_DEVINL unsigned att_tiles(const SeqView& q, int m) { return q.row_mode[m] ? (
 // order.  CTAs take contiguous ranges of virtual units, so a CTA that also gets the few pages of a short (CFG-negative) row gets
 // correspondingly fewer pages of the long one (measured before: the CTA owning both short groups arrived 8 us late at every layer's barrier).
 constexpr unsigned ST_ATT_SEGW = 4;
+#ifndef ST_PRE_SO
+#define ST_PRE_SO 0       // 1: swizzled B-operand offsets precomputed ahead of the barrier (sampler +0.4 %, LM +0.5 % slower: off)
+#endif
+#ifndef ST_PF_BREAK
+#define ST_PF_BREAK 0     // 1: epilogue-operand prefetch stops at the last live segment (no gain: off)
+#endif
 #ifndef ST_WIDE
 #define ST_WIDE 0      // 1: 4 activation chunks per thread in one L2 round trip. Measured on one box (tools/ab_run.sh): the LM gains 0.5 %, but the extra
                        // 1 900 instructions cost the sampler 4.7 % (instruction cache) -> off
@@ -290,7 +296,8 @@ VV_DEVINL void st_part(const SOp& op, unsigned& u0, unsigned& u1, int& KB) {
 // FEAT = the stage kinds / prologues / epilogue scalings a program may use (bit SP_x, bit 16 + SK_x, bit 24 + SA_x).  One instantiation per
 // program family: the all-features kernel is 224 KB of SASS and every stage runs its path exactly once, so the instruction cache misses
 // on most of it -- measured on one box (tools/ab_run.sh): +1 900 instructions of code a program never executes cost the sampler 4.7 %.
-template <unsigned FEAT>
+// TRACE = per-stage clock stamps compiled in (tools/stream_trace.py); the production instantiations carry none of that code.
+template <unsigned FEAT, bool TRACE>
 __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
 #define PRO_IS(x) (((FEAT >> (x)) & 1u) != 0u && pro == (x))
 #define KIND_IS(x) (((FEAT >> (16 + (x))) & 1u) != 0u && op.kind == (x))
@@ -392,7 +399,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
           // tile-major weights: unit u = (row tile, k-block) is the contiguous 16 KB block u, so a CTA streams one contiguous range
           tma_load_2d(ring + (size_t)slot * ST_TILE, tmap, 0, (int)(u * 128), &full_bar[slot], policy);
         }
-        if (P.trace && (int)blockIdx.x == P.trace_cta) P.trace[(size_t)oi * ST_TRACE + 9] = clock64();
+        if (TRACE && P.trace && (int)blockIdx.x == P.trace_cta) P.trace[(size_t)oi * ST_TRACE + 9] = clock64();
       }
     }
   } else if (warp == 1) {
@@ -428,7 +435,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       const unsigned bstep = (unsigned)(nB * 128) >> 4;          // descriptor start-address units (16 B) per k-block of the B operand
       mbar_wait_wd(&b_ready, gi & 1u, P.diag, 2u, (unsigned)oi, gi);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const bool tr = P.trace && (int)blockIdx.x == P.trace_cta && lane == 0;
+      const bool tr = TRACE && P.trace && (int)blockIdx.x == P.trace_cta && lane == 0;
       if (tr) P.trace[(size_t)oi * ST_TRACE + 6] = clock64();
       int kb = kb_first;                                         // k-block of the current unit; jloc = position in the staged B region
       unsigned jloc = 0, dcol = tmem, fresh = 1;
@@ -486,7 +493,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       if (oi + 1 < P.n_ops && wt < OPCH)
         cp_async16(s_opbuf[(oi + 1) & 1] + wt * 16, reinterpret_cast<const unsigned char*>(P.ops + oi + 1) + wt * 16, 16);
       cp_async_commit();
-      const bool tr = P.trace && (int)blockIdx.x == P.trace_cta && wt == 0;
+      const bool tr = TRACE && P.trace && (int)blockIdx.x == P.trace_cta && wt == 0;
       if (tr) P.trace[(size_t)oi * ST_TRACE + 0] = clock64();
       // the grid barrier sits as LATE as possible inside every stage: everything that only depends on the descriptor (unit range, chunk
       // coordinates and addresses: a dozen integer divisions, ~0.6 us) is computed by the waiting workers BEFORE it
@@ -494,7 +501,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       if (op.sync_before) {
         bar_target += G;
         if (wt == 0) {
-          if (P.trace2) P.trace2[((size_t)oi * G + blockIdx.x) * 2] = gtime_ns();
+          if (TRACE && P.trace2) P.trace2[((size_t)oi * G + blockIdx.x) * 2] = gtime_ns();
           red_add_release_u32(P.bar_count, 1u);
         }
       }
@@ -512,7 +519,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
                 else if (t - t0 > 6000000000ll) st_die(P.diag, 4u, (unsigned)oi, bar_target, ld_acquire_u32(P.bar_count));
               }
             }
-            if (P.trace2) P.trace2[((size_t)oi * G + blockIdx.x) * 2 + 1] = gtime_ns();
+            if (TRACE && P.trace2) P.trace2[((size_t)oi * G + blockIdx.x) * 2 + 1] = gtime_ns();
           }
           worker_sync();
         }
@@ -794,7 +801,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       const int cmb_nh = ((kb_first % cmb_kbh) + count - 1) / cmb_kbh + 1;   // distinct heads among this CTA's k-blocks
       const int cmb_off = cmb_base + ((M * cmb_nh * (int)G * 4 + 15) & ~15);
       const int cmb_part = (M * count * 256 > 2048) ? M * count * 256 : 2048;     // bytes of the group partial sums (npg * out4 float4)
-      struct ChunkRef { const float* xr; const float* pw; const float* psc; const float* psh; int m, jloc, ch, k; bool valid, live, fresh; };
+      struct ChunkRef { const float* xr; const float* pw; const float* psc; const float* psh; int m, jloc, ch, k, so_hi, so_lo; bool valid, live, fresh; };
       auto chunk_ref = [&](int c) -> ChunkRef {             // coordinates + source address of chunk c: descriptor-only arithmetic
         ChunkRef r;
         r.m = c / (count * 8);
@@ -803,6 +810,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         int kb = kb_first + r.jloc; if (kb >= KB) kb -= KB;
         r.k = kb * 64 + r.ch * 8;
         r.valid = c < total;
+        r.so_hi = 0; r.so_lo = 0;
+        if (ST_PRE_SO) {                                      // swizzled B-operand offsets of the hi row m and the lo row half + m
+          const int rl = half + r.m;
+          r.so_hi = r.jloc * (nB * 128) + (r.m >> 3) * 1024 + (r.m & 7) * 128 + ((r.ch ^ (r.m & 7)) << 4);
+          r.so_lo = r.jloc * (nB * 128) + (rl >> 3) * 1024 + (rl & 7) * 128 + ((r.ch ^ (rl & 7)) << 4);
+        }
         r.live = r.valid && r.k < K && !PRO_IS(SP_DPM) && !PRO_IS(SP_COMBINE);
         r.fresh = false;
         r.xr = op.x; r.pw = nullptr; r.psc = nullptr; r.psh = nullptr;
@@ -899,10 +912,15 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         const uint4 hv = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
         const uint4 lv = make_uint4(pack_bf16(v[0] - h[0], v[1] - h[1]), pack_bf16(v[2] - h[2], v[3] - h[3]),
                                     pack_bf16(v[4] - h[4], v[5] - h[5]), pack_bf16(v[6] - h[6], v[7] - h[7]));
+#if ST_PRE_SO
+        *reinterpret_cast<uint4*>(breg + r.so_hi) = hv;
+        *reinterpret_cast<uint4*>(breg + r.so_lo) = lv;
+#else
         unsigned char* blk = breg + (size_t)jloc * (size_t)(nB * 128);
         const int rl = half + m;
         *reinterpret_cast<uint4*>(blk + (m >> 3) * 1024 + (m & 7) * 128 + ((ch ^ (m & 7)) << 4)) = hv;
         *reinterpret_cast<uint4*>(blk + (rl >> 3) * 1024 + (rl & 7) * 128 + ((ch ^ (rl & 7)) << 4)) = lv;
+#endif
       };
       ChunkRef r0 = chunk_ref(wt), r1 = chunk_ref(wt + ST_WORKERS);
       // every prologue but AdaLN needs <= 4 float4 per chunk: the upper halves of the two register batches take a third and a fourth chunk,
@@ -914,6 +932,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       int rot = (int)((blockIdx.x * 67u) % (unsigned)(K4 > 0 ? K4 : 1));     // statistics loads: every CTA starts at a different column
       // materialise the descriptor-only values HERE, ahead of the barrier (the compiler would otherwise sink them to their first use)
       asm volatile("" : "+l"(r0.xr), "+r"(r0.m), "+r"(r0.k), "+r"(r0.jloc), "+l"(r1.xr), "+r"(r1.m), "+r"(r1.k), "+r"(r1.jloc), "+r"(rot));
+      if (ST_PRE_SO) asm volatile("" : "+r"(r0.so_hi), "+r"(r0.so_lo), "+r"(r1.so_hi), "+r"(r1.so_lo));
       if (norm) asm volatile("" : "+l"(r0.pw), "+l"(r0.psc), "+l"(r0.psh), "+l"(r1.pw), "+l"(r1.psc), "+l"(r1.psh));
       // attention merge: the (row, head) a warp merges first and the first accumulator item of every thread, again descriptor-only
       const bool cmb = PRO_IS(SP_COMBINE);
@@ -1049,12 +1068,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         // (rot: every CTA starts at a different column -- the 148 SMs read the same rows at the same moment, in phase they queue on the
         //  same L2 lines)
         const float* const sx = op.x; const long long sldx = op.ldx;
-        const int ngrp = (K4 + ST_WORKERS - 1) / ST_WORKERS;           // column groups of 128 float4 that exist (uniform; K = 1536: 3 of 8)
         for (int m0 = 0; m0 < M; m0 += 2) {
           float4 sv[2][8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            if (i >= ngrp) break;
             const int q = wt + i * ST_WORKERS;
             int qr = q + rot; if (qr >= K4) qr -= K4;
             const float* sp = sx + (long long)m0 * sldx + 4 * qr;
@@ -1066,7 +1083,6 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
           for (int r = 0; r < 2; ++r) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              if (i >= ngrp) break;
               ss[r] += sv[r][i].x * sv[r][i].x + sv[r][i].y * sv[r][i].y + sv[r][i].z * sv[r][i].z + sv[r][i].w * sv[r][i].w;
             }
             if (m0 + r < M)
@@ -1144,6 +1160,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
 #pragma unroll
       for (int sg = 0; sg < EPRE; ++sg) {
         const int rt = rt_first + sg;
+#if ST_PF_BREAK
+        if (rt > rt_last) break;
+#endif
         const int n = rt * 128 + wq * 32 + lane;
         const bool live = rt <= rt_last && n < N;
         const bool from0 = (sg > 0) || kb_first == 0;
@@ -1155,7 +1174,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
           const float* gp = e_al + n;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            if (j < M) e_alpha[sg][j] = ldcg1(gp);
+            if (j >= M) break;
+            e_alpha[sg][j] = ldcg1(gp);
             gp += e_lda;
           }
         }
@@ -1185,7 +1205,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int m = m0 + j;
-              if (m >= M) break;                                   // (uniform: rows beyond M cost no instructions)
+              // uniform early exit: the dead rows of an M = 2 stage were ~50 predicated-off instructions -- 6 % of the sampler's time on
+              // this instruction-fetch-bound path (profiles/r02_ab_epilogue_rows_stats_groups.txt)
+              if (m >= M) break;
               float val = __uint_as_float(rh[j]) + __uint_as_float(rl[j]) + bias;
               if (pre) val *= sg == 0 ? e_alpha[0][j] : (sg == 1 ? e_alpha[1][j] : e_alpha[2][j]);
               else if (e_gate) val *= ldcg1(e_al + (long long)m * e_lda + n);
