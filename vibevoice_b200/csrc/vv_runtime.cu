@@ -430,12 +430,15 @@ constexpr unsigned sfeat(std::initializer_list<int> pros, std::initializer_list<
 constexpr unsigned SF_SAMP = sfeat({SP_NONE, SP_ADALN, SP_SWIGLU, SP_DPM}, {SK_GEMV, SK_NOP}, {SA_ONE, SA_GATE});
 constexpr unsigned SF_LM = sfeat({SP_NONE, SP_RMSNORM, SP_SWIGLU, SP_COMBINE}, {SK_GEMV, SK_NOP, SK_ATTN}, {SA_ONE});
 constexpr unsigned SF_CODEC = sfeat({SP_NONE, SP_WINDOW, SP_RMSNORM, SP_GELU}, {SK_GEMV, SK_NOP, SK_MIX}, {SA_ONE, SA_GAMMA});
-constexpr unsigned SF_ALL = 0xffffffffu;
+constexpr unsigned SF_HD128 = 1u << 30;          // every attention stage has head_dim 128 (compile-time loop bounds)
+constexpr unsigned SF_LM128 = SF_LM | SF_HD128;
+constexpr unsigned SF_ALL = 0xffffffffu & ~SF_HD128;
 typedef void (*StreamFn)(SParams);
 static const struct { unsigned feat; StreamFn fn; StreamFn fn_trace; const char* name; } STREAM_VARIANTS[] = {
-  {SF_SAMP, stream_kernel<SF_SAMP, false>, stream_kernel<SF_SAMP, true>, "sampler"}, {SF_LM, stream_kernel<SF_LM, false>, stream_kernel<SF_LM, true>, "lm"},
+  {SF_SAMP, stream_kernel<SF_SAMP, false>, stream_kernel<SF_SAMP, true>, "sampler"},
+  {SF_LM128, stream_kernel<SF_LM128, false>, stream_kernel<SF_LM128, true>, "lm (head_dim 128)"}, {SF_LM, stream_kernel<SF_LM, false>, stream_kernel<SF_LM, true>, "lm"},
   {SF_CODEC, stream_kernel<SF_CODEC, false>, stream_kernel<SF_CODEC, true>, "codec"}, {SF_ALL, stream_kernel<SF_ALL, false>, stream_kernel<SF_ALL, true>, "all"}};
-constexpr int N_STREAM_VARIANTS = 4;
+constexpr int N_STREAM_VARIANTS = 5;
 
 static int finish_stream(StreamBuilder& b, vv_ctx::StreamProg* pr) {
   vv_ctx* c = b.c;
@@ -463,11 +466,15 @@ static int finish_stream(StreamBuilder& b, vv_ctx::StreamProg* pr) {
     if (U * (G + 1) >= (1ll << 32)) return fail(VV_ERR_INVALID, "stream: stage [%d x %d] has too many tiles for 32-bit scheduling", o.N, o.K);
   }
   unsigned feat = 0;
-  for (const SOp& o : b.ops) feat |= (1u << o.pro) | (1u << (16 + o.kind)) | (1u << (24 + o.alpha_kind));
+  bool hd128 = true;
+  for (const SOp& o : b.ops) {
+    feat |= (1u << o.pro) | (1u << (16 + o.kind)) | (1u << (24 + o.alpha_kind));
+    if ((o.kind == SK_ATTN || o.pro == SP_COMBINE || o.rope_rows > 0) && o.att.hd != 128) hd128 = false;
+  }
   pr->variant = N_STREAM_VARIANTS - 1;
   if (!getenv("VV_STREAM_GENERIC"))
     for (int v = 0; v < N_STREAM_VARIANTS; ++v)
-      if ((feat & ~STREAM_VARIANTS[v].feat) == 0) { pr->variant = v; break; }
+      if ((feat & ~STREAM_VARIANTS[v].feat) == 0 && (hd128 || !(STREAM_VARIANTS[v].feat & SF_HD128))) { pr->variant = v; break; }
   if (getenv("VV_VERBOSE")) fprintf(stderr, "[vv] stream program: %zu stages, features %08x -> kernel variant '%s'\n", b.ops.size(), feat, STREAM_VARIANTS[pr->variant].name);
   cudaFuncAttributes fa;
   CK(cudaFuncGetAttributes(&fa, STREAM_VARIANTS[pr->variant].fn));

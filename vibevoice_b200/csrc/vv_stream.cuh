@@ -302,6 +302,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
 #define PRO_IS(x) (((FEAT >> (x)) & 1u) != 0u && pro == (x))
 #define KIND_IS(x) (((FEAT >> (16 + (x))) & 1u) != 0u && op.kind == (x))
 #define ALPHA_IS(x) (((FEAT >> (24 + (x))) & 1u) != 0u && op.alpha_kind == (x))
+// bit 30: every attention stage of the program has head_dim 128 -> compile-time loop bounds (the run-time-bounded loops of the 64 / 128
+// generalisation cost the LM stack 13 % when they were introduced)
+#define ATT_HD(a) ((((FEAT >> 30) & 1u) != 0u) ? 128 : (a).hd)
   extern __shared__ unsigned char st_raw[];
   __shared__ unsigned long long full_bar[ST_MAX_STAGES], empty_bar[ST_MAX_STAGES];
   __shared__ unsigned long long b_ready, acc_full;
@@ -371,13 +374,13 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
             for (int t = sg.t0; t < sg.t1; ++t) {
               const int page = a.kv.page_table[(size_t)sg.m * a.kv.max_pages + t];
               const int row0 = (int)(a.row_base + (unsigned)((page * a.kv.kv_heads + sg.g) * KV_PAGE));
-              const unsigned pbytes = (unsigned)(KV_PAGE * a.hd * 2);
+              const unsigned pbytes = (unsigned)(KV_PAGE * ATT_HD(a) * 2);
               unsigned slot = acquire_slot(oi, pbytes);
               tma_load_2d(ring + (size_t)slot * ST_TILE, a.tmap_k, 0, row0, &full_bar[slot], policy_kv);
-              if (a.hd > 64) tma_load_2d(ring + (size_t)slot * ST_TILE + 8192, a.tmap_k, 64, row0, &full_bar[slot], policy_kv);
+              if (ATT_HD(a) > 64) tma_load_2d(ring + (size_t)slot * ST_TILE + 8192, a.tmap_k, 64, row0, &full_bar[slot], policy_kv);
               slot = acquire_slot(oi, pbytes);
               tma_load_2d(ring + (size_t)slot * ST_TILE, a.tmap_v, 0, row0, &full_bar[slot], policy_kv);
-              if (a.hd > 64) tma_load_2d(ring + (size_t)slot * ST_TILE + 8192, a.tmap_v, 64, row0, &full_bar[slot], policy_kv);
+              if (ATT_HD(a) > 64) tma_load_2d(ring + (size_t)slot * ST_TILE + 8192, a.tmap_v, 64, row0, &full_bar[slot], policy_kv);
             }
           }
           continue;
@@ -533,7 +536,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         if (op.init2_dst) {
           for (long long i = (long long)blockIdx.x * ST_WORKERS + wt; i < op.init2_n; i += (long long)G * ST_WORKERS) op.init2_dst[i] = 0.f;
         }
-        if (op.rope_rows > 0 && (int)blockIdx.x < op.rope_rows && wt < op.att.hd / 2) {
+        if (op.rope_rows > 0 && (int)blockIdx.x < op.rope_rows && wt < ATT_HD(op.att) / 2) {
           const int m = blockIdx.x;
           float sn, cs;
           sincosf((float)s_kvlen[m] * op.att.inv_freq[wt], &sn, &cs);
@@ -612,7 +615,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         const SAtt& a = op.att;
         const unsigned U = att_vtotal(seq, op.M);
         const int Gq = a.kv.q_heads / a.kv.kv_heads, nkv = a.kv.kv_heads;
-        const int hd = a.hd, hh2 = hd >> 1, nks = hd >> 4;                         // head_dim, RoPE half, 16-wide k / d steps
+        const int hd = ATT_HD(a), hh2 = hd >> 1, nks = hd >> 4;                         // head_dim, RoPE half, 16-wide k / d steps
         bf16 (*Qs)[AT2_LD] = reinterpret_cast<bf16 (*)[AT2_LD]>(breg);              // [16][136]: rows 0..7 hi, 8..15 lo of the G query heads
         bf16* knew = reinterpret_cast<bf16*>(breg + 16 * AT2_LD * 2);
         bf16* vnew = knew + HD;
@@ -797,7 +800,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       // SP_COMBINE scratch behind the B operand: [M][NH][G] merge weights w_p / sum_p w_p l_p | group partial sums | merged[M][count][64]
       const int cmb_base = (count * nB * 128 + 1023) & ~1023;
       float* s_w = reinterpret_cast<float*>(breg + cmb_base);
-      const int cmb_kbh = (PRO_IS(SP_COMBINE) ? op.att.hd : 128) >> 6;     // k-blocks per head (head_dim 128: two, 64: one)
+      const int cmb_kbh = (PRO_IS(SP_COMBINE) ? ATT_HD(op.att) : 128) >> 6;     // k-blocks per head (head_dim 128: two, 64: one)
       const int cmb_nh = ((kb_first % cmb_kbh) + count - 1) / cmb_kbh + 1;   // distinct heads among this CTA's k-blocks
       const int cmb_off = cmb_base + ((M * cmb_nh * (int)G * 4 + 15) & ~15);
       const int cmb_part = (M * count * 256 > 2048) ? M * count * 256 : 2048;     // bytes of the group partial sums (npg * out4 float4)
@@ -965,7 +968,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         r.o4 = w0 % out4; r.pg = w0 / out4;
         const int m = r.o4 / (count * 16), q = r.o4 - m * (count * 16), jloc = q >> 4, q4 = q & 15;
         int kb = kb_first + jloc; if (kb >= KB) kb -= KB;
-        const int k = kb * 64 + q4 * 4, h = k / a.hd, d = k - h * a.hd, g = h / cmb_Gq, hh = h - g * cmb_Gq;
+        const int k = kb * 64 + q4 * 4, h = k / ATT_HD(a), d = k - h * ATT_HD(a), g = h / cmb_Gq, hh = h - g * cmb_Gq;
         r.pi = m * cmb_nh + ((kb_first % cmb_kbh) + jloc) / cmb_kbh;
         r.ap = a.part_acc + ((((size_t)m * cmb_nkv + g) * G) * 8 + hh) * HD + d;             // slot stride 8 * 128 floats
         return r;
@@ -1236,6 +1239,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
 #undef PRO_IS
 #undef KIND_IS
 #undef ALPHA_IS
+#undef ATT_HD
 
 
 // ---------------------------------------------------------------------------------------------------------------------------------
