@@ -432,13 +432,16 @@ constexpr unsigned SF_LM = sfeat({SP_NONE, SP_RMSNORM, SP_SWIGLU, SP_COMBINE}, {
 constexpr unsigned SF_CODEC = sfeat({SP_NONE, SP_WINDOW, SP_RMSNORM, SP_GELU}, {SK_GEMV, SK_NOP, SK_MIX}, {SA_ONE, SA_GAMMA});
 constexpr unsigned SF_HD128 = 1u << 30;          // every attention stage has head_dim 128 (compile-time loop bounds)
 constexpr unsigned SF_LM128 = SF_LM | SF_HD128;
-constexpr unsigned SF_ALL = 0xffffffffu & ~SF_HD128;
+constexpr unsigned SF_NB16 = 1u << 29;           // every linear stage has a 16-row activation operand (compile-time nB)
+constexpr unsigned SF_ALL = 0xffffffffu & ~SF_HD128 & ~SF_NB16;
 typedef void (*StreamFn)(SParams);
 static const struct { unsigned feat; StreamFn fn; StreamFn fn_trace; const char* name; } STREAM_VARIANTS[] = {
-  {SF_SAMP, stream_kernel<SF_SAMP, false>, stream_kernel<SF_SAMP, true>, "sampler"},
-  {SF_LM128, stream_kernel<SF_LM128, false>, stream_kernel<SF_LM128, true>, "lm (head_dim 128)"}, {SF_LM, stream_kernel<SF_LM, false>, stream_kernel<SF_LM, true>, "lm"},
-  {SF_CODEC, stream_kernel<SF_CODEC, false>, stream_kernel<SF_CODEC, true>, "codec"}, {SF_ALL, stream_kernel<SF_ALL, false>, stream_kernel<SF_ALL, true>, "all"}};
-constexpr int N_STREAM_VARIANTS = 5;
+#define SVAR(f, name) {f, stream_kernel<f, false>, stream_kernel<f, true>, name}
+  SVAR(SF_SAMP | SF_NB16, "sampler (16-row operand)"), SVAR(SF_SAMP, "sampler"),
+  SVAR(SF_LM128 | SF_NB16, "lm (head_dim 128, 16-row operand)"), SVAR(SF_LM128, "lm (head_dim 128)"), SVAR(SF_LM, "lm"),
+  SVAR(SF_CODEC | SF_NB16, "codec (16-row operand)"), SVAR(SF_CODEC, "codec"), SVAR(SF_ALL, "all")};
+#undef SVAR
+constexpr int N_STREAM_VARIANTS = 8;
 
 static int finish_stream(StreamBuilder& b, vv_ctx::StreamProg* pr) {
   vv_ctx* c = b.c;
@@ -466,15 +469,17 @@ static int finish_stream(StreamBuilder& b, vv_ctx::StreamProg* pr) {
     if (U * (G + 1) >= (1ll << 32)) return fail(VV_ERR_INVALID, "stream: stage [%d x %d] has too many tiles for 32-bit scheduling", o.N, o.K);
   }
   unsigned feat = 0;
-  bool hd128 = true;
+  bool hd128 = true, nb16 = true;
   for (const SOp& o : b.ops) {
+    if (o.kind == SK_GEMV && o.nB != 16) nb16 = false;
     feat |= (1u << o.pro) | (1u << (16 + o.kind)) | (1u << (24 + o.alpha_kind));
     if ((o.kind == SK_ATTN || o.pro == SP_COMBINE || o.rope_rows > 0) && o.att.hd != 128) hd128 = false;
   }
   pr->variant = N_STREAM_VARIANTS - 1;
   if (!getenv("VV_STREAM_GENERIC"))
     for (int v = 0; v < N_STREAM_VARIANTS; ++v)
-      if ((feat & ~STREAM_VARIANTS[v].feat) == 0 && (hd128 || !(STREAM_VARIANTS[v].feat & SF_HD128))) { pr->variant = v; break; }
+      if ((feat & ~STREAM_VARIANTS[v].feat) == 0 && (hd128 || !(STREAM_VARIANTS[v].feat & SF_HD128)) && (nb16 || !(STREAM_VARIANTS[v].feat & SF_NB16)) &&
+          !(getenv("VV_STREAM_NO_NB16") && (STREAM_VARIANTS[v].feat & SF_NB16))) { pr->variant = v; break; }
   if (getenv("VV_VERBOSE")) fprintf(stderr, "[vv] stream program: %zu stages, features %08x -> kernel variant '%s'\n", b.ops.size(), feat, STREAM_VARIANTS[pr->variant].name);
   cudaFuncAttributes fa;
   CK(cudaFuncGetAttributes(&fa, STREAM_VARIANTS[pr->variant].fn));

@@ -305,6 +305,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
 // bit 30: every attention stage of the program has head_dim 128 -> compile-time loop bounds (the run-time-bounded loops of the 64 / 128
 // generalisation cost the LM stack 13 % when they were introduced)
 #define ATT_HD(a) ((((FEAT >> 30) & 1u) != 0u) ? 128 : (a).hd)
+// bit 29: every linear stage of the program has a 16-row activation operand (M <= 8 rows: one prompt per GPU) -> compile-time nB
+#define OP_NB(o) ((((FEAT >> 29) & 1u) != 0u) ? 16 : (o).nB)
   extern __shared__ unsigned char st_raw[];
   __shared__ unsigned long long full_bar[ST_MAX_STAGES], empty_bar[ST_MAX_STAGES];
   __shared__ unsigned long long b_ready, acc_full;
@@ -428,7 +430,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       unsigned u0, u1; int KB;
       st_part(op, u0, u1, KB);
       if (u0 == u1) continue;
-      const int nB = op.nB;
+      const int nB = OP_NB(op);
       // instruction descriptor: D = f32, A = B = bf16, both K-major, N = nB, M = 128
       const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(nB >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
       const int kb_first = (int)(u0 % (unsigned)KB);
@@ -787,7 +789,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       st_part(op, u0, u1, KB);
       ring_advance(u1 - u0);
       if (u0 == u1) { grid_barrier(); side_jobs(); break; }
-      const int M = op.M, K = op.K, N = op.N, nB = op.nB, half = nB >> 1;
+      const int M = op.M, K = op.K, N = op.N, nB = OP_NB(op), half = nB >> 1;
       const int units = (int)(u1 - u0);
       const int count = units < KB ? units : KB;          // k-blocks of activations this CTA needs (contiguous mod KB from kb_first)
       const int rt_first = (int)(u0 / (unsigned)KB), kb_first = (int)(u0 - (unsigned)rt_first * (unsigned)KB);
@@ -1240,6 +1242,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
 #undef KIND_IS
 #undef ALPHA_IS
 #undef ATT_HD
+#undef OP_NB
 
 
 // ---------------------------------------------------------------------------------------------------------------------------------
