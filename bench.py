@@ -40,9 +40,9 @@ AUDIO_S_PER_FRAME = 3200.0 / 24000.0
 TRAFFIC_NOTE = {
     "1.5b": "10.96 GB DRAM (read + write) per frame for 12.98 GB algorithmic at ctx 61440: the four stream_kernel launches move 4.39 (LM stack: "
             "4.40 algorithmic) + 5.02 (30-step sampler: 7.09 algorithmic, the rest of the head's re-reads hit the 126 MB L2) + 0.66 + 0.67 GB "
-            "(codec front / back), every other kernel 0.23 GB (ncu --set full + launch list, profiles/r02_prof_stream_kernel_raw.csv, "
-            "profiles/r02_launches_15b_ctx61440_frame.txt)",
-    "1.5b:lm": "4.387 GB dram read + 0.012 GB written for 4.40 GB algorithmic (ncu --set full, profiles/r02_prof_stream_kernel_raw.csv, launch 0)",
+            "(codec front / back), every other kernel 0.23 GB (ncu --set full + launch list of the final kernels, profiles/r02_prof_stream3_raw.csv, "
+            "profiles/r02_launches_15b_ctx61440_frame_final.txt)",
+    "1.5b:lm": "4.387 GB dram read + 0.012 GB written for 4.40 GB algorithmic (ncu --set full, profiles/r02_prof_stream3_raw.csv, launch 0)",
 }
 
 
