@@ -546,6 +546,49 @@ def test_streaming_variant_vs_oracle():
             m.engine.close()
 
 
+def test_streaming_from_pretrained_on_a_checkpoint_directory(tmp_path):
+    """`VibeVoiceStreamingForConditionalGenerationInference.from_pretrained(dir, torch_dtype=..., device_map="cuda",
+    attn_implementation=...)` as `demo/streaming_inference_from_file.py:244-284` calls it: sharded safetensors with the streaming key names +
+    a config.json carrying `tts_backbone_num_hidden_layers`; the loaded model must generate exactly what the in-memory one does."""
+    import json
+    from safetensors.torch import save_file
+    from oracle import vv_streaming as VS
+    from vibevoice.modular.modeling_vibevoice_streaming_inference import VibeVoiceStreamingForConditionalGenerationInference as M
+    from vibevoice_b200.configuration import preset_config
+    from vibevoice_b200.synth import synth_state_dict
+    cfg = preset_config("tiny")
+    sd = VS.streaming_state_dict(synth_state_dict(cfg, 1234, torch.bfloat16), cfg, 1, eos_bias=-6.0)
+    ck = tmp_path / "VibeVoice-Streaming-synth"
+    ck.mkdir()
+    d = cfg.to_dict()
+    d["model_type"] = "vibevoice_streaming"
+    d["tts_backbone_num_hidden_layers"] = 1
+    d.pop("semantic_tokenizer_config", None)                  # the streaming config has no semantic tokenizer (configuration_vibevoice_streaming.py:46-52)
+    (ck / "config.json").write_text(json.dumps(d))
+    keys = sorted(k for k in sd if not k.startswith("model.semantic"))
+    half = len(keys) // 2
+    for i, part in enumerate((keys[:half], keys[half:])):
+        save_file({k: sd[k].contiguous() for k in part}, str(ck / ("model-%05d-of-00002.safetensors" % (i + 1))))
+    model = M.from_pretrained(str(ck), torch_dtype=torch.bfloat16, device_map="cuda", attn_implementation="flash_attention_2")
+    try:
+        model.eval()
+        model.set_ddpm_inference_steps(num_steps=5)
+        assert model.model.language_model.config._attn_implementation == "flash_attention_2" and model.tts_layers == 1
+        g = torch.Generator().manual_seed(7)
+        prompt = torch.randint(0, 2000, (6,), generator=g)
+        text = torch.randint(0, 2000, (7,), generator=g)
+        torch.manual_seed(0)
+        out = model.generate(input_ids=prompt[None], tts_text_ids=text[None], neg_text_input_id=2047, cfg_scale=1.5, max_new_tokens=12)
+        torch.manual_seed(0)
+        ref = VS.generate_streaming(sd, cfg, 1, prompt, text, 2047, cfg_scale=1.5, num_steps=5, max_new_tokens=12, kv_bf16=True)
+        assert torch.equal(out.sequences, ref.sequences)
+        assert rel_l2(out.speech_outputs[0].cpu(), ref.speech_outputs[0]) < 1e-2
+    finally:
+        model.engine.close()
+    with pytest.raises(Exception):
+        M.from_pretrained(str(ck), device_map="cpu")
+
+
 @pytest.fixture(scope="module")
 def real15():
     """VibeVoice-1.5B layer shapes (H=1536, I=8960, 12/2 heads, full-size head and codec), 2 LM layers, small vocab."""

@@ -103,9 +103,9 @@ VV_DEVINL int xs_pos(int k) {
   return (c << 8) + ((j >> 2) << 7) + (lane << 2) + (j & 3);
 }
 
-VV_DEVINL void epi_store(const GemvP& p, int m, int n, float v) {
-  // n indexes the weight row; bias already added
-  switch (p.epi) {
+VV_DEVINL void epi_store_e(const GemvP& p, int epi, int m, int n, float v) {
+  // n indexes the weight row; bias already added; `epi` may be a compile-time constant at the call site
+  switch (epi) {
     case EPI_RESID: v += p.res[(long long)m * p.ldres + n]; break;
     case EPI_GATED_RESID: v = p.res[(long long)m * p.ldres + n] + p.epi_a[(long long)m * p.epi_lda + n] * v; break;
     case EPI_GAMMA_RESID: v = p.res[(long long)m * p.ldres + n] + p.epi_a[n] * v; break;
@@ -115,6 +115,7 @@ VV_DEVINL void epi_store(const GemvP& p, int m, int n, float v) {
   }
   p.y[(long long)m * p.ldy + n] = v;
 }
+VV_DEVINL void epi_store(const GemvP& p, int m, int n, float v) { epi_store_e(p, p.epi, m, n, v); }
 
 // ---------------------------------------------------------------------------------------------
 // GEMV: y[m, n] = epi( sum_k W[n,k] * pro(x)[m,k] + bias[n] ),  M <= 16 (blocks of MB rows).
@@ -533,6 +534,10 @@ constexpr int MR_A_BYTES = MM_BM * MR_ALD * 4, MR_W_BYTES = MM_BN * MM_LD * 2, M
 constexpr int MR_SMEM = MR_ST * MR_STAGE;
 constexpr int MR_MAXK_NORM = 512;                  // PRO_RMSNORM: the norm weight row is staged in shared memory behind the ring (2 CTAs/SM must still fit)
 constexpr int MR_SMEM_NORM = MR_SMEM + MR_MAXK_NORM * 4;
+// RMS / EPI >= 0: prologue and epilogue kind as compile-time facts (the codec tail launches this kernel 68 times per frame and every
+// launch runs its path once from a cold instruction cache: ncu shows 1.2-2.6 `no_instruction` stalls per issued instruction for the
+// run-time-switched version); -1 = decided at run time.
+template <int RMS, int EPI>
 __global__ void __launch_bounds__(128) gemm_mma_ring_kernel(GemvP p) {
   extern __shared__ __align__(16) unsigned char mr_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -576,7 +581,8 @@ __global__ void __launch_bounds__(128) gemm_mma_ring_kernel(GemvP p) {
   // with the GEMM, so the tile multiplies x * g (g = norm weight, applied while building fragments), every thread accumulates the
   // squares of the raw x values it converts anyway, and the row scale is applied to the accumulator in the epilogue.  No separate
   // normalisation pass, no extra read of x.
-  const bool rms = (p.pro == PRO_RMSNORM);
+  const bool rms = RMS >= 0 ? (RMS != 0) : (p.pro == PRO_RMSNORM);
+  const int epi = EPI >= 0 ? EPI : p.epi;
   float* gk = reinterpret_cast<float*>(mr_smem + MR_SMEM);
   float ss[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
 
@@ -647,11 +653,11 @@ __global__ void __launch_bounds__(128) gemm_mma_ring_kernel(GemvP p) {
         const int n = bn + warp * 16 + nt * 8 + (lane & 3) * 2 + (q & 1);
         if (m < p.M && n < p.N) {
           if (nz == 1) {
-            epi_store(p, m, n, acc[mt][nt][q] * (rms ? ss[mt][q >> 1] : 1.f) + (p.bias ? p.bias[n] : 0.f));
+            epi_store_e(p, epi, m, n, acc[mt][nt][q] * (rms ? ss[mt][q >> 1] : 1.f) + (p.bias ? p.bias[n] : 0.f));
           } else {
             float v = acc[mt][nt][q] + ((kz == 0 && p.bias) ? p.bias[n] : 0.f);
-            if (p.epi == EPI_GAMMA_RESID) v *= p.epi_a[n];
-            else if (p.epi == EPI_GATED_RESID) v *= p.epi_a[(long long)m * p.epi_lda + n];
+            if (epi == EPI_GAMMA_RESID) v *= p.epi_a[n];
+            else if (epi == EPI_GATED_RESID) v *= p.epi_a[(long long)m * p.epi_lda + n];
             atomicAdd(p.y + (long long)m * p.ldy + n, v);
           }
         }

@@ -251,8 +251,19 @@ static int linear(const L& l, GemvP p) {
     }
     const bool ring_rms = p.pro == PRO_RMSNORM && grid.z == 1 && p.K <= MR_MAXK_NORM && p.K % 4 == 0;
     if (l.c->mma_ring && (p.pro == PRO_NONE || ring_rms) && p.epi != EPI_SWIGLU) {
-      CK(cudaFuncSetAttribute(gemm_mma_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MR_SMEM_NORM));
-      CK(launch_k(l, gemm_mma_ring_kernel, dim3(grid), dim3(128), (size_t)(ring_rms ? MR_SMEM_NORM : MR_SMEM), p));
+      // the combinations the codec passes use get their own instantiation (FFN1: folded RMSNorm + GELU; FFN2 / transposed convs: plain or
+      // gamma-residual, split-K or not); anything else runs the run-time-switched one
+      void (*fn)(GemvP) = gemm_mma_ring_kernel<-1, -1>;
+      if (!getenv("VV_RING_GENERIC")) {
+        if (ring_rms && p.epi == EPI_GELU) fn = gemm_mma_ring_kernel<1, EPI_GELU>;
+        else if (ring_rms && p.epi == EPI_NONE) fn = gemm_mma_ring_kernel<1, EPI_NONE>;
+        else if (!ring_rms && p.epi == EPI_GAMMA_RESID) fn = gemm_mma_ring_kernel<0, EPI_GAMMA_RESID>;
+        else if (!ring_rms && p.epi == EPI_NONE) fn = gemm_mma_ring_kernel<0, EPI_NONE>;
+        else if (!ring_rms && p.epi == EPI_GELU) fn = gemm_mma_ring_kernel<0, EPI_GELU>;
+        else if (!ring_rms && p.epi == EPI_RESID) fn = gemm_mma_ring_kernel<0, EPI_RESID>;
+      }
+      CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, MR_SMEM_NORM));
+      CK(launch_k(l, fn, dim3(grid), dim3(128), (size_t)(ring_rms ? MR_SMEM_NORM : MR_SMEM), p));
       return 0;
     }
     CK(launch_k(l, gemm_mma_kernel, dim3(grid), dim3(128), 0, p));

@@ -70,6 +70,48 @@ class VibeVoiceStreamingForConditionalGenerationInference:
     def set_ddpm_inference_steps(self, num_steps=None):
         self.ddpm_inference_steps = num_steps or self.config.diffusion_head_config.ddpm_num_inference_steps
 
+    @classmethod
+    def from_pretrained(cls, path: str, torch_dtype=None, device_map=None, attn_implementation=None, **kw):
+        """HF checkpoint directory (config.json of `VibeVoiceStreamingConfig` + *.safetensors), as
+        `demo/streaming_inference_from_file.py:244-262` calls it.  `torch_dtype` / `attn_implementation` are accepted for drop-in
+        compatibility (storage is bf16, attention is the built-in paged kernel); the split point comes from the config's
+        `tts_backbone_num_hidden_layers` (`configuration_vibevoice_streaming.py:51, 90`)."""
+        import glob
+        import os
+        from safetensors import safe_open
+        cfg = VibeVoiceConfig.from_pretrained(path)
+        dev = 0
+        if isinstance(device_map, str) and device_map.startswith("cuda:"):
+            dev = int(device_map.split(":")[1])
+        elif device_map is not None and device_map not in ("cuda", "auto"):
+            raise N.VVError("vibevoice_b200 runs on CUDA devices only (device_map=%r); there is no CPU path" % (device_map,))
+        m = cls(cfg, tts_backbone_num_hidden_layers=int(getattr(cfg, "tts_backbone_num_hidden_layers", 20)), device=dev,
+                max_diffusion_steps=int(kw.pop("max_diffusion_steps", 64)))
+        files = sorted(glob.glob(os.path.join(path, "*.safetensors")))
+        if not files:
+            raise FileNotFoundError("no *.safetensors under %s" % path)
+
+        def it():
+            for f in files:
+                with safe_open(f, framework="pt", device="cpu") as sf:
+                    for k in sf.keys():
+                        yield k, sf.get_tensor(k)
+        m._attn_implementation = attn_implementation or "paged-split-kv"
+        return m.load_state_dict(it())
+
+    # the calls / attributes the demo touches between loading and generate() (`demo/streaming_inference_from_file.py:279-284`)
+    def eval(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    @property
+    def model(self):
+        from types import SimpleNamespace
+        return SimpleNamespace(language_model=SimpleNamespace(config=SimpleNamespace(
+            _attn_implementation=getattr(self, "_attn_implementation", "paged-split-kv"))))
+
     def _new_engine(self):
         return Engine(self.config, [0, 1], 2, self._device_index, self._max_steps)      # no token constraint here; ids are unused
 
