@@ -239,16 +239,9 @@ VV_DEVINL unsigned att_tiles(const SeqView& q, int m) { return q.row_mode[m] ? (
 // order.  CTAs take contiguous ranges of virtual units, so a CTA that also gets the few pages of a short (CFG-negative) row gets
 // correspondingly fewer pages of the long one (measured before: the CTA owning both short groups arrived 8 us late at every layer's barrier).
 constexpr unsigned ST_ATT_SEGW = 4;
-#ifndef ST_PRE_SO
-#define ST_PRE_SO 0       // 1: swizzled B-operand offsets precomputed ahead of the barrier (sampler +0.4 %, LM +0.5 % slower: off)
-#endif
-#ifndef ST_PF_BREAK
-#define ST_PF_BREAK 0     // 1: epilogue-operand prefetch stops at the last live segment (no gain: off)
-#endif
-#ifndef ST_WIDE
-#define ST_WIDE 0      // 1: 4 activation chunks per thread in one L2 round trip. Measured on one box (tools/ab_run.sh): the LM gains 0.5 %, but the extra
-                       // 1 900 instructions cost the sampler 4.7 % (instruction cache) -> off
-#endif
+// Tried and measured on one box, then removed again (profiles/r02_ab_wide_inflight.txt, r02_ab_gate_prefetch_trace_offsets.txt): four activation
+// chunks per thread in one L2 round trip (LM -0.5 %, sampler +4.7 %: 1 900 more instructions), swizzled B-operand offsets precomputed ahead of the
+// barrier (+0.5 %), epilogue-operand prefetch that stops at the last live segment (no gain).
 VV_DEVINL unsigned att_vtotal(const SeqView& q, int M) {
   unsigned V = 0;
   for (int m = 0; m < M; ++m) { const unsigned nt = att_tiles(q, m); if (nt) V += (nt + ST_ATT_SEGW) * (unsigned)q.kv_heads; }
@@ -806,7 +799,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       const int cmb_nh = ((kb_first % cmb_kbh) + count - 1) / cmb_kbh + 1;   // distinct heads among this CTA's k-blocks
       const int cmb_off = cmb_base + ((M * cmb_nh * (int)G * 4 + 15) & ~15);
       const int cmb_part = (M * count * 256 > 2048) ? M * count * 256 : 2048;     // bytes of the group partial sums (npg * out4 float4)
-      struct ChunkRef { const float* xr; const float* pw; const float* psc; const float* psh; int m, jloc, ch, k, so_hi, so_lo; bool valid, live, fresh; };
+      struct ChunkRef { const float* xr; const float* pw; const float* psc; const float* psh; int m, jloc, ch, k; bool valid, live, fresh; };
       auto chunk_ref = [&](int c) -> ChunkRef {             // coordinates + source address of chunk c: descriptor-only arithmetic
         ChunkRef r;
         r.m = c / (count * 8);
@@ -815,12 +808,6 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         int kb = kb_first + r.jloc; if (kb >= KB) kb -= KB;
         r.k = kb * 64 + r.ch * 8;
         r.valid = c < total;
-        r.so_hi = 0; r.so_lo = 0;
-        if (ST_PRE_SO) {                                      // swizzled B-operand offsets of the hi row m and the lo row half + m
-          const int rl = half + r.m;
-          r.so_hi = r.jloc * (nB * 128) + (r.m >> 3) * 1024 + (r.m & 7) * 128 + ((r.ch ^ (r.m & 7)) << 4);
-          r.so_lo = r.jloc * (nB * 128) + (rl >> 3) * 1024 + (rl & 7) * 128 + ((r.ch ^ (rl & 7)) << 4);
-        }
         r.live = r.valid && r.k < K && !PRO_IS(SP_DPM) && !PRO_IS(SP_COMBINE);
         r.fresh = false;
         r.xr = op.x; r.pw = nullptr; r.psc = nullptr; r.psh = nullptr;
@@ -917,27 +904,16 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
         const uint4 hv = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
         const uint4 lv = make_uint4(pack_bf16(v[0] - h[0], v[1] - h[1]), pack_bf16(v[2] - h[2], v[3] - h[3]),
                                     pack_bf16(v[4] - h[4], v[5] - h[5]), pack_bf16(v[6] - h[6], v[7] - h[7]));
-#if ST_PRE_SO
-        *reinterpret_cast<uint4*>(breg + r.so_hi) = hv;
-        *reinterpret_cast<uint4*>(breg + r.so_lo) = lv;
-#else
         unsigned char* blk = breg + (size_t)jloc * (size_t)(nB * 128);
         const int rl = half + m;
         *reinterpret_cast<uint4*>(blk + (m >> 3) * 1024 + (m & 7) * 128 + ((ch ^ (m & 7)) << 4)) = hv;
         *reinterpret_cast<uint4*>(blk + (rl >> 3) * 1024 + (rl & 7) * 128 + ((ch ^ (rl & 7)) << 4)) = lv;
-#endif
       };
       ChunkRef r0 = chunk_ref(wt), r1 = chunk_ref(wt + ST_WORKERS);
-      // every prologue but AdaLN needs <= 4 float4 per chunk: the upper halves of the two register batches take a third and a fourth chunk,
-      // so stages with up to 512 chunks (the LM's gate/up: 2 rows x 23 k-blocks) still stage their B operand with ONE L2 round trip
-      const bool wide = ST_WIDE && !PRO_IS(SP_ADALN) && total > 2 * ST_WORKERS;
-      ChunkRef r2 = chunk_ref(wide ? wt + 2 * ST_WORKERS : total), r3 = chunk_ref(wide ? wt + 3 * ST_WORKERS : total);
-      if (wide) asm volatile("" : "+l"(r2.xr), "+r"(r2.m), "+r"(r2.k), "+r"(r2.jloc), "+l"(r3.xr), "+r"(r3.m), "+r"(r3.k), "+r"(r3.jloc));
       const int K4 = K >> 2;
       int rot = (int)((blockIdx.x * 67u) % (unsigned)(K4 > 0 ? K4 : 1));     // statistics loads: every CTA starts at a different column
       // materialise the descriptor-only values HERE, ahead of the barrier (the compiler would otherwise sink them to their first use)
       asm volatile("" : "+l"(r0.xr), "+r"(r0.m), "+r"(r0.k), "+r"(r0.jloc), "+l"(r1.xr), "+r"(r1.m), "+r"(r1.k), "+r"(r1.jloc), "+r"(rot));
-      if (ST_PRE_SO) asm volatile("" : "+r"(r0.so_hi), "+r"(r0.so_lo), "+r"(r1.so_hi), "+r"(r1.so_lo));
       if (norm) asm volatile("" : "+l"(r0.pw), "+l"(r0.psc), "+l"(r0.psh), "+l"(r1.pw), "+l"(r1.psc), "+l"(r1.psh));
       // attention merge: the (row, head) a warp merges first and the first accumulator item of every thread, again descriptor-only
       const bool cmb = PRO_IS(SP_COMBINE);
@@ -1066,7 +1042,6 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       float4 in0[8], in1[8];
       chunk_load(r0, in0);                                  // first chunks of this thread: in flight during the statistics
       chunk_load(r1, in1);
-      if (wide) { chunk_load(r2, in0 + 4); chunk_load(r3, in1 + 4); }
       if (tr) P.trace[(size_t)oi * ST_TRACE + 10] = clock64();
       if (norm) {
         // sum of squares of every full row: rows in pairs, <= 16 float4 per thread in flight (K <= 4096), further columns looped
@@ -1137,9 +1112,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
       if (tr) P.trace[(size_t)oi * ST_TRACE + 2] = clock64();
       chunk_store(r0, in0);
       chunk_store(r1, in1);
-      if (wide) { chunk_store(r2, in0 + 4); chunk_store(r3, in1 + 4); }
 #pragma unroll 1
-      for (int c = wt + (wide ? 4 : 2) * ST_WORKERS; c < total; c += 2 * ST_WORKERS) {
+      for (int c = wt + 2 * ST_WORKERS; c < total; c += 2 * ST_WORKERS) {
         r0 = chunk_ref(c); r1 = chunk_ref(c + ST_WORKERS);
         chunk_load(r0, in0);
         chunk_load(r1, in1);
@@ -1165,9 +1139,6 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stream_kernel(SParams P) {
 #pragma unroll
       for (int sg = 0; sg < EPRE; ++sg) {
         const int rt = rt_first + sg;
-#if ST_PF_BREAK
-        if (rt > rt_last) break;
-#endif
         const int n = rt * 128 + wq * 32 + lane;
         const bool live = rt <= rt_last && n < N;
         const bool from0 = (sg > 0) || kb_first == 0;
