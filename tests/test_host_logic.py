@@ -374,3 +374,17 @@ def test_streaming_product_host_logic_against_reference_fixture(golden, monkeypa
         assert (a is None) == (b is None)
         if a is not None:
             assert a.shape == b.shape and float((a.double() - b.double()).norm() / b.double().norm()) < tol
+
+
+def test_streaming_from_pretrained_refuses_non_cuda_devices(tmp_path):
+    """`demo/streaming_inference_from_file.py:259-262` passes device_map="cpu" on CPU hosts: there is no CPU path, and the refusal must come
+    before any weights are touched."""
+    import json
+    from vibevoice.modular.modeling_vibevoice_streaming_inference import VibeVoiceStreamingForConditionalGenerationInference as M
+    from vibevoice_b200 import _native as N
+    from vibevoice_b200.configuration import preset_config
+    d = preset_config("tiny").to_dict()
+    d["tts_backbone_num_hidden_layers"] = 1
+    (tmp_path / "config.json").write_text(json.dumps(d))
+    with pytest.raises(N.VVError):
+        M.from_pretrained(str(tmp_path), device_map="cpu")

@@ -22,6 +22,16 @@
 // atomics.  That is why epilogues are linear (bias, scaling, residual) and the non-linearities (SwiGLU, GELU) live in the NEXT stage's
 // prologue.
 //
+// Attention stages (SK_ATTN) run in the same kernel: K / V pages of the paged cache arrive through the same ring, scores and P V by mma.sync,
+// RoPE / KV append fused, split-KV partials merged in the o-projection's prologue.  Codec stages add a causal-window gather prologue and a
+// distributed mixer stage (SK_MIX).
+//
+// What the round's measurements say about this kernel (profiles/r02_*): DRAM bytes = algorithmic bytes, DRAM ~30 % busy, tensor
+// pipe < 5 % -- it is bound by the chain of ~520 dependent grid-wide stages per frame, and INSIDE a stage by instruction fetch: every stage runs
+// its worker path once, straight-line.  Hence one instantiation per program family (stream_kernel<FEAT, TRACE>), compile-time head_dim / operand
+// height where a program allows it, descriptor fields in registers, descriptor-only arithmetic between barrier arrival and barrier wait, and
+// uniform early exits instead of predicated-off rows.
+//
 // Reference arithmetic: the stages are the same linears as the stand-alone kernels in vv_kernels.cuh (see the anchors there).
 #pragma once
 #include "vv_kernels.cuh"
