@@ -239,59 +239,93 @@ def config_dict(args, cfg, L0, F):
 
 # ------------------------------------------------------------------------------------------------------------------
 def run_extra_config(tag, preset, B, L0, F, args, rank, world, local, dev, peak):
-    """Steady-state loop of another BASELINE configuration (same method as `value`): 1 warm-up + 2 timed steps of F frames."""
+    """Steady-state loop of another BASELINE configuration (same method as `value`): 1 warm-up + 2 timed steps of F frames.
+    Every rank executes the same sequence of collectives whether or not its own part failed (a Python-level failure on one rank must
+    not leave the others waiting in a barrier): failures are agreed on with a MIN all-reduce after each phase."""
     import torch.distributed as dist
     from vibevoice_b200.configuration import preset_config
     from vibevoice_b200.modeling import VibeVoiceForConditionalGenerationInference
     from vibevoice_b200.synth import SynthTokenizer, iter_synth_state_dict_fast
-    cfg = preset_config(preset)
-    tok = SynthTokenizer(cfg.decoder_config.vocab_size)
-    model = VibeVoiceForConditionalGenerationInference(cfg, tok, max_batch=B, device=local, torch_prefill=True)
-    parts = ("lm", "head", "acoustic_decoder", "semantic", "connectors", "lm_head")
-    model.load_state_dict(iter_synth_state_dict_fast(cfg, 4321 + rank, device=dev, parts=parts), tok)
-    model.set_ddpm_inference_steps(args.diffusion_steps)
-    eng = model.engine
-    wb = eng.weight_bytes()
-    eng.kv_init(B * (L0 + F + 8) + B * (F + 8))
-    eng.set_diffusion_steps(args.diffusion_steps)
-    g = torch.Generator().manual_seed(200 + rank)
-    ids = torch.randint(0, 151643, (B, L0), generator=g)
-    ids[:, -1] = tok.speech_start_id
-    embw = model._lm_sd["model.language_model.embed_tokens.weight"]
-    with torch.cuda.stream(eng.stream):
-        for r in range(B):
-            model._prefill.run(eng, r, embw[ids[r].to(dev)])
-    eng.sync()
-    noise_tab = torch.randn(F, B, 64, device=dev)
-    ones = [1] * (2 * B)
 
-    def step():
-        eng.codec_state_reset()
-        for r in range(B):
-            eng.kv_set_len(r, L0); eng.kv_set_len(B + r, 0)
-        eng.embed_tokens([tok.speech_start_id] * (2 * B), eng.embeds)
+    def agree(ok):
+        if world == 1:
+            return ok
+        t = torch.tensor([1.0 if ok else 0.0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item() > 0.5)
+
+    err, model, eng, step, wb, cfg = None, None, None, None, None, None
+    try:
+        cfg = preset_config(preset)
+        tok = SynthTokenizer(cfg.decoder_config.vocab_size)
+        model = VibeVoiceForConditionalGenerationInference(cfg, tok, max_batch=B, device=local, torch_prefill=True)
+        parts = ("lm", "head", "acoustic_decoder", "semantic", "connectors", "lm_head")
+        model.load_state_dict(iter_synth_state_dict_fast(cfg, 4321 + rank, device=dev, parts=parts), tok)
+        model.set_ddpm_inference_steps(args.diffusion_steps)
+        eng = model.engine
+        wb = eng.weight_bytes()
+        eng.kv_init(B * (L0 + F + 8) + B * (F + 8))
+        eng.set_diffusion_steps(args.diffusion_steps)
+        g = torch.Generator().manual_seed(200 + rank)
+        ids = torch.randint(0, 151643, (B, L0), generator=g)
+        ids[:, -1] = tok.speech_start_id
+        embw = model._lm_sd["model.language_model.embed_tokens.weight"]
         with torch.cuda.stream(eng.stream):
-            eng.active.fill_(1)
-        for f in range(F):
-            eng.lm_decode()
-            eng.kv_commit(ones)
+            for r in range(B):
+                model._prefill.run(eng, r, embw[ids[r].to(dev)])
+        eng.sync()
+        noise_tab = torch.randn(F, B, 64, device=dev)
+        ones = [1] * (2 * B)
+
+        def step():
+            eng.codec_state_reset()
+            for r in range(B):
+                eng.kv_set_len(r, L0); eng.kv_set_len(B + r, 0)
+            eng.embed_tokens([tok.speech_start_id] * (2 * B), eng.embeds)
             with torch.cuda.stream(eng.stream):
-                eng.noise.copy_(noise_tab[f])
-            eng.frame_tail(args.cfg_scale)
-    step()
+                eng.active.fill_(1)
+            for f in range(F):
+                eng.lm_decode()
+                eng.kv_commit(ones)
+                with torch.cuda.stream(eng.stream):
+                    eng.noise.copy_(noise_tab[f])
+                eng.frame_tail(args.cfg_scale)
+        step()                                                  # warm-up
+    except Exception as e:
+        err = "%s: %s" % (type(e).__name__, str(e)[:300])
+
+    def cleanup():
+        try:
+            if eng is not None:
+                eng.close()
+        except Exception:
+            pass
+        torch.cuda.empty_cache()
+
+    if not agree(err is None):
+        cleanup()
+        return {"config": tag, "error": err or "failed on another rank"}
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
     K = 2
+    ms = 0.0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(eng.stream)
-    for _ in range(K):
-        step()
-    e1.record(eng.stream)
+    try:
+        e0.record(eng.stream)
+        for _ in range(K):
+            step()
+        e1.record(eng.stream)
+    except Exception as e:
+        err = "%s: %s" % (type(e).__name__, str(e)[:300])
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1)
+    if err is None:
+        ms = e0.elapsed_time(e1)
+    if not agree(err is None):
+        cleanup()
+        return {"config": tag, "error": err or "failed on another rank"}
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -303,9 +337,8 @@ def run_extra_config(tag, preset, B, L0, F, args, rank, world, local, dev, peak)
            "value": round(K * F * B * world * AUDIO_S_PER_FRAME / (ms / 1e3), 3), "unit": "audio-s/s", "n_gpus": world,
            "ms_per_frame": round(ms_frame, 4), "algorithmic_bytes_per_frame": int(abytes),
            "roofline": {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4)}}
-    eng.close()
+    cleanup()
     del model, eng
-    torch.cuda.empty_cache()
     return out
 
 
@@ -513,11 +546,9 @@ def run_b200(args):
         torch.cuda.empty_cache()
         for (tag, b7, L7, F7) in (("7b ctx 30720, 1 prompt/GPU (BASELINE config #3 shape)", 1, 30720, 48),
                                   ("7b 4 prompts/GPU, 256-token prompts (BASELINE config #4 per-GPU share)", 4, 256, 48)):
-            try:
-                extra_configs.append(run_extra_config(tag, "7b", b7, L7, F7, args, rank, world, local, dev, peak))
-                log("extra config done: %s" % tag)
-            except Exception as e:  # a sub-config must never take the headline line down with it
-                extra_configs.append({"config": tag, "error": "%s: %s" % (type(e).__name__, str(e)[:300])})
+            # (a sub-config must never take the headline line down with it: run_extra_config reports its own failures)
+            extra_configs.append(run_extra_config(tag, "7b", b7, L7, F7, args, rank, world, local, dev, peak))
+            log("extra config done: %s" % tag)
 
     if rank == 0:
         line = {"metric": "audio_seconds_per_second", "value": round(value, 3), "unit": "audio-s/s", "n_gpus": world, "steps": K, "warmup": W,
