@@ -388,3 +388,64 @@ def test_streaming_from_pretrained_refuses_non_cuda_devices(tmp_path):
     (tmp_path / "config.json").write_text(json.dumps(d))
     with pytest.raises(N.VVError):
         M.from_pretrained(str(tmp_path), device_map="cpu")
+
+
+@pytest.mark.parametrize("seed", list(range(16)))
+def test_product_negative_stream_bookkeeping_on_random_scripts(seed):
+    """The product's host state machine (fake engine, oracle arithmetic) against `oracle.generate` -- which reproduces the reference's own
+    generate() on the committed fixtures -- on RANDOM forced-token scripts: batches of 2-3 ragged rows, speaker turns, early EOS, and with
+    `refresh_negative=False` also ill-formed orders (diffusion tokens right after <speech_end>), which is where the reference's mask / cache
+    shifting and its guard off-by-one (modeling_vibevoice_inference.py:599-624) decide which negative KV entries stay visible.
+    Sequences and flags exact, audio 1e-5."""
+    import random
+    from fake_engine import make_model
+    from oracle import vv_oracle as O
+    from vibevoice_b200.configuration import preset_config
+    from vibevoice_b200.modeling import ForcedTokenScript
+    from vibevoice_b200.synth import SynthTokenizer, synth_state_dict
+    rnd = random.Random(1000 + seed)
+    cfg = preset_config("tiny")
+    tok = SynthTokenizer(cfg.decoder_config.vocab_size)
+    sd = synth_state_dict(cfg, 1234, torch.float32)
+    s, e, d, x = tok.speech_start_id, tok.speech_end_id, tok.speech_diffusion_id, tok.eos_token_id
+    refresh = seed % 2 == 0
+    B = 2 + seed % 2
+    scripts = []
+    for _ in range(B):
+        row, prev = [], s                                   # the prompt ends with <speech_start>
+        for _ in range(rnd.randint(3, 9)):
+            if refresh:                                     # well-formed: turns are s d+ e, in between only s or EOS
+                nxt = rnd.choice([d, d, d, e]) if prev in (s, d) else s
+            else:                                           # any order the constraint processor could emit
+                nxt = rnd.choice([d, d, e, s])
+            row.append(nxt)
+            prev = nxt
+        row.append(x)
+        scripts.append(row)
+    g = torch.Generator().manual_seed(seed)
+    lens = [rnd.randint(4, 9) for _ in range(B)]
+    L = max(lens)
+    ids = torch.randint(0, 1000, (B, L), generator=g)
+    mask = torch.zeros(B, L, dtype=torch.long)
+    for r, n in enumerate(lens):                           # left-padded ragged prompts, as the processor builds them
+        mask[r, L - n:] = 1
+        ids[r, :L - n] = tok.pad_id
+    ids[:, -1] = s
+    n_new = max(len(r) for r in scripts) + 1
+    model = make_model(cfg, tok, sd, max_batch=B)
+    model.set_ddpm_inference_steps(5)
+    torch.manual_seed(77)
+    out = model.generate(input_ids=ids, attention_mask=mask, tokenizer=tok, cfg_scale=1.3, is_prefill=False, max_new_tokens=n_new,
+                         max_length_times=1e9, show_progress_bar=False, logits_processor=[ForcedTokenScript(scripts)],
+                         refresh_negative=refresh)
+    torch.manual_seed(77)
+    ref = O.generate(sd, cfg, ids, mask, tok, cfg_scale=1.3, num_steps=5, max_new_tokens=n_new, max_length_times=1e9,
+                     forced_tokens=scripts, refresh_negative=refresh)
+    assert torch.equal(out.sequences, ref.sequences), (scripts, out.sequences, ref.sequences)
+    assert torch.equal(out.reach_max_step_sample, ref.reach_max_step_sample)
+    for a, b in zip(out.speech_outputs, ref.speech_outputs):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert a.shape == b.shape, scripts
+            rel = float((a.double() - b.double()).norm() / b.double().norm())
+            assert rel < 1e-5, (rel, scripts, refresh)
