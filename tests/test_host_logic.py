@@ -449,3 +449,40 @@ def test_product_negative_stream_bookkeeping_on_random_scripts(seed):
             assert a.shape == b.shape, scripts
             rel = float((a.double() - b.double()).norm() / b.double().norm())
             assert rel < 1e-5, (rel, scripts, refresh)
+
+
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_streaming_product_host_logic_on_random_inputs(monkeypatch, seed):
+    """The streaming variant's host loop (engine stand-in) against `oracle/vv_streaming.generate_streaming` -- which reproduces the reference's
+    own streaming generate() on the committed fixtures -- for random prompt / text lengths (0..3 text windows, partial last window), EOS
+    classifier biases (early stop, never stop) and step limits (`reach_max_step_sample`)."""
+    import random
+    import fake_engine
+    from oracle import vv_streaming as VS
+    from vibevoice_b200 import streaming as S
+    from vibevoice_b200.configuration import preset_config
+    from vibevoice_b200.synth import synth_state_dict
+    rnd = random.Random(500 + seed)
+    cfg = preset_config("tiny")
+    tts_layers = 1
+    eos_bias = rnd.choice([-6.0, -0.3, 0.5])
+    sd = VS.streaming_state_dict(synth_state_dict(cfg, 1234, torch.float32), cfg, tts_layers, eos_bias=eos_bias)
+    m = S.VibeVoiceStreamingForConditionalGenerationInference(cfg, tts_backbone_num_hidden_layers=tts_layers)
+    monkeypatch.setattr(m, "_new_engine", lambda: fake_engine.FakeEngine(cfg, [0, 1], 2))
+    m.load_state_dict(sd)
+    m.set_ddpm_inference_steps(5)
+    g = torch.Generator().manual_seed(seed)
+    prompt = torch.randint(0, 2000, (rnd.randint(2, 9),), generator=g)
+    text = torch.randint(0, 2000, (rnd.randint(1, 14),), generator=g)
+    max_new = rnd.randint(3, 30)
+    cfg_scale = rnd.choice([1.0, 1.5, 3.0])
+    torch.manual_seed(9)
+    out = m.generate(input_ids=prompt[None], tts_text_ids=text[None], neg_text_input_id=2047, cfg_scale=cfg_scale, max_new_tokens=max_new)
+    torch.manual_seed(9)
+    ref = VS.generate_streaming(sd, cfg, tts_layers, prompt, text, 2047, cfg_scale=cfg_scale, num_steps=5, max_new_tokens=max_new)
+    assert torch.equal(out.sequences, ref.sequences), (out.sequences, ref.sequences)
+    assert torch.equal(out.reach_max_step_sample, ref.reach_max_step_sample)
+    a, b = out.speech_outputs[0], ref.speech_outputs[0]
+    assert (a is None) == (b is None)
+    if a is not None:
+        assert a.shape == b.shape and float((a.double() - b.double()).norm() / b.double().norm()) < 1e-5
