@@ -19,7 +19,7 @@ name = lambda i: byid[i][0]["Kernel Name"]
 stream = [i for i in ids if "stream_kernel" in name(i)]
 if len(stream) < 5:
     sys.exit("need at least two LM-stack launches in the capture (raise -c)")
-lm_variant = re.search(r"stream_kernel<\(unsigned int\)(\d+)", name(stream[0])).group(1)      # the first stream launch of a frame is the LM stack
+lm_variant = re.search(r"stream_kernel<(?:\(unsigned int\))?(\d+)", name(stream[0])).group(1)      # the first stream launch of a frame is the LM stack
 lm = [i for i in stream if lm_variant in name(i)]
 start, end = lm[0], lm[1]
 ONE_TIME = ("tile_pack_kernel", "set_float_kernel")
@@ -31,7 +31,7 @@ with open(prefix + ".csv", "w") as f:
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
 for r in keep:
     k = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "")
-    m2 = re.search(r"stream_kernel<\(unsigned int\)(\d+)", r["Kernel Name"])
+    m2 = re.search(r"stream_kernel<(?:\(unsigned int\))?(\d+)", r["Kernel Name"])
     if m2:
         k = "vv::stream_kernel<%s>" % m2.group(1)
     v = float(r["Metric Value"].replace(",", ""))
